@@ -1,0 +1,135 @@
+/*
+ * wv_b200.h - C ABI of the B200 (sm_100a) WaveVerify embed / detect / locate hot path.
+ *
+ * The reference (pujariaditya/WaveVerify) is pure Python/PyTorch: it has no FFI of its own.
+ * The entry points below are what a binding for THIS path has to expose so that the
+ * reference's Python call sites can be served by hand-written CUDA:
+ *
+ *   wv_generator_forward  <- model/generator.py:360-423  Generator.forward  (+ the add at
+ *                            model/watermarking.py:440)
+ *   wv_generator_encode / wv_generator_decode
+ *                         <- model/generator.py:290-358  Generator.encode / .decode
+ *   wv_detector_forward   <- model/detector.py:366-391   Detector.forward, fused with the bit
+ *                            decode of waveverify/core.py:577-586 + waveverify/utils.py:385-401
+ *                            and the masked variant of scripts/evaluate.py:471-494
+ *   wv_locator_forward    <- model/locator.py:268-299    Locator.forward, fused with the mask
+ *                            threshold of model/watermarking.py:717,797 and the sigmoid of
+ *                            waveverify/core.py:632
+ *   wv_metrics_accumulate <- scripts/evaluate.py:498-505 (BER) and :636-656 (MIoU) as six exact
+ *                            integer counters (the only quantity all-reduced across GPUs)
+ *
+ * Conventions: plain pointers and sizes only, no torch types.  Every function returns 0 on
+ * success or a negative code; wv_last_error() gives the message (thread local).  All data
+ * pointers passed to *_forward are DEVICE pointers owned by the caller; nullable outputs are
+ * skipped.  Work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit sync.
+ * A wv_net owns its weights, TMA descriptors and workspace; it is bound to one device and is
+ * not safe for concurrent use from several threads.  There is no CPU fallback.
+ */
+#ifndef WV_B200_H
+#define WV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WV_KIND_GENERATOR 0
+#define WV_KIND_DETECTOR 1
+#define WV_KIND_LOCATOR 2
+
+#define WV_OK 0
+#define WV_ERR_INVALID -1
+#define WV_ERR_CUDA -2
+#define WV_ERR_MISSING_WEIGHT -3
+#define WV_ERR_UNSUPPORTED -4
+
+typedef struct wv_net wv_net;
+
+/* Topology: the supported subset of the reference constructor kwargs (conf/base.yml:5-112). */
+typedef struct wv_net_config {
+  int kind;            /* WV_KIND_* */
+  int sample_rate;
+  int dimension;       /* latent channels */
+  int channels_enc;    /* n_filters of the encoder */
+  int channels_dec;    /* n_filters of the decoder (generator only) */
+  int n_fft_base;
+  int n_residual_enc;
+  int n_residual_dec;
+  int n_strides;
+  int strides[8];      /* as given to the reference (the encoder walks them reversed) */
+  float res_scale_enc;
+  float res_scale_dec;
+  int nbits;           /* detector: 16, locator: 1 */
+  int output_dim;      /* head hidden width (32) */
+  int msg_dimension;
+  int embedding_dim;
+  int embedding_layers;
+  int freq_bands;
+} wv_net_config;
+
+/* One folded fp32 host tensor, keyed by the reference state_dict name with the weight-norm /
+ * weight-standardisation parametrisation collapsed to `<prefix>.weight`. */
+typedef struct wv_tensor {
+  const char* name;
+  const float* data;   /* host pointer, contiguous */
+  int ndim;
+  int64_t shape[4];
+} wv_tensor;
+
+int wv_version(void);
+const char* wv_last_error(void);
+
+int wv_net_create(const wv_net_config* cfg, const wv_tensor* tensors, int n_tensors, int device,
+                  wv_net** out);
+int wv_net_destroy(wv_net* net);
+/* Build (or fetch) the launch plan for [B, 1, T] inputs and size the workspace. */
+int wv_net_reserve(wv_net* net, int B, int T);
+size_t wv_net_workspace_bytes(const wv_net* net);
+/* Number of kernel launches one forward at the reserved shape enqueues. */
+int wv_net_launches(const wv_net* net, int B, int T);
+/* Max clips processed per internal sub-batch (0 = whole batch). */
+int wv_net_set_chunk(wv_net* net, int max_clip_samples);
+
+/* x [B,T] fp32, msg [B,msg_dimension] fp32 (0/1).  wm_out [B,T] = watermark residual,
+ * y_out [B,T] = x + wm, latent_out [B,dimension,ceil(T/hop)] fp32.  Any output may be NULL. */
+int wv_generator_forward(wv_net* net, const float* x, const float* msg, int B, int T,
+                         float* wm_out, float* y_out, float* latent_out, void* stream);
+int wv_generator_encode(wv_net* net, const float* x, const float* msg, int B, int T,
+                        float* latent_out, void* stream);
+/* z [B,dimension,F] fp32 -> wav_out [B, F*hop] fp32 */
+int wv_generator_decode(wv_net* net, const float* z, int B, int F, float* wav_out, void* stream);
+
+/* y [B,T] fp32.  logits [B,nbits,T] fp32 raw; bits [B,nbits] u8 = (avg >= 0.5);
+ * avg [B,nbits] fp32 = (masked) time-mean of sigmoid(logit); conf [B] = mean over bits;
+ * valid [B,nbits] u8 = bit has >=1 unmasked sample; presence [B,T] u8 mask or NULL. */
+int wv_detector_forward(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* bits,
+                        float* avg, float* conf, uint8_t* valid, const uint8_t* presence,
+                        void* stream);
+/* y [B,T] fp32.  logits [B,T] fp32 raw, mask [B,T] u8 = (logit > 0.5), probs = sigmoid(logit). */
+int wv_locator_forward(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* mask,
+                       float* probs, void* stream);
+
+/* counters[6] (device int64): += {bit_errors, valid_bits, I_fg, U_fg, I_bg, U_bg}. */
+int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8_t* msg_bits,
+                          int B, int nbits, const uint8_t* pred_mask, const uint8_t* gt_mask,
+                          long long n_mask, long long* counters, void* stream);
+
+/* ---- single-kernel entry points (unit tests / micro-benchmarks; device pointers) -------- */
+/* out = epilogue(A[M,K] * W[N,K]^T): bf16 in, fp32 accumulate on tcgen05; see DESIGN.md. */
+int wv_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
+               const float* bias, const void* residual, void* out_raw, void* out_act,
+               float act_scale, int a_is_fp16, void* stream);
+int wv_op_dw5(const void* in, const float* w5c, const float* bias, const void* residual,
+              void* out_raw, void* out_act, float act_scale, int B, int T, int C, void* stream);
+int wv_op_down(const void* in, const float* wkc, const float* bias, const float* film,
+               int film_stride, int bands, void* out_raw, void* out_act, float act_scale, int B,
+               int Tin, int C, int r, void* stream);
+int wv_op_up(const void* in, const float* wkc, void* out, int B, int Tin, int C, int r,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WV_B200_H */

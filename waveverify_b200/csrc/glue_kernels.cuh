@@ -1,0 +1,459 @@
+// Memory-bound kernels around the GEMMs.  Activations are channels-last bf16 [B, T, C]; every
+// thread owns 8 consecutive channels (one 128-bit vector) so a warp reads/writes whole rows
+// coalesced.  Depthwise weights are stored tap-major fp32 [k][C] for the same reason.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace wv {
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  F8 r;
+  unpack_bf16x2(u.x, r.v[0], r.v[1]);
+  unpack_bf16x2(u.y, r.v[2], r.v[3]);
+  unpack_bf16x2(u.z, r.v[4], r.v[5]);
+  unpack_bf16x2(u.w, r.v[6], r.v[7]);
+  return r;
+}
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const F8& r) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
+                 pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7]));
+}
+__device__ __forceinline__ F8 ld_f32x8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  F8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Causal depthwise conv k=5 (SConv1d groups=C, modules/conv.py:715-763; left pad 4 zeros):
+//   v[t,c] = bias[c] + sum_j w[j][c] * in[t-4+j, c]  (+ residual[t,c])
+//   out_raw = v ; out_act = ELU(v * act_scale)            (each optional)
+// The resblock tail scale RS*res_scale_param (modules/seanet.py:271-277) is folded into w/bias.
+constexpr int DW_TT = 8;  // consecutive time steps per thread (sliding window in registers)
+
+__global__ void __launch_bounds__(256)
+dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+           const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+           __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
+           float act_scale, int B, int T, int C) {
+  const int C8 = C >> 3;
+  const int runs = (T + DW_TT - 1) / DW_TT;
+  const long long total = static_cast<long long>(B) * runs * C8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % C8);
+    const long long rr = idx / C8;
+    const int run = static_cast<int>(rr % runs);
+    const int b = static_cast<int>(rr / runs);
+    const int c = cg * 8;
+    const int t0 = run * DW_TT;
+    F8 wt[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) wt[j] = ld_f32x8(w + j * C + c);
+    F8 bs;
+    if (bias != nullptr) bs = ld_f32x8(bias + c);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bs.v[i] = 0.f;
+    }
+    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * T) * C + c;
+    F8 win[5];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 - 4 + j;
+      if (t >= 0) win[j + 1] = ld_bf16x8(ip + static_cast<long long>(t) * C);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) win[j + 1].v[i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < DW_TT; ++s) {
+      const int t = t0 + s;
+      if (t >= T) break;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) win[j] = win[j + 1];
+      win[4] = ld_bf16x8(ip + static_cast<long long>(t) * C);
+      F8 o = bs;
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = fmaf(wt[j].v[i], win[j].v[i], o.v[i]);
+      const long long off = (static_cast<long long>(b) * T + t) * C + c;
+      if (residual != nullptr) {
+        const F8 rs = ld_bf16x8(residual + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] += rs.v[i];
+      }
+      if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+      if (out_act != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = elu1(o.v[i] * act_scale);
+        st_bf16x8(out_act + off, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Causal strided depthwise down-conv k=2r, s=r (modules/seanet.py:759-770; left pad r zeros,
+// right zero padding up to a whole window, modules/conv.py:160-203) + FiLM (seanet.py:928-966):
+//   v[i,c] = bias[c] + sum_{j<2r} w[j][c] * in[i*r - r + j, c];  v = v*gamma[b,band] + beta
+__global__ void __launch_bounds__(256)
+down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+            const float* __restrict__ bias, const float* __restrict__ film, int film_stride,
+            int bands, __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
+            float act_scale, int B, int Tin, int Tout, int C, int r) {
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(B) * Tout * C8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % C8);
+    const long long rr = idx / C8;
+    const int i = static_cast<int>(rr % Tout);
+    const int b = static_cast<int>(rr / Tout);
+    const int c = cg * 8;
+    F8 o;
+    if (bias != nullptr) o = ld_f32x8(bias + c);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+    }
+    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * Tin) * C + c;
+    const int tb = i * r - r;
+    for (int j = 0; j < 2 * r; ++j) {
+      const int t = tb + j;
+      if (t < 0 || t >= Tin) continue;
+      const F8 x = ld_bf16x8(ip + static_cast<long long>(t) * C);
+      const F8 wj = ld_f32x8(w + j * C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wj.v[k], x.v[k], o.v[k]);
+    }
+    if (film != nullptr) {
+      const int band = c / (C / bands);
+      const float gm = __ldg(film + static_cast<long long>(b) * film_stride + band * 2);
+      const float bt = __ldg(film + static_cast<long long>(b) * film_stride + band * 2 + 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(o.v[k], gm, bt);
+    }
+    const long long off = (static_cast<long long>(b) * Tout + i) * C + c;
+    if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+    if (out_act != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = elu1(o.v[k] * act_scale);
+      st_bf16x8(out_act + off, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Causal depthwise transposed conv k=2r, s=r, right-trim r (modules/conv.py:838-874):
+//   out[i*r + j, c] = a[i,c]*w[j][c] + a[i-1,c]*w[j+r][c],  0 <= j < r,  a[-1] = 0
+__global__ void __launch_bounds__(256)
+up_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+          __nv_bfloat16* __restrict__ out, int B, int Tin, int C, int r) {
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(B) * Tin * C8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % C8);
+    const long long rr = idx / C8;
+    const int i = static_cast<int>(rr % Tin);
+    const int b = static_cast<int>(rr / Tin);
+    const int c = cg * 8;
+    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * Tin + i) * C + c;
+    const F8 a0 = ld_bf16x8(ip);
+    F8 a1;
+    if (i > 0) a1 = ld_bf16x8(ip - C);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a1.v[k] = 0.f;
+    }
+    __nv_bfloat16* op = out + (static_cast<long long>(b) * Tin * r + static_cast<long long>(i) * r) * C + c;
+    for (int j = 0; j < r; ++j) {
+      const F8 w0 = ld_f32x8(w + j * C + c);
+      const F8 w1 = ld_f32x8(w + (j + r) * C + c);
+      F8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(a0.v[k], w0.v[k], a1.v[k] * w1.v[k]);
+      st_bf16x8(op + static_cast<long long>(j) * C, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv_pre: 1 -> C, k=5 causal, 1/wav_std folded into w (modules/seanet.py:657-664):
+//   v[t,c] = bias[c] + sum_j w[j][c] * x[t-4+j];  out_raw = v, out_act = ELU(v*act_scale)
+__global__ void __launch_bounds__(256)
+conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_raw,
+                __nv_bfloat16* __restrict__ out_act, float act_scale, int B, int T, int C) {
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(B) * T * C8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % C8);
+    const long long rr = idx / C8;
+    const int t = static_cast<int>(rr % T);
+    const int b = static_cast<int>(rr / T);
+    const int c = cg * 8;
+    F8 o = ld_f32x8(bias + c);
+    const float* xp = x + static_cast<long long>(b) * T;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int tt = t - 4 + j;
+      const float xv = tt >= 0 ? __ldg(xp + tt) : 0.f;
+      const F8 wj = ld_f32x8(w + j * C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wj.v[k], xv, o.v[k]);
+    }
+    const long long off = (static_cast<long long>(b) * T + t) * C + c;
+    if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+    if (out_act != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = elu1(o.v[k] * act_scale);
+      st_bf16x8(out_act + off, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Decoder tail (modules/seanet.py:1177-1202) fused with the trim (model/generator.py:410) and the
+// watermark add (model/watermarking.py:440):  in = ELU'd activations [B, Tp, C] (Tp >= T)
+//   s[t] = b + sum_j sum_c w[j][c] * in[t-4+j, c];  wm = tanh(s)   (wav_std folded into w, b)
+//   wm_out[b,t] = wm ; y_out[b,t] = x[b,t] + wm        for t < T
+// One block per 128-step time tile; the tile (+4 halo rows) is staged in shared memory with a
+// padded row pitch so that the 16-byte reads of consecutive rows hit distinct bank groups.
+constexpr int CL_TILE = 128;
+__global__ void __launch_bounds__(CL_TILE)
+conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, float bias,
+                 const float* __restrict__ x, float* __restrict__ wm_out,
+                 float* __restrict__ y_out, int B, int Tp, int T, int C) {
+  extern __shared__ uint8_t cl_smem[];
+  const int pitch = C * 2 + 16;  // bytes
+  float* ws = reinterpret_cast<float*>(cl_smem);                        // [5][C]
+  uint8_t* tile = cl_smem + ((5 * C * 4 + 15) & ~15);                    // [(CL_TILE+4)][pitch]
+  const int tiles = (T + CL_TILE - 1) / CL_TILE;
+  const int b = blockIdx.x / tiles;
+  const int t0 = (blockIdx.x % tiles) * CL_TILE;
+  for (int i = threadIdx.x; i < 5 * C; i += blockDim.x) ws[i] = w[i];
+  const int C8 = C >> 3;
+  for (int i = threadIdx.x; i < (CL_TILE + 4) * C8; i += blockDim.x) {
+    const int row = i / C8, cg = i % C8;
+    const int t = t0 - 4 + row;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (t >= 0 && t < Tp)
+      u = __ldg(reinterpret_cast<const uint4*>(in + (static_cast<long long>(b) * Tp + t) * C) + cg);
+    *reinterpret_cast<uint4*>(tile + row * pitch + cg * 16) = u;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= T) return;
+  float acc = bias;
+  for (int j = 0; j < 5; ++j) {
+    const uint8_t* rp = tile + (threadIdx.x + j) * pitch;
+    for (int cg = 0; cg < C8; ++cg) {
+      const uint4 u = *reinterpret_cast<const uint4*>(rp + cg * 16);
+      float a[8];
+      unpack_bf16x2(u.x, a[0], a[1]);
+      unpack_bf16x2(u.y, a[2], a[3]);
+      unpack_bf16x2(u.z, a[4], a[5]);
+      unpack_bf16x2(u.w, a[6], a[7]);
+      const float* wp = ws + j * C + cg * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(a[k], wp[k], acc);
+    }
+  }
+  const float wm = tanhf(acc);
+  const long long o = static_cast<long long>(b) * T + t;
+  if (wm_out != nullptr) wm_out[o] = wm;
+  if (y_out != nullptr) y_out[o] = __ldg(x + o) + wm;
+}
+
+// ---------------------------------------------------------------------------------------
+// Waveform staging for the conv-as-DFT STFTs (modules/conv.py:1036-1068): fp16 copy of x*scale
+// per clip with `lead` leading zeros (the causal n_fft-1 padding of the largest scale) and zero
+// tail up to the row pitch.
+__global__ void __launch_bounds__(256)
+wav_stage_kernel(const float* __restrict__ x, __half* __restrict__ out, float scale, int B, int T,
+                 int lead, int pitch) {
+  const long long total = static_cast<long long>(B) * pitch;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % pitch);
+    const int b = static_cast<int>(idx / pitch);
+    const int t = p - lead;
+    const float v = (t >= 0 && t < T) ? __ldg(x + static_cast<long long>(b) * T + t) * scale : 0.f;
+    out[idx] = __float2half_rn(v);
+  }
+}
+
+// Frame matrix for hops that TMA cannot stride (hop*2 B not a multiple of 16):
+//   frames[b*F + f, n] = wav16[b, base + f*hop + n],  n < n_fft
+__global__ void __launch_bounds__(256)
+frames_kernel(const __half* __restrict__ wav16, __half* __restrict__ frames, int B, int F, int hop,
+              int n_fft, int base, int pitch) {
+  const int N8 = n_fft >> 3;
+  const long long total = static_cast<long long>(B) * F * N8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n8 = static_cast<int>(idx % N8);
+    const long long rr = idx / N8;
+    const int f = static_cast<int>(rr % F);
+    const int b = static_cast<int>(rr / F);
+    const __half* sp = wav16 + static_cast<long long>(b) * pitch + base + f * hop + n8 * 8;
+    __half h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = sp[k];
+    *reinterpret_cast<uint4*>(frames + (rr * n_fft) + n8 * 8) = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Message MLP + FiLM scalars (modules/seanet.py:830-839, 518-550): one block of E threads per
+// clip.  e = ReLU(L3 ReLU(L2 (L1 m + b1) + b2) + b3);  film[b, s, band, {gamma,beta}].
+struct FilmArgs {
+  const float* w[4];   // L1 [E,msg], then up to 3 [E,E]
+  const float* b[4];
+  int n_hidden;        // number of (Linear, ReLU) pairs after L1
+  const float* gw;     // [S*bands, E] gamma weights
+  const float* gb;     // [S*bands]
+  const float* bw;     // [S*bands, E] beta weights
+  const float* bb;     // [S*bands]
+  int msg_dim, E, n_film;
+};
+__global__ void film_kernel(const float* __restrict__ msg, float* __restrict__ film, FilmArgs a) {
+  extern __shared__ float fs[];
+  float* e0 = fs;
+  float* e1 = fs + a.E;
+  const int b = blockIdx.x, i = threadIdx.x;
+  if (i < a.E) {
+    float s = a.b[0][i];
+    for (int k = 0; k < a.msg_dim; ++k) s = fmaf(a.w[0][i * a.msg_dim + k], msg[b * a.msg_dim + k], s);
+    e0[i] = s;
+  }
+  __syncthreads();
+  for (int l = 1; l <= a.n_hidden; ++l) {
+    if (i < a.E) {
+      float s = a.b[l][i];
+      for (int k = 0; k < a.E; ++k) s = fmaf(a.w[l][i * a.E + k], e0[k], s);
+      e1[i] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    float* t = e0; e0 = e1; e1 = t;
+  }
+  for (int f = i; f < a.n_film * 2; f += blockDim.x) {
+    const int q = f >> 1;
+    const float* wv = (f & 1) ? a.bw + q * a.E : a.gw + q * a.E;
+    float s = (f & 1) ? a.bb[q] : a.gb[q];
+    for (int k = 0; k < a.E; ++k) s = fmaf(wv[k], e0[k], s);
+    film[static_cast<long long>(b) * a.n_film * 2 + f] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Bit decode finish (waveverify/core.py:577-586, waveverify/utils.py:385-401, masked variant
+// scripts/evaluate.py:471-494): one warp per (clip, bit) sums the per-frame partial sigmoid sums
+// in a fixed order (deterministic), divides by T (or mask count + 1e-8) and thresholds >= 0.5.
+__global__ void bits_finish_kernel(const float* __restrict__ partial, int F, int tiles_n,
+                                   int tiles_per_bit, const uint8_t* __restrict__ presence, int T,
+                                   int nbits, uint8_t* __restrict__ bits, float* __restrict__ avg,
+                                   uint8_t* __restrict__ valid) {
+  const int b = blockIdx.x, o = blockIdx.y, lane = threadIdx.x;
+  float s = 0.f;
+  const int n = F * tiles_per_bit;
+  for (int i = lane; i < n; i += 32) {
+    const int f = i / tiles_per_bit, tl = i % tiles_per_bit;
+    s += partial[(static_cast<long long>(b) * F + f) * tiles_n + o * tiles_per_bit + tl];
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  float cnt = static_cast<float>(T);
+  bool ok = true;
+  if (presence != nullptr) {
+    int c = 0;
+    for (int t = lane; t < T; t += 32) c += presence[static_cast<long long>(b) * T + t] ? 1 : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    ok = c > 0;
+    cnt = static_cast<float>(c) + 1e-8f;
+  }
+  if (lane == 0) {
+    const float a = s / cnt;
+    if (avg) avg[b * nbits + o] = a;
+    if (bits) bits[b * nbits + o] = a >= 0.5f ? 1 : 0;
+    if (valid) valid[b * nbits + o] = ok ? 1 : 0;
+  }
+}
+__global__ void conf_kernel(const float* __restrict__ avg, float* __restrict__ conf, int B,
+                            int nbits) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int o = 0; o < nbits; ++o) s += avg[b * nbits + o];
+  conf[b] = s / nbits;
+}
+
+// ---------------------------------------------------------------------------------------
+// BER / MIoU counters (scripts/evaluate.py:498-505, 636-656): exact int64 sums, one atomic per
+// block per counter.  counters += {bit_errors, valid_bits, I_fg, U_fg, I_bg, U_bg}.
+__global__ void __launch_bounds__(256)
+metrics_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ valid,
+               const uint8_t* __restrict__ msg, long long n_bits,
+               const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt, long long n_mask,
+               unsigned long long* __restrict__ counters) {
+  unsigned int c[6] = {0, 0, 0, 0, 0, 0};
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long start = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (bits != nullptr)
+    for (long long i = start; i < n_bits; i += stride) {
+      const bool v = valid ? valid[i] != 0 : true;
+      c[0] += (v && ((bits[i] != 0) != (msg[i] != 0))) ? 1 : 0;
+      c[1] += v ? 1 : 0;
+    }
+  if (pred != nullptr)
+    for (long long i = start; i < n_mask; i += stride) {
+      const bool p = pred[i] != 0, q = gt[i] != 0;
+      c[2] += (p && q) ? 1 : 0;
+      c[3] += (p || q) ? 1 : 0;
+      c[4] += (!p && !q) ? 1 : 0;
+      c[5] += (!p || !q) ? 1 : 0;
+    }
+  __shared__ unsigned int sh[6];
+  if (threadIdx.x < 6) sh[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    unsigned int v = c[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 6 && sh[threadIdx.x])
+    atomicAdd(&counters[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x]));
+}
+
+// fp32 [B, C, F] -> bf16 [B, F, C] (Generator.decode entry, model/generator.py:334)
+__global__ void latent_in_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out,
+                                 int B, int C, int F) {
+  const long long total = static_cast<long long>(B) * F * C;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const long long rr = idx / C;
+    const int f = static_cast<int>(rr % F);
+    const int b = static_cast<int>(rr / F);
+    out[idx] = __float2bfloat16_rn(z[(static_cast<long long>(b) * C + c) * F + f]);
+  }
+}
+
+}  // namespace wv

@@ -1,0 +1,1282 @@
+// Host side of the C ABI (include/wv_b200.h): weight folding/packing, TMA descriptors, the
+// per-(B,T) launch plan with an arena-planned workspace, and the forward entry points.
+// sm_100a only; every compute step is a kernel from gemm_sm100.cuh / glue_kernels.cuh.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/wv_b200.h"
+#include "gemm_sm100.cuh"
+#include "glue_kernels.cuh"
+
+namespace {
+
+using namespace wv;
+typedef __nv_bfloat16 bf16;
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+struct WvError {
+  int code;
+  std::string msg;
+};
+#define WV_THROW(code, ...)                           \
+  do {                                                \
+    char _b[512];                                     \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);            \
+    throw WvError{code, std::string(_b)};             \
+  } while (0)
+#define CK(expr)                                                                      \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      WV_THROW(WV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+               __LINE__);                                                             \
+  } while (0)
+
+constexpr float WAV_STD = 0.1122080159f;                                   // seanet.py:631
+const float SPEC_MEANS[5] = {-4.554f, -4.315f, -4.021f, -3.726f, -3.477f};  // seanet.py:632
+const float SPEC_STDS[5] = {2.830f, 2.837f, 2.817f, 2.796f, 2.871f};        // seanet.py:633
+constexpr float WAV_FP16_SCALE = 64.f;  // keeps quiet audio out of fp16 subnormals (exact 2^6)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !p)
+    WV_THROW(WV_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+// 16-bit tensor map over (k, row, clip): element strides in ELEMENTS for row / clip.
+CUtensorMap make_tmap(const void* base, int rank, uint64_t dim_k, uint64_t dim_row, uint64_t dim_clip,
+                      uint64_t row_stride, uint64_t clip_stride, int box_k, int box_row, bool fp16) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {dim_k, dim_row, dim_clip};
+  cuuint64_t strides[2] = {row_stride * 2, clip_stride * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_row), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (rank == 3 && (strides[1] & 15)))
+    WV_THROW(WV_ERR_INVALID, "TMA alignment violated (base %p, strides %llu %llu)", base,
+             (unsigned long long)strides[0], (unsigned long long)strides[1]);
+  CUresult r = get_encode_fn()(
+      &m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) WV_THROW(WV_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return m;
+}
+
+int pick_block_n(int N, int must_divide = 0) {
+  static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
+  for (int c : cands)
+    if (N % c == 0 && (must_divide == 0 || must_divide % c == 0)) return c;
+  WV_THROW(WV_ERR_UNSUPPORTED, "no tile width for N=%d", N);
+}
+
+int g_num_sms = 0;
+void init_device_once() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    WV_THROW(WV_ERR_UNSUPPORTED, "this library targets sm_100a (B200); device is sm_%d%d",
+             prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  done = true;
+}
+
+// ------------------------------------------------------------------------------------------
+// weights
+struct HostTensor {
+  const float* data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct DevMem {
+  std::vector<void*> ptrs;
+  ~DevMem() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    ptrs.push_back(p);
+    return p;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& h) {
+    T* d = static_cast<T*>(alloc(h.size() * sizeof(T)));
+    CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+};
+
+struct GemmW {          // B operand of a GEMM: 16-bit [N, ldw] K-major, zero padded
+  void* w = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0, ldw = 0, block_n = 0;
+  bool fp16 = false;
+  CUtensorMap tm;
+};
+struct DwW {            // depthwise taps fp32 [k][C]
+  float* w = nullptr;
+  float* bias = nullptr;
+  int k = 0, C = 0;
+};
+struct ResW {
+  GemmW pw1, pw2;
+  DwW dw1, dw2;          // dw2 carries RS * res_scale_param
+  float pre_scale;
+};
+struct SpecW {
+  GemmW dft;             // fp16 [n_fft, n_fft] (re,im) interleaved rows
+  GemmW layer;           // bf16 [C, n_fft/2+1] * RS * scale_param
+  int n_fft, hop;
+  float mean, stdv;
+};
+struct EncStageW {
+  std::vector<ResW> res;
+  SpecW spec;
+  GemmW down_pw;
+  DwW down_dw;
+  int r, C;
+};
+struct EncoderW {
+  DwW conv_pre;          // [5][C0], 1/wav_std folded
+  std::vector<EncStageW> stages;
+  SpecW spec_post;
+  DwW post_dw;
+  GemmW post_pw;
+  int C0, C_last, dim, hop, nfft_max;
+  bool has_film = false;
+  FilmArgs film;
+  int n_film = 0, bands = 0;
+};
+struct DecStageW {
+  DwW up;                // [2r][C]
+  GemmW halve;           // [C/2, C] + bias
+  std::vector<ResW> res;
+  int r, C;
+};
+struct DecoderW {
+  GemmW pw0;
+  DwW dw0;
+  std::vector<DecStageW> stages;
+  float* last_w = nullptr;   // [5][C]
+  float last_b = 0.f;
+  int C_last;
+  float stage_scale;
+};
+struct HeadW {
+  GemmW w;               // [n_out*hop, dim] pre-multiplied, bias = combined [n_out]
+  int n_out, hop;
+};
+
+struct Weights {
+  std::map<std::string, HostTensor> host;
+  DevMem dev;
+  const HostTensor& get(const std::string& name) const {
+    auto it = host.find(name);
+    if (it == host.end()) WV_THROW(WV_ERR_MISSING_WEIGHT, "missing tensor '%s'", name.c_str());
+    return it->second;
+  }
+  const HostTensor* find(const std::string& name) const {
+    auto it = host.find(name);
+    return it == host.end() ? nullptr : &it->second;
+  }
+  float scalar_or(const std::string& name, float dflt) const {
+    auto* t = find(name);
+    return t ? t->data[0] : dflt;
+  }
+};
+
+uint16_t f2bf(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+uint16_t f2h(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+
+// rows[N][K] fp32 (already scaled) -> device 16-bit [N, ldw] + tensor map
+GemmW make_gemm_w(Weights& W, const std::vector<float>& rows, int N, int K, bool fp16, int block_n,
+                  const float* bias, int n_bias) {
+  GemmW g;
+  g.N = N; g.K = K; g.fp16 = fp16;
+  g.ldw = static_cast<int>(round_up(K, 8));
+  g.block_n = block_n;
+  std::vector<uint16_t> h(static_cast<size_t>(N) * g.ldw, 0);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k)
+      h[static_cast<size_t>(n) * g.ldw + k] =
+          fp16 ? f2h(rows[static_cast<size_t>(n) * K + k]) : f2bf(rows[static_cast<size_t>(n) * K + k]);
+  g.w = W.dev.upload(h);
+  if (bias) g.bias = W.dev.upload(std::vector<float>(bias, bias + n_bias));
+  g.tm = make_tmap(g.w, 2, K, N, 1, g.ldw, 0, BK, block_n, fp16);
+  return g;
+}
+
+GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias) {
+  const HostTensor& t = W.get(p + ".weight");
+  if (t.shape.size() != 3 || t.shape[2] != 1)
+    WV_THROW(WV_ERR_INVALID, "'%s.weight' is not a 1x1 conv", p.c_str());
+  const int N = static_cast<int>(t.shape[0]), K = static_cast<int>(t.shape[1]);
+  std::vector<float> rows(t.data, t.data + static_cast<size_t>(N) * K);
+  for (auto& v : rows) v *= scale;
+  const HostTensor* b = with_bias ? W.find(p + ".bias") : nullptr;
+  std::vector<float> bb;
+  if (b) {
+    bb.assign(b->data, b->data + N);
+    for (auto& v : bb) v *= scale;
+  }
+  return make_gemm_w(W, rows, N, K, false, pick_block_n(N), b ? bb.data() : nullptr, N);
+}
+
+// depthwise [C,1,k] -> [k][C]; transposed conv weights have the same memory shape
+DwW depthwise(Weights& W, const std::string& p, float scale, bool with_bias) {
+  const HostTensor& t = W.get(p + ".weight");
+  if (t.shape.size() != 3 || t.shape[1] != 1)
+    WV_THROW(WV_ERR_INVALID, "'%s.weight' is not depthwise", p.c_str());
+  DwW d;
+  d.C = static_cast<int>(t.shape[0]);
+  d.k = static_cast<int>(t.shape[2]);
+  std::vector<float> h(static_cast<size_t>(d.k) * d.C);
+  for (int c = 0; c < d.C; ++c)
+    for (int j = 0; j < d.k; ++j) h[static_cast<size_t>(j) * d.C + c] = t.data[c * d.k + j] * scale;
+  d.w = W.dev.upload(h);
+  const HostTensor* b = with_bias ? W.find(p + ".bias") : nullptr;
+  if (b) {
+    std::vector<float> bb(b->data, b->data + d.C);
+    for (auto& v : bb) v *= scale;
+    d.bias = W.dev.upload(bb);
+  }
+  return d;
+}
+
+ResW resblock_w(Weights& W, const std::string& p, int idx, float rs) {
+  ResW r;
+  r.pre_scale = 1.f / std::sqrt(1.f + idx * rs * rs);                     // seanet.py:183
+  r.pw1 = pointwise(W, p + ".block.1.conv.conv", 1.f, false);
+  r.dw1 = depthwise(W, p + ".block.2.conv.conv", 1.f, true);
+  r.pw2 = pointwise(W, p + ".block.4.conv.conv", 1.f, false);
+  const float tail = rs * W.scalar_or(p + ".res_scale_param", 1.f);       // seanet.py:271-277
+  r.dw2 = depthwise(W, p + ".block.5.conv.conv", tail, true);
+  return r;
+}
+
+SpecW spec_w(Weights& W, const std::string& p, int n_fft, int hop, float mean, float stdv, float rs) {
+  SpecW s;
+  s.n_fft = n_fft; s.hop = hop; s.mean = mean; s.stdv = stdv;
+  const HostTensor& d = W.get(p + ".spec.weight");                        // [(n_fft+2), 1, n_fft]
+  if (d.shape.size() != 3 || d.shape[0] != n_fft + 2 || d.shape[2] != n_fft)
+    WV_THROW(WV_ERR_INVALID, "'%s.spec.weight' has an unexpected shape", p.c_str());
+  const int half = n_fft / 2;
+  auto row = [&](int r) { return d.data + static_cast<size_t>(r) * n_fft; };
+  // imaginary rows of bins 0 and n_fft/2 must vanish: they share a column pair (see gemm epilogue)
+  for (int n = 0; n < n_fft; ++n)
+    if (std::fabs(row(half + 1)[n]) > 1e-3f || std::fabs(row(half + 1 + half)[n]) > 1e-3f)
+      WV_THROW(WV_ERR_UNSUPPORTED, "'%s.spec.weight' is not a real-input DFT basis", p.c_str());
+  std::vector<float> rows(static_cast<size_t>(n_fft) * n_fft);
+  for (int pr = 0; pr < half; ++pr) {
+    const float* re = pr == 0 ? row(0) : row(pr);
+    const float* im = pr == 0 ? row(half) : row(half + 1 + pr);          // pair 0 = (bin 0, bin N/2)
+    std::copy(re, re + n_fft, rows.begin() + static_cast<size_t>(2 * pr) * n_fft);
+    std::copy(im, im + n_fft, rows.begin() + static_cast<size_t>(2 * pr + 1) * n_fft);
+  }
+  s.dft = make_gemm_w(W, rows, n_fft, n_fft, true, pick_block_n(n_fft), nullptr, 0);
+  const float sc = rs * W.scalar_or(p + ".scale_param", 1.f);            // seanet.py:499-505
+  s.layer = pointwise(W, p + ".layer.conv.conv", sc, false);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+struct Arena {
+  struct Blk { size_t off, size; };
+  std::vector<Blk> free_list;
+  size_t top = 0, high = 0;
+  size_t alloc(size_t bytes) {
+    bytes = round_up(std::max<size_t>(bytes, 256), 256);
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].size >= bytes) {
+        size_t off = free_list[i].off;
+        free_list[i].off += bytes;
+        free_list[i].size -= bytes;
+        if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
+        return off;
+      }
+    if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+      size_t off = free_list.back().off;          // grow the trailing free block
+      top = off + bytes;
+      free_list.pop_back();
+      high = std::max(high, top);
+      return off;
+    }
+    size_t off = top;
+    top += bytes;
+    high = std::max(high, top);
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = round_up(std::max<size_t>(bytes, 256), 256);
+    free_list.push_back({off, bytes});
+    std::sort(free_list.begin(), free_list.end(), [](const Blk& a, const Blk& b) { return a.off < b.off; });
+    std::vector<Blk> m;
+    for (auto& b : free_list) {
+      if (!m.empty() && m.back().off + m.back().size == b.off) m.back().size += b.size;
+      else m.push_back(b);
+    }
+    free_list.swap(m);
+  }
+};
+
+struct Buf {
+  size_t off = 0, bytes = 0;
+  bool valid = false;
+};
+
+struct IoPtrs {
+  const float* x = nullptr;       // [B,T]
+  const float* msg = nullptr;
+  float* wm = nullptr;
+  float* y = nullptr;
+  float* latent = nullptr;
+  const float* z_in = nullptr;
+  float* logits = nullptr;
+  uint8_t* bits = nullptr;
+  float* avg = nullptr;
+  float* conf = nullptr;
+  uint8_t* valid = nullptr;
+  const uint8_t* presence = nullptr;
+  uint8_t* mask = nullptr;
+  float* probs = nullptr;
+};
+
+enum OpType { OP_GEMM, OP_DW5, OP_DOWN, OP_UP, OP_CONV_PRE, OP_CONV_LAST, OP_WAV_STAGE, OP_FRAMES,
+              OP_FILM, OP_BITS, OP_CONF, OP_LATENT_IN };
+
+struct Op {
+  OpType type;
+  // GEMM
+  int epi = 0;
+  CUtensorMap tmA, tmB;
+  GemmArgs g;
+  int grid = 0;
+  // generic
+  const void* in = nullptr;
+  const void* res = nullptr;
+  void* out0 = nullptr;
+  void* out1 = nullptr;
+  const float* w = nullptr;
+  const float* bias = nullptr;
+  const float* film = nullptr;
+  float fa = 0.f, fb = 0.f;
+  int i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  FilmArgs fargs;
+};
+
+struct Plan {
+  int B = 0, T = 0;
+  std::vector<Op> ops;
+  size_t ws_bytes = 0;
+  Buf latent;          // bf16 [B*F, dim]
+  int F = 0;
+};
+
+struct PlanCtx {
+  Arena arena;
+  uint8_t* base = nullptr;   // nullptr => sizing pass (no tensor maps encoded)
+  std::vector<Op>* ops = nullptr;
+  int B = 0, T = 0;
+  Buf alloc(size_t bytes) {
+    Buf b;
+    b.bytes = bytes;
+    b.off = arena.alloc(bytes);
+    b.valid = true;
+    return b;
+  }
+  void release(Buf& b) {
+    if (b.valid) arena.release(b.off, b.bytes);
+    b.valid = false;
+  }
+  template <typename T>
+  T* ptr(const Buf& b) const { return reinterpret_cast<T*>(base ? base + b.off : nullptr); }
+  bool dry() const { return base == nullptr; }
+};
+
+int elem_grid(long long total_threads) {
+  long long blocks = (total_threads + 255) / 256;
+  const long long cap = static_cast<long long>(g_num_sms) * 16;
+  return static_cast<int>(std::max<long long>(1, std::min(blocks, cap)));
+}
+
+// generic GEMM op: A given either as a flat [M, lda] 16-bit buffer or as a prebuilt 3-D view
+void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long long M, int K,
+              GemmArgs g, const CUtensorMap* custom_tmA = nullptr, int rows_per_clip = 0,
+              int n_clips = 1) {
+  Op op;
+  op.type = OP_GEMM;
+  op.epi = epi;
+  g.N = w.N;
+  g.K = K;
+  g.block_n = w.block_n;
+  g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
+  if (custom_tmA) {
+    g.rows_per_clip = rows_per_clip;
+    g.n_clips = n_clips;
+    op.tmA = *custom_tmA;
+  } else {
+    g.rows_per_clip = static_cast<int>(M);
+    g.n_clips = 1;
+    if (!c.dry()) op.tmA = make_tmap(A, 3, K, M, 1, lda, static_cast<uint64_t>(lda) * M, BK, BM, w.fp16);
+  }
+  op.tmB = w.tm;
+  op.g = g;
+  const int tiles = ceil_div(g.rows_per_clip, BM) * g.n_clips * (w.N / w.block_n);
+  op.grid = std::min(tiles, g_num_sms);
+  c.ops->push_back(op);
+}
+
+GemmArgs std_args(const float* bias, const bf16* res, bf16* out_raw, bf16* out_act, float act_scale, int ldo) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.bias = bias; g.residual = res; g.out_raw = out_raw; g.out_act = out_act;
+  g.act_scale = act_scale; g.ldo = ldo;
+  return g;
+}
+
+void add_dw5(PlanCtx& c, const DwW& w, const bf16* in, const bf16* res, bf16* out_raw, bf16* out_act,
+             float act_scale, int T, int C) {
+  Op op;
+  op.type = OP_DW5;
+  op.in = in; op.res = res; op.out0 = out_raw; op.out1 = out_act;
+  op.w = w.w; op.bias = w.bias; op.fa = act_scale;
+  op.i[0] = c.B; op.i[1] = T; op.i[2] = C;
+  op.grid = elem_grid(static_cast<long long>(c.B) * ceil_div(T, DW_TT) * (C / 8));
+  c.ops->push_back(op);
+}
+
+// One residual block (modules/seanet.py:245-281).  X raw (residual), A = ELU(X*pre_scale).
+// Produces Xn (raw, if need_raw) and An = ELU(Xn*next_act_scale) (if need_act); frees X and A.
+void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool need_raw, bool need_act,
+                   float next_act_scale, Buf& Xn, Buf& An) {
+  const long long M = static_cast<long long>(c.B) * T;
+  const size_t bytes = static_cast<size_t>(M) * C * 2;
+  Buf G1 = c.alloc(bytes);
+  add_gemm(c, EPI_STD, r.pw1, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G1), nullptr, 1.f, C));
+  c.release(A);
+  Buf A2 = c.alloc(bytes);
+  add_dw5(c, r.dw1, c.ptr<bf16>(G1), nullptr, nullptr, c.ptr<bf16>(A2), 1.f, T, C);
+  c.release(G1);
+  Buf G2 = c.alloc(bytes);
+  add_gemm(c, EPI_STD, r.pw2, c.ptr<bf16>(A2), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G2), nullptr, 1.f, C));
+  c.release(A2);
+  Xn = Buf(); An = Buf();
+  if (need_raw) Xn = c.alloc(bytes);
+  if (need_act) An = c.alloc(bytes);
+  add_dw5(c, r.dw2, c.ptr<bf16>(G2), c.ptr<bf16>(X), need_raw ? c.ptr<bf16>(Xn) : nullptr,
+          need_act ? c.ptr<bf16>(An) : nullptr, next_act_scale, T, C);
+  c.release(G2);
+  c.release(X);
+}
+
+struct Net;
+void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, Buf& X,
+               int C, float act_scale, Buf& Aout);
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+struct wv_net {
+  wv_net_config cfg;
+  int device = 0;
+  Weights W;
+  EncoderW enc;
+  DecoderW dec;
+  HeadW head;
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;       // full forward
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> dec_plans;   // decode-only (B, F)
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  long long chunk_samples = 0;
+  ~wv_net() {
+    if (ws) cudaFree(ws);
+  }
+};
+
+namespace {
+
+void build_encoder_w(wv_net& n) {
+  Weights& W = n.W;
+  const wv_net_config& cf = n.cfg;
+  EncoderW& e = n.enc;
+  const std::string p = "encoder";
+  const float rs = cf.res_scale_enc;
+  e.C0 = cf.channels_enc;
+  e.dim = cf.dimension;
+  e.conv_pre = depthwise(W, p + ".conv_pre.1.conv.conv", 1.f / WAV_STD, true);   // seanet.py:658
+  if (e.conv_pre.k != 5) WV_THROW(WV_ERR_UNSUPPORTED, "conv_pre kernel size %d (only 5)", e.conv_pre.k);
+  if (!e.conv_pre.bias) WV_THROW(WV_ERR_MISSING_WEIGHT, "conv_pre bias missing (bias=True required)");
+  int C = e.C0, nfft = cf.n_fft_base, hop = 1;
+  const int S = cf.n_strides;
+  if (S + 1 > 5) WV_THROW(WV_ERR_UNSUPPORTED, "more than 4 strides");
+  for (int s = 0; s < S; ++s) {
+    EncStageW st;
+    st.r = cf.strides[S - 1 - s];                                              // seanet.py:646
+    st.C = C;
+    for (int j = 1; j <= cf.n_residual_enc; ++j)                                // idx=j, seanet.py:684
+      st.res.push_back(resblock_w(W, p + ".blocks." + std::to_string(s) + "." + std::to_string(j - 1), j, rs));
+    st.spec = spec_w(W, p + ".spec_blocks." + std::to_string(s), nfft, hop, SPEC_MEANS[s], SPEC_STDS[s], rs);
+    st.down_pw = pointwise(W, p + ".downsample." + std::to_string(s) + ".2.conv.conv", 1.f, false);
+    st.down_dw = depthwise(W, p + ".downsample." + std::to_string(s) + ".3.conv.conv", 1.f, true);
+    if (st.down_dw.k != 2 * st.r) WV_THROW(WV_ERR_INVALID, "downsample kernel != 2*stride");
+    e.stages.push_back(st);
+    C *= 2; nfft *= 2; hop *= st.r;
+  }
+  e.C_last = C; e.hop = hop; e.nfft_max = nfft;
+  e.spec_post = spec_w(W, p + ".spec_post", nfft, hop, SPEC_MEANS[4], SPEC_STDS[4], rs);
+  e.post_dw = depthwise(W, p + ".conv_post.1.conv.conv", 1.f, false);
+  e.post_pw = pointwise(W, p + ".conv_post.2.conv.conv", 1.f, true);
+  if (e.post_pw.N > MAX_BN) WV_THROW(WV_ERR_UNSUPPORTED, "latent dimension > 256");
+  e.post_pw.block_n = e.post_pw.N;   // L2 norm needs the whole row in one tile
+  e.post_pw.tm = make_tmap(e.post_pw.w, 2, e.post_pw.K, e.post_pw.N, 1, e.post_pw.ldw, 0, BK, e.post_pw.N, false);
+  if (cf.kind == WV_KIND_GENERATOR) {
+    e.has_film = true;
+    FilmArgs& f = e.film;
+    memset(&f, 0, sizeof(f));
+    f.msg_dim = cf.msg_dimension; f.E = cf.embedding_dim; f.n_hidden = cf.embedding_layers;
+    if (f.n_hidden > 3) WV_THROW(WV_ERR_UNSUPPORTED, "embedding_layers > 3");
+    auto up = [&](const std::string& name, int64_t n_expect) {
+      const HostTensor& t = W.get(name);
+      if (t.numel() != n_expect) WV_THROW(WV_ERR_INVALID, "'%s' has %lld elements, expected %lld", name.c_str(), (long long)t.numel(), (long long)n_expect);
+      return W.dev.upload(std::vector<float>(t.data, t.data + t.numel()));
+    };
+    f.w[0] = up(p + ".msg_embedding.0.weight", (int64_t)f.E * f.msg_dim);
+    f.b[0] = up(p + ".msg_embedding.0.bias", f.E);
+    for (int l = 0; l < f.n_hidden; ++l) {
+      f.w[l + 1] = up(p + ".msg_embedding." + std::to_string(1 + 2 * l) + ".weight", (int64_t)f.E * f.E);
+      f.b[l + 1] = up(p + ".msg_embedding." + std::to_string(1 + 2 * l) + ".bias", f.E);
+    }
+    e.bands = cf.freq_bands;
+    e.n_film = S * e.bands;
+    std::vector<float> gw, gb, bw, bb;
+    for (int s = 0; s < S; ++s)
+      for (int b = 0; b < e.bands; ++b) {
+        const std::string q = p + ".film_layers." + std::to_string(s) + "." + std::to_string(b);
+        const HostTensor& a = W.get(q + ".gamma_layer.weight");
+        const HostTensor& c2 = W.get(q + ".beta_layer.weight");
+        gw.insert(gw.end(), a.data, a.data + f.E);
+        bw.insert(bw.end(), c2.data, c2.data + f.E);
+        gb.push_back(W.get(q + ".gamma_layer.bias").data[0]);
+        bb.push_back(W.get(q + ".beta_layer.bias").data[0]);
+      }
+    f.gw = W.dev.upload(gw); f.gb = W.dev.upload(gb);
+    f.bw = W.dev.upload(bw); f.bb = W.dev.upload(bb);
+    f.n_film = e.n_film;
+    for (auto& st : e.stages)
+      if ((2 * st.C) % e.bands != 0 || ((2 * st.C) / e.bands) % 8 != 0)
+        WV_THROW(WV_ERR_INVALID, "Number of channels (%d) must be divisible by freq_bands (%d)", 2 * st.C, e.bands);
+  }
+}
+
+void build_decoder_w(wv_net& n) {
+  Weights& W = n.W;
+  const wv_net_config& cf = n.cfg;
+  DecoderW& d = n.dec;
+  const std::string p = "decoder.model";
+  const float rs = cf.res_scale_dec;
+  int i = 0;
+  d.pw0 = pointwise(W, p + "." + std::to_string(i++) + ".conv.conv", 1.f, false);
+  d.dw0 = depthwise(W, p + "." + std::to_string(i++) + ".conv.conv", 1.f, true);
+  int C = d.pw0.N;
+  d.stage_scale = 1.f / std::sqrt(1.f + cf.n_residual_dec * rs * rs);            // seanet.py:1104
+  for (int s = 0; s < cf.n_strides; ++s) {
+    DecStageW st;
+    st.r = cf.strides[s];
+    st.C = C;
+    i += 2;
+    st.up = depthwise(W, p + "." + std::to_string(i++) + ".convtr.convtr", 1.f, false);
+    if (st.up.k != 2 * st.r) WV_THROW(WV_ERR_INVALID, "upsample kernel != 2*stride");
+    st.halve = pointwise(W, p + "." + std::to_string(i++) + ".conv.conv", 1.f, true);
+    for (int j = 0; j < cf.n_residual_dec; ++j)
+      st.res.push_back(resblock_w(W, p + "." + std::to_string(i++), j, rs));     // idx=j, seanet.py:1159
+    d.stages.push_back(st);
+    C /= 2;
+  }
+  i += 2;
+  const HostTensor& lw = W.get(p + "." + std::to_string(i) + ".conv.conv.weight");   // [1, C, 5]
+  if (lw.shape.size() != 3 || lw.shape[0] != 1 || lw.shape[1] != C || lw.shape[2] != 5)
+    WV_THROW(WV_ERR_INVALID, "decoder output conv has an unexpected shape");
+  std::vector<float> h(5 * C);
+  for (int c = 0; c < C; ++c)
+    for (int j = 0; j < 5; ++j) h[j * C + c] = lw.data[c * 5 + j] * WAV_STD;        // seanet.py:1193
+  d.last_w = W.dev.upload(h);
+  const HostTensor* lb = W.find(p + "." + std::to_string(i) + ".conv.conv.bias");
+  d.last_b = lb ? lb->data[0] * WAV_STD : 0.f;
+  d.C_last = C;
+}
+
+void build_head_w(wv_net& n) {
+  Weights& W = n.W;
+  const HostTensor& rc = W.get("reverse_convolution.weight");      // [dim, OD, hop]
+  const HostTensor& rb = W.get("reverse_convolution.bias");        // [OD]
+  const HostTensor& ll = W.get("last_layer.weight");               // [O, OD, 1]
+  const HostTensor& lb = W.get("last_layer.bias");                 // [O]
+  const int dim = static_cast<int>(rc.shape[0]), OD = static_cast<int>(rc.shape[1]), hop = static_cast<int>(rc.shape[2]);
+  const int O = static_cast<int>(ll.shape[0]);
+  if (hop != n.enc.hop || dim != n.cfg.dimension || ll.shape[1] != OD)
+    WV_THROW(WV_ERR_INVALID, "head shapes inconsistent with the encoder");
+  // logits[o, f*hop+j] = b_ll[o] + sum_c W_ll[o,c] (b_rc[c] + sum_z W_rc[z,c,j] z[z,f])
+  // (model/detector.py:304-310): both maps are linear with nothing in between -> pre-multiply.
+  std::vector<float> rows(static_cast<size_t>(O) * hop * dim);
+  for (int o = 0; o < O; ++o)
+    for (int j = 0; j < hop; ++j)
+      for (int z = 0; z < dim; ++z) {
+        double s = 0;
+        for (int c = 0; c < OD; ++c)
+          s += static_cast<double>(ll.data[o * OD + c]) * rc.data[(static_cast<size_t>(z) * OD + c) * hop + j];
+        rows[(static_cast<size_t>(o) * hop + j) * dim + z] = static_cast<float>(s);
+      }
+  std::vector<float> bias(O);
+  for (int o = 0; o < O; ++o) {
+    double s = lb.data[o];
+    for (int c = 0; c < OD; ++c) s += static_cast<double>(ll.data[o * OD + c]) * rb.data[c];
+    bias[o] = static_cast<float>(s);
+  }
+  n.head.n_out = O; n.head.hop = hop;
+  n.head.w = make_gemm_w(W, rows, O * hop, dim, false, pick_block_n(O * hop, hop), bias.data(), O);
+}
+
+// STFT branch + 1x1 + residual add (modules/seanet.py:463-507): Aout = ELU((X + spec) * act_scale)
+void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, Buf& X,
+               int C, float act_scale, Buf& Aout) {
+  const long long M = static_cast<long long>(c.B) * F;
+  const int K2 = s.n_fft / 2 + 1;
+  const int ldy = static_cast<int>(round_up(K2, 8));
+  Buf Y = c.alloc(static_cast<size_t>(M) * ldy * 2);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.out_raw = c.ptr<bf16>(Y);
+  g.ldo = ldy;
+  g.log_offset = s.mean + std::log(WAV_FP16_SCALE);
+  g.inv_sigma = 1.f / s.stdv;
+  g.clamp_sq = (1e-5f * WAV_FP16_SCALE) * (1e-5f * WAV_FP16_SCALE);
+  g.n_half = s.n_fft / 2;
+  const int base = lead - (s.n_fft - 1);       // first sample of frame 0 inside the staged clip
+  if ((s.hop * 2) % 16 == 0) {
+    CUtensorMap tm;
+    if (!c.dry())
+      tm = make_tmap(c.ptr<__half>(wav16) + base, 3, s.n_fft, F, c.B, s.hop, pitch, BK, BM, true);
+    add_gemm(c, EPI_STFT, s.dft, nullptr, 0, 0, s.n_fft, g, &tm, F, c.B);
+  } else {
+    Buf FR = c.alloc(static_cast<size_t>(M) * s.n_fft * 2);
+    Op op;
+    op.type = OP_FRAMES;
+    op.in = c.ptr<__half>(wav16); op.out0 = c.ptr<__half>(FR);
+    op.i[0] = c.B; op.i[1] = F; op.i[2] = s.hop; op.i[3] = s.n_fft; op.i[4] = base; op.i[5] = pitch;
+    op.grid = elem_grid(M * (s.n_fft / 8));
+    c.ops->push_back(op);
+    add_gemm(c, EPI_STFT, s.dft, c.ptr<__half>(FR), s.n_fft, M, s.n_fft, g);
+    c.release(FR);
+  }
+  Aout = c.alloc(static_cast<size_t>(M) * C * 2);
+  add_gemm(c, EPI_STD, s.layer, c.ptr<bf16>(Y), ldy, M, K2,
+           std_args(nullptr, c.ptr<bf16>(X), nullptr, c.ptr<bf16>(Aout), act_scale, C));
+  c.release(Y);
+  c.release(X);
+}
+
+// SEANetEncoder.forward (modules/seanet.py:883-976).  Leaves the latent bf16 [B*F, dim].
+void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
+  const EncoderW& e = n.enc;
+  const int B = c.B, T = c.T;
+  const int lead = e.nfft_max - 1;
+  const int pitch = static_cast<int>(round_up(lead + T, 8));
+  Buf wav16 = c.alloc(static_cast<size_t>(B) * pitch * 2);
+  {
+    Op op;
+    op.type = OP_WAV_STAGE;
+    op.out0 = c.ptr<__half>(wav16);
+    op.fa = WAV_FP16_SCALE;
+    op.i[0] = B; op.i[1] = T; op.i[2] = lead; op.i[3] = pitch;
+    op.grid = elem_grid(static_cast<long long>(B) * pitch);
+    c.ops->push_back(op);
+  }
+  Buf film;
+  if (e.has_film) {
+    film = c.alloc(static_cast<size_t>(B) * e.n_film * 2 * 4);
+    Op op;
+    op.type = OP_FILM;
+    op.out0 = c.ptr<float>(film);
+    op.fargs = e.film;
+    op.i[0] = B;
+    c.ops->push_back(op);
+  }
+  int Ts = T, C = e.C0;
+  Buf X = c.alloc(static_cast<size_t>(B) * Ts * C * 2), A = c.alloc(static_cast<size_t>(B) * Ts * C * 2);
+  {
+    Op op;
+    op.type = OP_CONV_PRE;
+    op.out0 = c.ptr<bf16>(X); op.out1 = c.ptr<bf16>(A);
+    op.w = e.conv_pre.w; op.bias = e.conv_pre.bias;
+    op.fa = e.stages[0].res[0].pre_scale;
+    op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
+    op.grid = elem_grid(static_cast<long long>(B) * Ts * (C / 8));
+    c.ops->push_back(op);
+  }
+  const float down_scale = 1.f / std::sqrt(1.f + n.cfg.n_residual_enc * n.cfg.res_scale_enc * n.cfg.res_scale_enc);
+  const int S = static_cast<int>(e.stages.size());
+  for (int s = 0; s < S; ++s) {
+    const EncStageW& st = e.stages[s];
+    const int nres = static_cast<int>(st.res.size());
+    for (int j = 0; j < nres; ++j) {
+      const bool last = j == nres - 1;
+      Buf Xn, An;
+      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An);
+      X = Xn; A = An;
+    }
+    plan_spec(c, st.spec, wav16, pitch, lead, Ts, X, C, down_scale, A);   // A = ELU((x+spec)*scale)
+    const long long M = static_cast<long long>(B) * Ts;
+    Buf G = c.alloc(static_cast<size_t>(M) * 2 * C * 2);
+    add_gemm(c, EPI_STD, st.down_pw, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, 2 * C));
+    c.release(A);
+    const int To = ceil_div(Ts, st.r);
+    const bool last_stage = s == S - 1;
+    X = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2);
+    if (!last_stage) A = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2);
+    {
+      Op op;
+      op.type = OP_DOWN;
+      op.in = c.ptr<bf16>(G); op.out0 = c.ptr<bf16>(X); op.out1 = last_stage ? nullptr : c.ptr<bf16>(A);
+      op.w = st.down_dw.w; op.bias = st.down_dw.bias;
+      op.film = e.has_film ? c.ptr<float>(film) + static_cast<size_t>(s) * e.bands * 2 : nullptr;
+      op.fa = last_stage ? 1.f : e.stages[s + 1].res[0].pre_scale;
+      op.i[0] = B; op.i[1] = Ts; op.i[2] = To; op.i[3] = 2 * C; op.i[4] = st.r; op.i[5] = e.n_film * 2; op.i[6] = e.bands;
+      op.grid = elem_grid(static_cast<long long>(B) * To * (2 * C / 8));
+      c.ops->push_back(op);
+    }
+    c.release(G);
+    Ts = To; C *= 2;
+  }
+  plan.F = Ts;
+  plan_spec(c, e.spec_post, wav16, pitch, lead, Ts, X, C, 1.f, A);         // ELU(x + spec)
+  c.release(wav16);
+  if (film.valid) c.release(film);
+  const long long M = static_cast<long long>(B) * Ts;
+  Buf D = c.alloc(static_cast<size_t>(M) * C * 2);
+  add_dw5(c, e.post_dw, c.ptr<bf16>(A), nullptr, c.ptr<bf16>(D), nullptr, 1.f, Ts, C);
+  c.release(A);
+  plan.latent = c.alloc(static_cast<size_t>(M) * e.dim * 2);
+  GemmArgs g = std_args(e.post_pw.bias, nullptr, c.ptr<bf16>(plan.latent), nullptr, 1.f, e.dim);
+  g.l2_scale = std::sqrt(static_cast<float>(e.dim));                         // seanet.py:299
+  g.f32_F = Ts;
+  add_gemm(c, EPI_L2NORM, e.post_pw, c.ptr<bf16>(D), C, M, C, g);
+  c.release(D);
+}
+
+// SEANetDecoder.forward (modules/seanet.py:1212-1227) + trim + watermark add.
+void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
+  const DecoderW& d = n.dec;
+  const int B = c.B;
+  int Ts = F, C = d.pw0.N;
+  long long M = static_cast<long long>(B) * Ts;
+  Buf G = c.alloc(static_cast<size_t>(M) * C * 2);
+  add_gemm(c, EPI_STD, d.pw0, c.ptr<bf16>(Z), d.pw0.K, M, d.pw0.K, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, C));
+  Buf A = c.alloc(static_cast<size_t>(M) * C * 2);
+  add_dw5(c, d.dw0, c.ptr<bf16>(G), nullptr, nullptr, c.ptr<bf16>(A), 1.f, Ts, C);   // ELU of stage 0
+  c.release(G);
+  for (size_t s = 0; s < d.stages.size(); ++s) {
+    const DecStageW& st = d.stages[s];
+    const int To = Ts * st.r;
+    Buf U = c.alloc(static_cast<size_t>(B) * To * C * 2);
+    {
+      Op op;
+      op.type = OP_UP;
+      op.in = c.ptr<bf16>(A); op.out0 = c.ptr<bf16>(U); op.w = st.up.w;
+      op.i[0] = B; op.i[1] = Ts; op.i[2] = C; op.i[3] = st.r;
+      op.grid = elem_grid(static_cast<long long>(B) * Ts * (C / 8));
+      c.ops->push_back(op);
+    }
+    c.release(A);
+    Ts = To;
+    M = static_cast<long long>(B) * Ts;
+    const int Ch = C / 2;
+    Buf X = c.alloc(static_cast<size_t>(M) * Ch * 2);
+    A = c.alloc(static_cast<size_t>(M) * Ch * 2);
+    add_gemm(c, EPI_STD, st.halve, c.ptr<bf16>(U), C, M, C,
+             std_args(st.halve.bias, nullptr, c.ptr<bf16>(X), c.ptr<bf16>(A), st.res.empty() ? d.stage_scale : st.res[0].pre_scale, Ch));
+    c.release(U);
+    C = Ch;
+    const int nres = static_cast<int>(st.res.size());
+    for (int j = 0; j < nres; ++j) {
+      const bool last = j == nres - 1;
+      Buf Xn, An;
+      plan_resblock(c, st.res[j], X, A, Ts, C, !last, true, last ? d.stage_scale : st.res[j + 1].pre_scale, Xn, An);
+      X = Xn; A = An;
+    }
+    if (nres == 0) c.release(X);
+  }
+  {
+    Op op;
+    op.type = OP_CONV_LAST;
+    op.in = c.ptr<bf16>(A); op.w = d.last_w; op.fa = d.last_b;
+    op.i[0] = B; op.i[1] = Ts; op.i[2] = T_out; op.i[3] = C;
+    op.grid = B * ceil_div(T_out, CL_TILE);
+    c.ops->push_back(op);
+  }
+  c.release(A);
+}
+
+void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
+  const HeadW& h = n.head;
+  const long long M = static_cast<long long>(c.B) * F;
+  const int tiles_n = h.w.N / h.w.block_n;
+  Buf partial = c.alloc(static_cast<size_t>(M) * tiles_n * 4);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.bias = h.w.bias;
+  g.partial = c.ptr<float>(partial);
+  g.hop = h.hop; g.T = c.T; g.n_out = h.n_out; g.head_F = F;
+  add_gemm(c, EPI_HEAD, h.w, c.ptr<bf16>(Z), h.w.K, M, h.w.K, g);
+  {
+    Op op;
+    op.type = OP_BITS;
+    op.in = c.ptr<float>(partial);
+    op.i[0] = c.B; op.i[1] = F; op.i[2] = tiles_n; op.i[3] = h.hop / h.w.block_n; op.i[4] = c.T; op.i[5] = h.n_out;
+    c.ops->push_back(op);
+    Op op2;
+    op2.type = OP_CONF;
+    op2.i[0] = c.B; op2.i[1] = h.n_out;
+    c.ops->push_back(op2);
+  }
+  c.release(partial);
+}
+
+void build_plan_pass(wv_net& n, Plan& plan, uint8_t* base) {
+  plan.ops.clear();
+  PlanCtx c;
+  c.base = base; c.ops = &plan.ops; c.B = plan.B; c.T = plan.T;
+  plan_encoder(c, n, plan);
+  if (n.cfg.kind == WV_KIND_GENERATOR) plan_decoder(c, n, plan.latent, plan.F, plan.T);
+  else plan_head(c, n, plan.latent, plan.F);
+  plan.ws_bytes = c.arena.high;
+}
+
+void ensure_ws(wv_net& n, size_t bytes) {
+  if (bytes <= n.ws_bytes) return;
+  // the workspace moves: every cached plan holds pointers/tensor maps into the old one
+  n.plans.clear();
+  n.dec_plans.clear();
+  if (n.ws) CK(cudaFree(n.ws));
+  n.ws = nullptr; n.ws_bytes = 0;
+  CK(cudaMalloc(reinterpret_cast<void**>(&n.ws), bytes));
+  n.ws_bytes = bytes;
+}
+
+Plan& get_plan(wv_net& n, int B, int T) {
+  auto key = std::make_pair(B, T);
+  auto it = n.plans.find(key);
+  if (it != n.plans.end()) return *it->second;
+  auto plan = std::make_unique<Plan>();
+  plan->B = B; plan->T = T;
+  build_plan_pass(n, *plan, nullptr);
+  ensure_ws(n, plan->ws_bytes);
+  build_plan_pass(n, *plan, n.ws);
+  Plan& ref = *plan;
+  n.plans[key] = std::move(plan);
+  return ref;
+}
+
+Plan& get_dec_plan(wv_net& n, int B, int F) {
+  auto key = std::make_pair(B, F);
+  auto it = n.dec_plans.find(key);
+  if (it != n.dec_plans.end()) return *it->second;
+  auto build = [&](Plan& plan, uint8_t* base) {
+    plan.ops.clear();
+    PlanCtx c;
+    c.base = base; c.ops = &plan.ops; c.B = B; c.T = F * n.enc.hop;
+    plan.latent = c.alloc(static_cast<size_t>(B) * F * n.enc.dim * 2);
+    Op op;
+    op.type = OP_LATENT_IN;
+    op.out0 = c.ptr<bf16>(plan.latent);
+    op.i[0] = B; op.i[1] = n.enc.dim; op.i[2] = F;
+    op.grid = elem_grid(static_cast<long long>(B) * F * n.enc.dim);
+    c.ops->push_back(op);
+    plan_decoder(c, n, plan.latent, F, F * n.enc.hop);
+    plan.ws_bytes = c.arena.high;
+  };
+  auto plan = std::make_unique<Plan>();
+  plan->B = B; plan->T = F * n.enc.hop; plan->F = F;
+  build(*plan, nullptr);
+  ensure_ws(n, plan->ws_bytes);
+  build(*plan, n.ws);
+  Plan& ref = *plan;
+  n.dec_plans[key] = std::move(plan);
+  return ref;
+}
+
+void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
+  switch (op.epi) {
+    case EPI_STD: gemm_sm100_kernel<EPI_STD><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
+    case EPI_L2NORM: gemm_sm100_kernel<EPI_L2NORM><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
+    case EPI_STFT: gemm_sm100_kernel<EPI_STFT><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
+    default: gemm_sm100_kernel<EPI_HEAD><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
+  }
+}
+
+void run_plan(wv_net& n, const Plan& plan, const IoPtrs& io, cudaStream_t st) {
+  for (const Op& op : plan.ops) {
+    switch (op.type) {
+      case OP_GEMM: {
+        GemmArgs g = op.g;
+        if (op.epi == EPI_L2NORM) g.out_f32_t = io.latent;
+        if (op.epi == EPI_HEAD) {
+          g.logits = io.logits; g.mask_out = io.mask; g.probs = io.probs; g.presence = io.presence;
+          if (!(io.bits || io.avg || io.conf || io.valid)) g.partial = nullptr;
+        }
+        launch_gemm(op, g, st);
+        break;
+      }
+      case OP_DW5:
+        dw5_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, op.bias, static_cast<const bf16*>(op.res),
+                                            static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        break;
+      case OP_DOWN:
+        down_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, op.bias, op.film, op.i[5], op.i[6],
+                                             static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]);
+        break;
+      case OP_UP:
+        up_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3]);
+        break;
+      case OP_CONV_PRE:
+        conv_pre_kernel<<<op.grid, 256, 0, st>>>(io.x, op.w, op.bias, static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        break;
+      case OP_CONV_LAST: {
+        const int C = op.i[3];
+        const size_t smem = ((5 * C * 4 + 15) & ~15) + static_cast<size_t>(CL_TILE + 4) * (C * 2 + 16);
+        conv_last_kernel<<<op.grid, CL_TILE, smem, st>>>(static_cast<const bf16*>(op.in), op.w, op.fa, io.x, io.wm, io.y, op.i[0], op.i[1], op.i[2], C);
+        break;
+      }
+      case OP_WAV_STAGE:
+        wav_stage_kernel<<<op.grid, 256, 0, st>>>(io.x, static_cast<__half*>(op.out0), op.fa, op.i[0], op.i[1], op.i[2], op.i[3]);
+        break;
+      case OP_FRAMES:
+        frames_kernel<<<op.grid, 256, 0, st>>>(static_cast<const __half*>(op.in), static_cast<__half*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], op.i[5]);
+        break;
+      case OP_FILM:
+        film_kernel<<<op.i[0], std::max(64, op.fargs.E), 2 * op.fargs.E * sizeof(float), st>>>(io.msg, static_cast<float*>(op.out0), op.fargs);
+        break;
+      case OP_BITS:
+        if (io.bits || io.avg || io.conf || io.valid) {
+          // avg is needed for conf: use caller's buffer or skip conf when absent
+          bits_finish_kernel<<<dim3(op.i[0], op.i[5]), 32, 0, st>>>(static_cast<const float*>(op.in), op.i[1], op.i[2], op.i[3], io.presence, op.i[4], op.i[5], io.bits, io.avg, io.valid);
+        }
+        break;
+      case OP_CONF:
+        if (io.conf && io.avg) conf_kernel<<<ceil_div(op.i[0], 128), 128, 0, st>>>(io.avg, io.conf, op.i[0], op.i[1]);
+        break;
+      case OP_LATENT_IN:
+        latent_in_kernel<<<op.grid, 256, 0, st>>>(io.z_in, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2]);
+        break;
+    }
+  }
+  CK(cudaGetLastError());
+}
+
+int sub_batch(const wv_net& n, int B, int T) {
+  if (n.chunk_samples <= 0) return B;
+  long long bc = n.chunk_samples / std::max(1, T);
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(B, bc)));
+}
+
+template <typename Fn>
+int guarded(Fn&& fn) {
+  try {
+    fn();
+    return WV_OK;
+  } catch (const WvError& e) {
+    return fail(e.code, e.msg);
+  } catch (const std::exception& e) {
+    return fail(WV_ERR_INVALID, e.what());
+  }
+}
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    want = dev;
+  }
+  ~DeviceGuard() {
+    if (prev != want) cudaSetDevice(prev);
+  }
+  int want;
+};
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+int wv_version(void) { return 1; }
+const char* wv_last_error(void) { return g_err.c_str(); }
+
+int wv_net_create(const wv_net_config* cfg, const wv_tensor* tensors, int n_tensors, int device, wv_net** out) {
+  if (!cfg || !tensors || !out) return fail(WV_ERR_INVALID, "null argument");
+  *out = nullptr;
+  return guarded([&] {
+    DeviceGuard dg(device);
+    init_device_once();
+    std::unique_ptr<wv_net> n(new wv_net());
+    n->cfg = *cfg;
+    n->device = device;
+    if (cfg->n_strides < 1 || cfg->n_strides > 4) WV_THROW(WV_ERR_UNSUPPORTED, "n_strides must be 1..4");
+    if (cfg->n_residual_enc < 1) WV_THROW(WV_ERR_UNSUPPORTED, "n_residual_enc must be >= 1");
+    if (cfg->channels_enc % 32 != 0) WV_THROW(WV_ERR_UNSUPPORTED, "channels_enc must be a multiple of 32");
+    for (int i = 0; i < n_tensors; ++i) {
+      HostTensor t;
+      t.data = tensors[i].data;
+      t.shape.assign(tensors[i].shape, tensors[i].shape + tensors[i].ndim);
+      n->W.host[tensors[i].name] = t;
+    }
+    build_encoder_w(*n);
+    if (cfg->kind == WV_KIND_GENERATOR) {
+      if (cfg->channels_dec % 32 != 0) WV_THROW(WV_ERR_UNSUPPORTED, "channels_dec must be a multiple of 32");
+      build_decoder_w(*n);
+    } else {
+      build_head_w(*n);
+    }
+    n->W.host.clear();   // host pointers are only valid during this call
+    CK(cudaDeviceSynchronize());
+    *out = n.release();
+  });
+}
+
+int wv_net_destroy(wv_net* net) {
+  if (!net) return WV_OK;
+  cudaSetDevice(net->device);
+  cudaDeviceSynchronize();
+  delete net;
+  return WV_OK;
+}
+
+int wv_net_reserve(wv_net* net, int B, int T) {
+  if (!net || B < 1 || T < 1) return fail(WV_ERR_INVALID, "bad arguments to wv_net_reserve");
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    const int bc = sub_batch(*net, B, T);
+    // size for the largest sub-batch first so that the workspace never moves afterwards
+    get_plan(*net, bc, T);
+    if (B % bc) get_plan(*net, B % bc, T);
+    get_plan(*net, bc, T);
+  });
+}
+
+size_t wv_net_workspace_bytes(const wv_net* net) { return net ? net->ws_bytes : 0; }
+
+int wv_net_launches(const wv_net* net, int B, int T) {
+  if (!net) return 0;
+  wv_net* n = const_cast<wv_net*>(net);
+  const int bc = sub_batch(*n, B, T);
+  int total = 0;
+  for (int b0 = 0; b0 < B; b0 += bc) {
+    auto it = n->plans.find(std::make_pair(std::min(bc, B - b0), T));
+    if (it == n->plans.end()) return -1;
+    total += static_cast<int>(it->second->ops.size());
+  }
+  return total;
+}
+
+int wv_net_set_chunk(wv_net* net, int max_clip_samples) {
+  if (!net) return fail(WV_ERR_INVALID, "null net");
+  net->chunk_samples = max_clip_samples;
+  return WV_OK;
+}
+
+static int forward_common(wv_net* net, int B, int T, const IoPtrs& io0, cudaStream_t st) {
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    if (B < 1 || T < 1) WV_THROW(WV_ERR_INVALID, "empty batch or clip (B=%d, T=%d)", B, T);
+    const int bc = sub_batch(*net, B, T);
+    get_plan(*net, bc, T);
+    if (B % bc) get_plan(*net, B % bc, T);
+    const int nb = net->cfg.nbits;
+    const int F = ceil_div(T, net->enc.hop);
+    for (int b0 = 0; b0 < B; b0 += bc) {
+      const int bn = std::min(bc, B - b0);
+      Plan& plan = get_plan(*net, bn, T);
+      IoPtrs io = io0;
+      const size_t so = static_cast<size_t>(b0) * T;
+      if (io.x) io.x += so;
+      if (io.msg) io.msg += static_cast<size_t>(b0) * net->cfg.msg_dimension;
+      if (io.wm) io.wm += so;
+      if (io.y) io.y += so;
+      if (io.latent) io.latent += static_cast<size_t>(b0) * net->enc.dim * F;
+      if (io.logits) io.logits += so * nb;
+      if (io.bits) io.bits += static_cast<size_t>(b0) * nb;
+      if (io.avg) io.avg += static_cast<size_t>(b0) * nb;
+      if (io.conf) io.conf += b0;
+      if (io.valid) io.valid += static_cast<size_t>(b0) * nb;
+      if (io.presence) io.presence += so;
+      if (io.mask) io.mask += so;
+      if (io.probs) io.probs += so;
+      run_plan(*net, plan, io, st);
+    }
+  });
+}
+
+int wv_generator_forward(wv_net* net, const float* x, const float* msg, int B, int T, float* wm_out,
+                         float* y_out, float* latent_out, void* stream) {
+  if (!net || net->cfg.kind != WV_KIND_GENERATOR) return fail(WV_ERR_INVALID, "not a generator net");
+  if (!x || !msg) return fail(WV_ERR_INVALID, "x and msg are required");
+  IoPtrs io;
+  io.x = x; io.msg = msg; io.wm = wm_out; io.y = y_out; io.latent = latent_out;
+  return forward_common(net, B, T, io, static_cast<cudaStream_t>(stream));
+}
+
+int wv_generator_encode(wv_net* net, const float* x, const float* msg, int B, int T, float* latent_out, void* stream) {
+  // The decoder tail is cheap to skip only with a separate plan; encode() is an API-completeness
+  // entry (model/generator.py:290), so it runs the full plan and discards the waveform.
+  return wv_generator_forward(net, x, msg, B, T, nullptr, nullptr, latent_out, stream);
+}
+
+int wv_generator_decode(wv_net* net, const float* z, int B, int F, float* wav_out, void* stream) {
+  if (!net || net->cfg.kind != WV_KIND_GENERATOR) return fail(WV_ERR_INVALID, "not a generator net");
+  if (!z || !wav_out || B < 1 || F < 1) return fail(WV_ERR_INVALID, "bad arguments to wv_generator_decode");
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    Plan& plan = get_dec_plan(*net, B, F);
+    IoPtrs io;
+    io.z_in = z; io.wm = wav_out;
+    run_plan(*net, plan, io, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int wv_detector_forward(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* bits, float* avg,
+                        float* conf, uint8_t* valid, const uint8_t* presence, void* stream) {
+  if (!net || net->cfg.kind != WV_KIND_DETECTOR) return fail(WV_ERR_INVALID, "not a detector net");
+  if (!y) return fail(WV_ERR_INVALID, "y is required");
+  if (conf && !avg) return fail(WV_ERR_INVALID, "conf requires avg");
+  IoPtrs io;
+  io.x = y; io.logits = logits; io.bits = bits; io.avg = avg; io.conf = conf; io.valid = valid; io.presence = presence;
+  return forward_common(net, B, T, io, static_cast<cudaStream_t>(stream));
+}
+
+int wv_locator_forward(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* mask, float* probs, void* stream) {
+  if (!net || net->cfg.kind != WV_KIND_LOCATOR) return fail(WV_ERR_INVALID, "not a locator net");
+  if (!y) return fail(WV_ERR_INVALID, "y is required");
+  IoPtrs io;
+  io.x = y; io.logits = logits; io.mask = mask; io.probs = probs;
+  return forward_common(net, B, T, io, static_cast<cudaStream_t>(stream));
+}
+
+int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8_t* msg_bits, int B, int nbits,
+                          const uint8_t* pred_mask, const uint8_t* gt_mask, long long n_mask, long long* counters, void* stream) {
+  if (!counters) return fail(WV_ERR_INVALID, "counters is required");
+  if (bits && !msg_bits) return fail(WV_ERR_INVALID, "msg_bits is required with bits");
+  if (pred_mask && !gt_mask) return fail(WV_ERR_INVALID, "gt_mask is required with pred_mask");
+  return guarded([&] {
+    init_device_once();
+    const long long nb = static_cast<long long>(B) * nbits;
+    const long long work = std::max(bits ? nb : 0, pred_mask ? n_mask : 0);
+    if (work <= 0) return;
+    metrics_kernel<<<elem_grid(work), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bits, valid, msg_bits, nb, pred_mask, gt_mask, n_mask, reinterpret_cast<unsigned long long*>(counters));
+    CK(cudaGetLastError());
+  });
+}
+
+// ---- single-kernel entry points --------------------------------------------------------
+int wv_op_gemm(const void* A, int lda, const void* Wt, int ldw, int M, int N, int K, const float* bias,
+               const void* residual, void* out_raw, void* out_act, float act_scale, int a_is_fp16, void* stream) {
+  return guarded([&] {
+    init_device_once();
+    GemmW w;
+    w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = ldw; w.fp16 = a_is_fp16 != 0;
+    w.block_n = pick_block_n(N);
+    w.tm = make_tmap(Wt, 2, K, N, 1, ldw, 0, BK, w.block_n, w.fp16);
+    std::vector<Op> ops;
+    PlanCtx c;
+    c.base = reinterpret_cast<uint8_t*>(16);   // non-null: encode tensor maps
+    c.ops = &ops;
+    add_gemm(c, EPI_STD, w, A, lda, M, K,
+             std_args(bias, static_cast<const bf16*>(residual), static_cast<bf16*>(out_raw), static_cast<bf16*>(out_act), act_scale, N));
+    launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_op_dw5(const void* in, const float* w5c, const float* bias, const void* residual, void* out_raw, void* out_act,
+              float act_scale, int B, int T, int C, void* stream) {
+  return guarded([&] {
+    init_device_once();
+    dw5_kernel<<<elem_grid(static_cast<long long>(B) * ceil_div(T, DW_TT) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(in), w5c, bias, static_cast<const bf16*>(residual), static_cast<bf16*>(out_raw),
+        static_cast<bf16*>(out_act), act_scale, B, T, C);
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_op_down(const void* in, const float* wkc, const float* bias, const float* film, int film_stride, int bands,
+               void* out_raw, void* out_act, float act_scale, int B, int Tin, int C, int r, void* stream) {
+  return guarded([&] {
+    init_device_once();
+    const int To = ceil_div(Tin, r);
+    down_kernel<<<elem_grid(static_cast<long long>(B) * To * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(in), wkc, bias, film, film_stride, bands, static_cast<bf16*>(out_raw),
+        static_cast<bf16*>(out_act), act_scale, B, Tin, To, C, r);
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_op_up(const void* in, const float* wkc, void* out, int B, int Tin, int C, int r, void* stream) {
+  return guarded([&] {
+    init_device_once();
+    up_kernel<<<elem_grid(static_cast<long long>(B) * Tin * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(in), wkc, static_cast<bf16*>(out), B, Tin, C, r);
+    CK(cudaGetLastError());
+  });
+}
+
+}  // extern "C"
