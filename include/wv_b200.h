@@ -116,6 +116,17 @@ int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8
                           int B, int nbits, const uint8_t* pred_mask, const uint8_t* gt_mask,
                           long long n_mask, long long* counters, void* stream);
 
+/* ---- profiling / debugging (used by bench.py and the tests) ------------------------------- */
+/* When enabled, every launch of a forward is bracketed by CUDA events on the caller's stream. */
+int wv_net_set_profile(wv_net* net, int enable);
+/* Per-launch device time (ms), algorithmic FLOPs and bytes, and kernel class of the last profiled
+ * forward (one sub-batch).  Returns the number of launches written, or a negative code. */
+int wv_net_profile_read(wv_net* net, int max_ops, float* ms, double* flops, double* bytes, int* cls);
+const char* wv_net_profile_tag(wv_net* net, int i);
+/* Run up to the launch tagged `tag` and copy its output (0 = raw, 1 = activated) to dst. */
+int wv_debug_tap(wv_net* net, const float* x, const float* msg, int B, int T, const char* tag,
+                 int which, void* dst, size_t dst_bytes, size_t* written);
+
 /* ---- single-kernel entry points (unit tests / micro-benchmarks; device pointers) -------- */
 /* out = epilogue(A[M,K] * W[N,K]^T): bf16 in, fp32 accumulate on tcgen05; see DESIGN.md. */
 int wv_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K,

@@ -1,0 +1,174 @@
+"""GPU: each hand-written kernel against a plain fp32 PyTorch statement of the same op, called
+through the C ABI (wv_op_*)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from waveverify_b200 import _lib as L
+    return L.lib()
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def S():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def bf16_close(out, ref, rel=2 ** -8, abs_=1e-3):
+    """bf16 has 8 significant bits: one rounding of the fp32 result is <= 2^-9 relative; allow 2x."""
+    err = (out.float() - ref).abs()
+    tol = rel * ref.abs() + abs_
+    assert bool((err <= tol).all()), f"max err {err.max().item()} (ref max {ref.abs().max().item()})"
+
+
+GEMM_CASES = [
+    # M, N, K, bias, residual, act
+    (128, 64, 64, False, False, False),
+    (1, 32, 32, True, False, True),            # single row, locator width
+    (1000, 64, 64, True, True, True),
+    (4096, 256, 256, False, False, False),
+    (300, 96, 192, True, False, True),          # decoder widths, BLOCK_N=96
+    (777, 1536, 128, False, True, False),       # 6 N tiles
+    (5000, 128, 33, False, True, True),         # spec 1x1: K=33 zero-filled to 64 by TMA
+    (513, 1024, 513, False, True, True),        # K tail 513 -> 9 k-blocks
+    (333, 768, 1536, True, False, False),       # long K
+    (64000, 192, 192, False, True, True),       # many M tiles per CTA (persistent loop, both TMEM stages)
+    (40000, 384, 384, False, False, True),
+]
+
+
+@pytest.mark.parametrize("M,N,K,bias,res,act", GEMM_CASES)
+def test_gemm_tcgen05(M, N, K, bias, res, act):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    lda = (K + 7) // 8 * 8
+    A = torch.zeros(M, lda, dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = torch.zeros(N, lda, dtype=torch.bfloat16)
+    W[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g).to(dev) if bias else None
+    R = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev) if res else None
+    A, W = A.to(dev), W.to(dev)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    outa = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev) if act else None
+    rc = _lib().wv_op_gemm(P(A), lda, P(W), lda, M, N, K, P(b), P(R), P(out), P(outa), 0.8, 0, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+    ref = A[:, :K].double() @ W[:, :K].double().t()
+    if bias:
+        ref = ref + b.double()
+    if res:
+        ref = ref + R.double()
+    ref = ref.float()
+    bf16_close(out, ref)
+    if act:
+        bf16_close(outa, F.elu(ref * 0.8), abs_=2e-3)
+
+
+def test_gemm_fp16_operands():
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    M, N, K = 3000, 128, 128
+    A = torch.randn(M, K, generator=g).half().to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(dev)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    rc = _lib().wv_op_gemm(P(A), K, P(W), K, M, N, K, None, None, P(out), None, 1.0, 1, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+    bf16_close(out, (A.double() @ W.double().t()).float())
+
+
+def _cl(x):  # [B,C,T] fp32 -> channels-last bf16 [B,T,C]
+    return x.transpose(1, 2).contiguous().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 1000, 64), (1, 7, 32), (3, 4097, 96), (1, 50, 1536), (2, 333, 384)])
+@pytest.mark.parametrize("mode", ["act", "res_both", "raw_nobias"])
+def test_dw5(B, T, C, mode):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T + C)
+    x = torch.randn(B, C, T, generator=g)
+    w = torch.randn(C, 1, 5, generator=g) * 0.4
+    b = None if mode == "raw_nobias" else torch.randn(C, generator=g)
+    r = torch.randn(B, C, T, generator=g) if mode == "res_both" else None
+    xin = _cl(x).to(dev)
+    wk = w[:, 0, :].t().contiguous().to(dev)             # [5][C]
+    out_raw = torch.empty(B, T, C, dtype=torch.bfloat16, device=dev) if mode != "act" else None
+    out_act = torch.empty(B, T, C, dtype=torch.bfloat16, device=dev) if mode != "raw_nobias" else None
+    rin = _cl(r).to(dev) if r is not None else None
+    rc = _lib().wv_op_dw5(P(xin), P(wk), P(b.to(dev)) if b is not None else None, P(rin), P(out_raw), P(out_act),
+                          0.7, B, T, C, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+    xq = xin.float().cpu().transpose(1, 2)
+    ref = F.conv1d(F.pad(xq, (4, 0)), w, b, groups=C)
+    if r is not None:
+        ref = ref + rin.float().cpu().transpose(1, 2)
+    ref = ref.transpose(1, 2)
+    if out_raw is not None:
+        bf16_close(out_raw.cpu(), ref)
+    if out_act is not None:
+        bf16_close(out_act.cpu(), F.elu(ref * 0.7), abs_=2e-3)
+
+
+@pytest.mark.parametrize("B,Tin,C,r", [(2, 1000, 128, 2), (1, 16001, 64, 4), (3, 401, 256, 5), (2, 77, 1024, 8), (1, 3, 64, 8)])
+@pytest.mark.parametrize("film", [False, True])
+def test_down_conv_film(B, Tin, C, r, film):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Tin + C + r)
+    x = torch.randn(B, C, Tin, generator=g)
+    w = torch.randn(C, 1, 2 * r, generator=g) * 0.3
+    b = torch.randn(C, generator=g)
+    xin = _cl(x).to(dev)
+    wk = w[:, 0, :].t().contiguous().to(dev)
+    To = -(-Tin // r)
+    ft = torch.randn(B, 3, 4, 2, generator=g) if film else None    # [B, scales, bands, 2]; use scale 1
+    out_raw = torch.empty(B, To, C, dtype=torch.bfloat16, device=dev)
+    out_act = torch.empty(B, To, C, dtype=torch.bfloat16, device=dev)
+    ftd = ft.to(dev) if film else None
+    fptr = C_void(ftd[:, 1]) if film else None
+    rc = _lib().wv_op_down(P(xin), P(wk), P(b.to(dev)), fptr, 3 * 4 * 2, 4, P(out_raw), P(out_act), 0.9,
+                           B, Tin, C, r, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+    xq = xin.float().cpu().transpose(1, 2)
+    extra = (To - 1) * r + 2 * r - r - Tin                       # modules/conv.py:160-203
+    ref = F.conv1d(F.pad(xq, (r, max(0, extra))), w, b, stride=r, groups=C)
+    assert ref.shape[-1] == To
+    if film:
+        gam = ft[:, 1, :, 0].repeat_interleave(C // 4, dim=1).unsqueeze(-1)
+        bet = ft[:, 1, :, 1].repeat_interleave(C // 4, dim=1).unsqueeze(-1)
+        ref = ref * gam + bet
+    ref = ref.transpose(1, 2)
+    bf16_close(out_raw.cpu(), ref, abs_=2e-3)
+    bf16_close(out_act.cpu(), F.elu(ref * 0.9), abs_=3e-3)
+
+
+def C_void(t):
+    # pointer to the first element of a (possibly strided) view
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("B,Tin,C,r", [(2, 50, 1536, 8), (1, 400, 768, 5), (2, 1001, 384, 4), (1, 8000, 192, 2), (1, 1, 96, 2)])
+def test_up_conv_transposed(B, Tin, C, r):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Tin + C + r)
+    x = torch.randn(B, C, Tin, generator=g)
+    w = torch.randn(C, 1, 2 * r, generator=g) * 0.3
+    xin = _cl(x).to(dev)
+    wk = w[:, 0, :].t().contiguous().to(dev)
+    out = torch.empty(B, Tin * r, C, dtype=torch.bfloat16, device=dev)
+    rc = _lib().wv_op_up(P(xin), P(wk), P(out), B, Tin, C, r, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+    xq = xin.float().cpu().transpose(1, 2)
+    ref = F.conv_transpose1d(xq, w, None, stride=r, groups=C)[..., : Tin * r]   # modules/conv.py:838-874
+    bf16_close(out.cpu(), ref.transpose(1, 2), abs_=2e-3)

@@ -1,0 +1,256 @@
+"""GPU: the CUDA path (through the Python shim -> C ABI) against (a) the committed outputs of
+the reference itself (tests/golden) and (b) the CPU oracle on fresh inputs, plus
+size-independent properties at the benchmark sizes.
+
+Stated tolerances (bf16 activations, fp32 accumulation, fp16 STFT operands; cf. BASELINE.md
+section 4 - PyTorch's own bf16 autocast of the reference reaches 31.5 dB on the residual):
+  watermark residual / watermarked audio : SNR >= 40 dB, max-abs <= 2e-3
+  latent                                 : SNR >= 38 dB
+  detector logits                        : SNR >= 40 dB, max-abs <= 0.3 ; avg prob max-abs <= 1.5e-3
+  locator logits                         : SNR >= 40 dB, max-abs <= 0.12
+  decoded bits                           : exact wherever |avg_ref - 0.5| > 2e-3 (guard band)
+  locator mask                           : exact wherever |logit_ref - 0.5| > 0.08; inside the
+                                           band at most 30 % of the in-band samples may differ
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import wv_oracle as O
+from helpers import BASE_KW, fixture_weights, golden_cases, load_case, oracle_cfg, snr_db
+
+pytestmark = pytest.mark.gpu
+CASES = golden_cases()
+_CACHE = {}
+
+
+def models(zero_init, seed):
+    key = (bool(zero_init), int(seed))
+    if key not in _CACHE:
+        from waveverify_b200 import Detector, Generator, Locator
+        dev = torch.device("cuda:0")
+        out = {}
+        for kind, cls in (("generator", Generator), ("detector", Detector), ("locator", Locator)):
+            c, sd = fixture_weights(kind, key[0], key[1])
+            m = cls(**{**BASE_KW[kind], "bias": True, "zero_init": key[0]})
+            m.load_state_dict(sd)
+            out[kind] = (m.to(dev), O.fold_state_dict(sd), oracle_cfg(c))
+        _CACHE[key] = out
+    return _CACHE[key]
+
+
+def check_wave(ref, got, what):
+    assert snr_db(ref, got) >= 40.0, f"{what}: snr {snr_db(ref, got):.1f} dB"
+    assert np.abs(ref - got).max() <= 2e-3, f"{what}: max-abs {np.abs(ref - got).max()}"
+
+
+def check_bits(avg_ref, bits_ref, avg, bits):
+    assert np.abs(avg - avg_ref).max() <= 1.5e-3
+    safe = np.abs(avg_ref - 0.5) > 2e-3
+    assert (bits == bits_ref)[safe].all()
+
+
+def check_mask(logit_ref, mask_ref, mask):
+    safe = np.abs(logit_ref - 0.5) > 0.08
+    assert (mask == mask_ref)[safe].all(), "mask differs outside the guard band"
+    band = ~safe
+    if band.sum() > 50:
+        assert (mask != mask_ref)[band].mean() <= 0.30
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_cuda_path_matches_reference_golden(path):
+    z = load_case(path)
+    m = models(z["zero_init"], z["wseed"])
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(z["x"]).to(dev); msg = torch.from_numpy(z["msg"]).to(dev)
+    wm, y, lat = m["generator"][0].embed_batch(x, msg, want_latent=True)
+    check_wave(z["wm"], wm.cpu().numpy(), "wm")
+    check_wave(z["y"], y.cpu().numpy(), "y")
+    assert torch.equal(y, x + wm)            # fused add is the same fp32 add
+    assert snr_db(z["latent"], lat.cpu().numpy()) >= 38.0
+    yg = torch.from_numpy(z["y"]).to(dev)
+    d = m["detector"][0].detect_batch(yg, want_logits=True)
+    dd = int(z["det_decim"])
+    lg = d["logits"][:, :, ::dd].cpu().numpy()
+    assert snr_db(z["det_logits_decim"], lg) >= 40.0
+    assert np.abs(lg - z["det_logits_decim"]).max() <= 0.3
+    check_bits(z["det_avg"], z["det_bits"], d["avg"].cpu().numpy(), d["bits"].cpu().numpy())
+    np.testing.assert_allclose(d["conf"].cpu().numpy(), z["det_conf"], atol=1e-3)
+    assert bool(d["valid"].all())
+    l = m["locator"][0].locate_batch(yg, want_logits=True, want_probs=True)
+    ll = l["logits"].cpu().numpy()
+    assert snr_db(z["loc_logits"], ll) >= 40.0
+    assert np.abs(ll - z["loc_logits"]).max() <= 0.12
+    check_mask(z["loc_logits"], z["loc_mask"], l["mask"].cpu().numpy())
+    # fused outputs are consistent with the logits the same launch wrote
+    assert torch.equal(l["mask"], (l["logits"] > 0.5).to(torch.uint8))
+    np.testing.assert_allclose(l["probs"].cpu().numpy(), 1 / (1 + np.exp(-ll.astype(np.float64))), atol=2e-6)
+    assert (m["detector"][0].postprocess(d["logits"]).cpu().numpy() == z["det_post"]).all()
+
+
+def test_cuda_path_matches_oracle_fresh_batch():
+    """B=8 x 1 s, new inputs: same checks against the oracle (pinned to the reference by
+    tests/test_oracle_golden.py)."""
+    m = models(False, 0)
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(99)
+    B, T = 8, 16000
+    x = torch.from_numpy((0.1 * rng.standard_normal((B, 1, T))).astype(np.float32))
+    msg = torch.from_numpy(rng.randint(0, 2, (B, 16)).astype(np.int64))
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        wm_o = O.generator_forward(x, msg, m["generator"][1], m["generator"][2])
+    wm, y, _ = m["generator"][0].embed_batch(x.to(dev), msg.to(dev))
+    check_wave(wm_o.numpy(), wm.cpu().numpy(), "wm")
+    yc = y.cpu()
+    with torch.no_grad():
+        lg_o = O.detector_forward(yc, m["detector"][1], m["detector"][2])
+        ll_o = O.locator_forward(yc, m["locator"][1], m["locator"][2])
+    bits_o, avg_o, conf_o, _ = O.decode_bits(lg_o)
+    d = m["detector"][0].detect_batch(y, want_logits=True)
+    assert snr_db(lg_o.numpy(), d["logits"].cpu().numpy()) >= 40.0
+    check_bits(avg_o.numpy(), bits_o.numpy(), d["avg"].cpu().numpy(), d["bits"].cpu().numpy())
+    l = m["locator"][0].locate_batch(y, want_logits=True)
+    assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 40.0
+    check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy())
+
+
+def test_masked_bit_decode_and_metric_counters():
+    """scripts/evaluate.py:442-516 (masked BER) and :591-665 (MIoU) semantics, incl. an all-zero mask."""
+    from waveverify_b200 import ber_miou, metric_counters
+    m = models(False, 0)
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(5)
+    B, T = 4, 8000
+    y = torch.from_numpy((0.1 * rng.standard_normal((B, 1, T))).astype(np.float32))
+    msg = torch.from_numpy(rng.randint(0, 2, (B, 16)).astype(np.int64))
+    pres = torch.zeros(B, 1, T, dtype=torch.uint8)
+    pres[0, :, :] = 1
+    pres[1, :, 1000:5000] = 1
+    pres[2, :, 7999:] = 1                     # single valid sample
+    # clip 3: empty mask -> no valid bits
+    with torch.no_grad():
+        lg_o = O.detector_forward(y, m["detector"][1], m["detector"][2])
+        ll_o = O.locator_forward(y, m["locator"][1], m["locator"][2])
+    bits_o, avg_o, conf_o, valid_o = O.decode_bits(lg_o, pres)
+    d = m["detector"][0].detect_batch(y.to(dev), presence=pres.to(dev))
+    assert (d["valid"].cpu().numpy().astype(bool) == valid_o.numpy()).all()
+    v = valid_o.numpy()
+    assert np.abs(d["avg"].cpu().numpy() - avg_o.numpy())[v].max() <= 3e-3
+    assert np.abs(d["avg"].cpu().numpy())[~v].max() == 0.0
+    safe = v & (np.abs(avg_o.numpy() - 0.5) > 4e-3)
+    assert (d["bits"].cpu().numpy() == bits_o.numpy())[safe].all()
+    # counters: feed identical bits/masks to both sides -> integers must be EXACT
+    l = m["locator"][0].locate_batch(y.to(dev))
+    gt = torch.from_numpy(rng.randint(0, 2, (B, 1, T)).astype(np.uint8))
+    c = metric_counters(d["bits"], d["valid"], msg.to(dev), l["mask"], gt.to(dev))
+    c_o = O.metric_counters(d["bits"].cpu(), d["valid"].cpu().bool(), msg, l["mask"].cpu(), gt)
+    assert c.tolist() == c_o
+    assert ber_miou(c) == O.ber_miou_from_counters(c_o)
+    c2 = metric_counters(d["bits"], d["valid"], msg.to(dev), l["mask"], gt.to(dev), counters=c.clone())
+    assert c2.tolist() == [2 * v_ for v_ in c_o]            # accumulation is additive
+
+
+def test_batch_independence_bit_exact():
+    """Clips are independent units: a clip embedded inside a 64-clip batch equals the same clip
+    embedded alone, bit for bit (same per-row arithmetic regardless of tile position)."""
+    m = models(False, 0)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    B, T = 64, 16000
+    x = (0.1 * torch.randn(B, 1, T, generator=g)).to(dev)
+    msg = torch.randint(0, 2, (B, 16), generator=g).to(dev)
+    wm, y, _ = m["generator"][0].embed_batch(x, msg)
+    d = m["detector"][0].detect_batch(y, want_logits=True)
+    l = m["locator"][0].locate_batch(y, want_logits=True)
+    for b in (0, 17, 63):
+        wm1, y1, _ = m["generator"][0].embed_batch(x[b:b + 1], msg[b:b + 1])
+        assert torch.equal(wm1, wm[b:b + 1])
+        d1 = m["detector"][0].detect_batch(y[b:b + 1], want_logits=True)
+        assert torch.equal(d1["logits"], d["logits"][b:b + 1])
+        assert torch.equal(d1["bits"], d["bits"][b:b + 1])
+        l1 = m["locator"][0].locate_batch(y[b:b + 1], want_logits=True)
+        assert torch.equal(l1["logits"], l["logits"][b:b + 1])
+    # sub-batching (set_chunk_samples) is invisible in the results
+    gen = m["generator"][0]
+    gen.set_chunk_samples(10 * T)
+    wm_c, _, _ = gen.embed_batch(x, msg)
+    gen.set_chunk_samples(0)
+    assert torch.equal(wm_c, wm)
+
+
+def test_causality_prefix_property():
+    """All convs are causal with zero left padding: the output up to t < T1 depends only on
+    x[:T1].  With T1 a multiple of the hop the prefix of a long clip equals the short clip exactly."""
+    m = models(True, 1)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(12)
+    T, T1 = 48000, 16000
+    x = (0.1 * torch.randn(2, 1, T, generator=g)).to(dev)
+    msg = torch.randint(0, 2, (2, 16), generator=g).to(dev)
+    wm, _, _ = m["generator"][0].embed_batch(x, msg)
+    wm1, _, _ = m["generator"][0].embed_batch(x[:, :, :T1].contiguous(), msg)
+    assert torch.equal(wm[:, :, :T1], wm1)
+    l = m["locator"][0].locate_batch(x, want_logits=True)["logits"]
+    l1 = m["locator"][0].locate_batch(x[:, :, :T1].contiguous(), want_logits=True)["logits"]
+    assert torch.equal(l[:, :, :T1], l1)
+
+
+def test_reference_api_surface():
+    """Forward signatures / return types / error behaviour of the reference classes."""
+    from waveverify_b200 import AudioSignal, AudioWatermarking
+    m = models(False, 0)
+    dev = torch.device("cuda:0")
+    G, D, L = m["generator"][0], m["detector"][0], m["locator"][0]
+    x = 0.1 * torch.randn(2, 1, 4000, device=dev)
+    msg = torch.randint(0, 2, (2, 16))                       # long, on CPU: moved + cast like the reference
+    sig = AudioSignal(x, 16000)
+    wm_sig = G(sig, msg)
+    assert isinstance(wm_sig, AudioSignal) and wm_sig.audio_data.shape == x.shape and wm_sig.sample_rate == 16000
+    assert float(wm_sig.audio_data.abs().max()) <= 1.0
+    with pytest.raises(RuntimeError, match="Forward pass failed"):
+        G(x, msg)                                            # not an AudioSignal (generator.py:383, 421)
+    model = AudioWatermarking(G, D, L)
+    wm2, y2 = model(sig, msg, phase="audio_sample")
+    assert torch.equal(wm2.audio_data, wm_sig.audio_data)
+    assert torch.equal(y2.audio_data, x + wm2.audio_data)
+    with pytest.raises(NotImplementedError):
+        model(sig, msg, phase="train")
+    logits = D(y2)
+    assert logits.shape == (2, 16, 4000) and logits.dtype == torch.float32
+    assert D.detect(y2).shape == (2, 16)
+    loc = L(y2)
+    assert loc.shape == (2, 1, 4000)
+    z = G.encode(x, msg)
+    assert z.shape == (2, 128, 13)
+    np.testing.assert_allclose(z.pow(2).sum(1).sqrt().cpu().numpy(), np.sqrt(128.0), rtol=2e-2)
+    wav = G.decode(z)
+    assert wav.shape == (2, 1, 13 * 320)
+    # decode(encode(x)) is forward() before the trim, up to bf16 rounding of z
+    assert snr_db(wm_sig.audio_data.cpu().numpy(), wav[:, :, :4000].cpu().numpy()) > 35
+    with pytest.raises(RuntimeError):
+        G.embed_batch(x.cpu(), msg)                          # no CPU fallback
+    with pytest.raises(ValueError):
+        G.embed_batch(x[:, :, :0], msg)                      # empty clip
+
+
+def test_large_batch_config2_shapes_and_sanity():
+    """BASELINE config 2 size (64 x 1 s) through the whole path; results are finite, bounded, and
+    the decoded bits agree with the bits decoded from the materialised logits."""
+    m = models(False, 0)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    B, T = 64, 16000
+    x = (0.1 * torch.randn(B, 1, T, generator=g)).to(dev)
+    msg = torch.randint(0, 2, (B, 16), generator=g).to(dev)
+    wm, y, _ = m["generator"][0].embed_batch(x, msg)
+    assert torch.isfinite(wm).all() and float(wm.abs().max()) <= 1.0
+    d = m["detector"][0].detect_batch(y, want_logits=True)
+    avg = torch.sigmoid(d["logits"].double()).mean(dim=2)
+    assert float((avg - d["avg"].double()).abs().max()) < 2e-6
+    safe = (avg - 0.5).abs() > 1e-5
+    assert bool(((avg >= 0.5).to(torch.uint8) == d["bits"])[safe].all())
+    np.testing.assert_allclose(d["conf"].cpu().numpy(), avg.mean(dim=1).cpu().numpy(), atol=1e-6)

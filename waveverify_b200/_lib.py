@@ -53,6 +53,12 @@ _SIGS = {
     "wv_metrics_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                         C.c_void_p]),
+    "wv_net_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "wv_net_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "wv_net_profile_tag": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "wv_debug_tap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                               C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "wv_op_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
                              C.c_void_p]),

@@ -273,7 +273,8 @@ GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias) {
 }
 
 // depthwise [C,1,k] -> [k][C]; transposed conv weights have the same memory shape
-DwW depthwise(Weights& W, const std::string& p, float scale, bool with_bias) {
+DwW depthwise(Weights& W, const std::string& p, float scale, bool with_bias, float bias_scale = -1.f) {
+  if (bias_scale < 0.f) bias_scale = scale;
   const HostTensor& t = W.get(p + ".weight");
   if (t.shape.size() != 3 || t.shape[1] != 1)
     WV_THROW(WV_ERR_INVALID, "'%s.weight' is not depthwise", p.c_str());
@@ -287,7 +288,7 @@ DwW depthwise(Weights& W, const std::string& p, float scale, bool with_bias) {
   const HostTensor* b = with_bias ? W.find(p + ".bias") : nullptr;
   if (b) {
     std::vector<float> bb(b->data, b->data + d.C);
-    for (auto& v : bb) v *= scale;
+    for (auto& v : bb) v *= bias_scale;
     d.bias = W.dev.upload(bb);
   }
   return d;
@@ -413,11 +414,16 @@ struct Op {
   float fa = 0.f, fb = 0.f;
   int i[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   FilmArgs fargs;
+  // bookkeeping for taps / profiling
+  std::string tag;
+  double flops = 0, bytes = 0;      // algorithmic work of this launch
+  size_t out_bytes[2] = {0, 0};
 };
 
 struct Plan {
   int B = 0, T = 0;
   std::vector<Op> ops;
+  std::vector<cudaEvent_t> events;   // profiling: ops.size() + 1 events
   size_t ws_bytes = 0;
   Buf latent;          // bf16 [B*F, dim]
   int F = 0;
@@ -428,6 +434,16 @@ struct PlanCtx {
   uint8_t* base = nullptr;   // nullptr => sizing pass (no tensor maps encoded)
   std::vector<Op>* ops = nullptr;
   int B = 0, T = 0;
+  std::string next_tag;
+  void push(Op& op) {
+    op.tag = next_tag;
+    next_tag.clear();
+    ops->push_back(op);
+  }
+  PlanCtx& tag(const std::string& t) {
+    next_tag = t;
+    return *this;
+  }
   Buf alloc(size_t bytes) {
     Buf b;
     b.bytes = bytes;
@@ -472,9 +488,24 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   }
   op.tmB = w.tm;
   op.g = g;
+  op.out0 = g.out_raw;
+  op.out1 = g.out_act;
   const int tiles = ceil_div(g.rows_per_clip, BM) * g.n_clips * (w.N / w.block_n);
   op.grid = std::min(tiles, g_num_sms);
-  c.ops->push_back(op);
+  {
+    const double Mt = static_cast<double>(g.rows_per_clip) * g.n_clips;
+    op.flops = 2.0 * Mt * w.N * K;
+    double outs = 0;
+    if (epi == EPI_STFT) outs = Mt * (w.N / 2 + 1) * 2;
+    else if (epi == EPI_HEAD) outs = 0;   // logits / mask bytes are caller dependent, added at run time
+    else outs = Mt * w.N * 2.0 * ((g.out_raw ? 1 : 0) + (g.out_act ? 1 : 0));
+    // the strided STFT frame view re-reads each sample n_fft/hop times from L2; algorithmic = once
+    const double a_bytes = custom_tmA ? Mt * 2.0 * std::min<double>(K, 64) : Mt * K * 2.0;
+    op.bytes = a_bytes + outs + (g.residual ? Mt * w.N * 2.0 : 0.0) + static_cast<double>(w.N) * K * 2.0;
+    op.out_bytes[0] = g.out_raw ? static_cast<size_t>(Mt) * g.ldo * 2 : 0;
+    op.out_bytes[1] = g.out_act ? static_cast<size_t>(Mt) * g.ldo * 2 : 0;
+  }
+  c.push(op);
 }
 
 GemmArgs std_args(const float* bias, const bf16* res, bf16* out_raw, bf16* out_act, float act_scale, int ldo) {
@@ -493,27 +524,36 @@ void add_dw5(PlanCtx& c, const DwW& w, const bf16* in, const bf16* res, bf16* ou
   op.w = w.w; op.bias = w.bias; op.fa = act_scale;
   op.i[0] = c.B; op.i[1] = T; op.i[2] = C;
   op.grid = elem_grid(static_cast<long long>(c.B) * ceil_div(T, DW_TT) * (C / 8));
-  c.ops->push_back(op);
+  const double n = static_cast<double>(c.B) * T * C;
+  op.flops = 10.0 * n;
+  op.bytes = 2.0 * n * (1 + (res ? 1 : 0) + (out_raw ? 1 : 0) + (out_act ? 1 : 0));
+  op.out_bytes[0] = out_raw ? static_cast<size_t>(n) * 2 : 0;
+  op.out_bytes[1] = out_act ? static_cast<size_t>(n) * 2 : 0;
+  c.push(op);
 }
 
 // One residual block (modules/seanet.py:245-281).  X raw (residual), A = ELU(X*pre_scale).
 // Produces Xn (raw, if need_raw) and An = ELU(Xn*next_act_scale) (if need_act); frees X and A.
 void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool need_raw, bool need_act,
-                   float next_act_scale, Buf& Xn, Buf& An) {
+                   float next_act_scale, Buf& Xn, Buf& An, const std::string& name) {
   const long long M = static_cast<long long>(c.B) * T;
   const size_t bytes = static_cast<size_t>(M) * C * 2;
   Buf G1 = c.alloc(bytes);
+  c.tag(name + ".pw1");
   add_gemm(c, EPI_STD, r.pw1, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G1), nullptr, 1.f, C));
   c.release(A);
   Buf A2 = c.alloc(bytes);
+  c.tag(name + ".dw1");
   add_dw5(c, r.dw1, c.ptr<bf16>(G1), nullptr, nullptr, c.ptr<bf16>(A2), 1.f, T, C);
   c.release(G1);
   Buf G2 = c.alloc(bytes);
+  c.tag(name + ".pw2");
   add_gemm(c, EPI_STD, r.pw2, c.ptr<bf16>(A2), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G2), nullptr, 1.f, C));
   c.release(A2);
   Xn = Buf(); An = Buf();
   if (need_raw) Xn = c.alloc(bytes);
   if (need_act) An = c.alloc(bytes);
+  c.tag(name + ".out");
   add_dw5(c, r.dw2, c.ptr<bf16>(G2), c.ptr<bf16>(X), need_raw ? c.ptr<bf16>(Xn) : nullptr,
           need_act ? c.ptr<bf16>(An) : nullptr, next_act_scale, T, C);
   c.release(G2);
@@ -522,7 +562,7 @@ void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool
 
 struct Net;
 void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, Buf& X,
-               int C, float act_scale, Buf& Aout);
+               int C, float act_scale, Buf& Aout, const std::string& name);
 
 }  // namespace
 
@@ -539,7 +579,11 @@ struct wv_net {
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
   long long chunk_samples = 0;
+  bool profile = false;
+  const Plan* last_plan = nullptr;   // plan whose events hold the last profiled run
   ~wv_net() {
+    for (auto& kv : plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
+    for (auto& kv : dec_plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
     if (ws) cudaFree(ws);
   }
 };
@@ -554,7 +598,8 @@ void build_encoder_w(wv_net& n) {
   const float rs = cf.res_scale_enc;
   e.C0 = cf.channels_enc;
   e.dim = cf.dimension;
-  e.conv_pre = depthwise(W, p + ".conv_pre.1.conv.conv", 1.f / WAV_STD, true);   // seanet.py:658
+  // x/wav_std feeds the conv (seanet.py:658): fold into the taps, NOT into the bias
+  e.conv_pre = depthwise(W, p + ".conv_pre.1.conv.conv", 1.f / WAV_STD, true, 1.f);
   if (e.conv_pre.k != 5) WV_THROW(WV_ERR_UNSUPPORTED, "conv_pre kernel size %d (only 5)", e.conv_pre.k);
   if (!e.conv_pre.bias) WV_THROW(WV_ERR_MISSING_WEIGHT, "conv_pre bias missing (bias=True required)");
   int C = e.C0, nfft = cf.n_fft_base, hop = 1;
@@ -689,7 +734,7 @@ void build_head_w(wv_net& n) {
 
 // STFT branch + 1x1 + residual add (modules/seanet.py:463-507): Aout = ELU((X + spec) * act_scale)
 void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, Buf& X,
-               int C, float act_scale, Buf& Aout) {
+               int C, float act_scale, Buf& Aout, const std::string& name) {
   const long long M = static_cast<long long>(c.B) * F;
   const int K2 = s.n_fft / 2 + 1;
   const int ldy = static_cast<int>(round_up(K2, 8));
@@ -707,6 +752,7 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
     CUtensorMap tm;
     if (!c.dry())
       tm = make_tmap(c.ptr<__half>(wav16) + base, 3, s.n_fft, F, c.B, s.hop, pitch, BK, BM, true);
+    c.tag(name + ".stft");
     add_gemm(c, EPI_STFT, s.dft, nullptr, 0, 0, s.n_fft, g, &tm, F, c.B);
   } else {
     Buf FR = c.alloc(static_cast<size_t>(M) * s.n_fft * 2);
@@ -715,11 +761,16 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
     op.in = c.ptr<__half>(wav16); op.out0 = c.ptr<__half>(FR);
     op.i[0] = c.B; op.i[1] = F; op.i[2] = s.hop; op.i[3] = s.n_fft; op.i[4] = base; op.i[5] = pitch;
     op.grid = elem_grid(M * (s.n_fft / 8));
-    c.ops->push_back(op);
+    op.bytes = static_cast<double>(M) * s.n_fft * 2.0 + static_cast<double>(c.B) * pitch * 2.0;
+    op.out_bytes[0] = static_cast<size_t>(M) * s.n_fft * 2;
+    c.tag(name + ".frames");
+    c.push(op);
+    c.tag(name + ".stft");
     add_gemm(c, EPI_STFT, s.dft, c.ptr<__half>(FR), s.n_fft, M, s.n_fft, g);
     c.release(FR);
   }
   Aout = c.alloc(static_cast<size_t>(M) * C * 2);
+  c.tag(name + ".out");
   add_gemm(c, EPI_STD, s.layer, c.ptr<bf16>(Y), ldy, M, K2,
            std_args(nullptr, c.ptr<bf16>(X), nullptr, c.ptr<bf16>(Aout), act_scale, C));
   c.release(Y);
@@ -740,7 +791,10 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     op.fa = WAV_FP16_SCALE;
     op.i[0] = B; op.i[1] = T; op.i[2] = lead; op.i[3] = pitch;
     op.grid = elem_grid(static_cast<long long>(B) * pitch);
-    c.ops->push_back(op);
+    op.bytes = static_cast<double>(B) * (T * 4.0 + pitch * 2.0);
+    op.out_bytes[0] = static_cast<size_t>(B) * pitch * 2;
+    c.tag("enc.wav16");
+    c.push(op);
   }
   Buf film;
   if (e.has_film) {
@@ -750,7 +804,9 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     op.out0 = c.ptr<float>(film);
     op.fargs = e.film;
     op.i[0] = B;
-    c.ops->push_back(op);
+    op.out_bytes[0] = static_cast<size_t>(B) * e.n_film * 2 * 4;
+    c.tag("enc.film");
+    c.push(op);
   }
   int Ts = T, C = e.C0;
   Buf X = c.alloc(static_cast<size_t>(B) * Ts * C * 2), A = c.alloc(static_cast<size_t>(B) * Ts * C * 2);
@@ -762,7 +818,11 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     op.fa = e.stages[0].res[0].pre_scale;
     op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
     op.grid = elem_grid(static_cast<long long>(B) * Ts * (C / 8));
-    c.ops->push_back(op);
+    op.flops = 10.0 * B * Ts * C;
+    op.bytes = static_cast<double>(B) * Ts * (4.0 + 4.0 * C);
+    op.out_bytes[0] = op.out_bytes[1] = static_cast<size_t>(B) * Ts * C * 2;
+    c.tag("enc.pre");
+    c.push(op);
   }
   const float down_scale = 1.f / std::sqrt(1.f + n.cfg.n_residual_enc * n.cfg.res_scale_enc * n.cfg.res_scale_enc);
   const int S = static_cast<int>(e.stages.size());
@@ -772,12 +832,14 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     for (int j = 0; j < nres; ++j) {
       const bool last = j == nres - 1;
       Buf Xn, An;
-      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An);
+      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An,
+                    "enc.s" + std::to_string(s) + ".r" + std::to_string(j));
       X = Xn; A = An;
     }
-    plan_spec(c, st.spec, wav16, pitch, lead, Ts, X, C, down_scale, A);   // A = ELU((x+spec)*scale)
+    plan_spec(c, st.spec, wav16, pitch, lead, Ts, X, C, down_scale, A, "enc.s" + std::to_string(s) + ".spec");   // A = ELU((x+spec)*scale)
     const long long M = static_cast<long long>(B) * Ts;
     Buf G = c.alloc(static_cast<size_t>(M) * 2 * C * 2);
+    c.tag("enc.s" + std::to_string(s) + ".down_pw");
     add_gemm(c, EPI_STD, st.down_pw, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, 2 * C));
     c.release(A);
     const int To = ceil_div(Ts, st.r);
@@ -793,23 +855,30 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
       op.fa = last_stage ? 1.f : e.stages[s + 1].res[0].pre_scale;
       op.i[0] = B; op.i[1] = Ts; op.i[2] = To; op.i[3] = 2 * C; op.i[4] = st.r; op.i[5] = e.n_film * 2; op.i[6] = e.bands;
       op.grid = elem_grid(static_cast<long long>(B) * To * (2 * C / 8));
-      c.ops->push_back(op);
+      op.flops = 2.0 * 2 * st.r * B * To * 2.0 * C;
+      op.bytes = 2.0 * (static_cast<double>(M) * 2 * C + static_cast<double>(B) * To * 2 * C * (last_stage ? 1 : 2));
+      op.out_bytes[0] = static_cast<size_t>(B) * To * 2 * C * 2;
+      op.out_bytes[1] = last_stage ? 0 : op.out_bytes[0];
+      c.tag("enc.s" + std::to_string(s) + ".down");
+      c.push(op);
     }
     c.release(G);
     Ts = To; C *= 2;
   }
   plan.F = Ts;
-  plan_spec(c, e.spec_post, wav16, pitch, lead, Ts, X, C, 1.f, A);         // ELU(x + spec)
+  plan_spec(c, e.spec_post, wav16, pitch, lead, Ts, X, C, 1.f, A, "enc.post.spec");         // ELU(x + spec)
   c.release(wav16);
   if (film.valid) c.release(film);
   const long long M = static_cast<long long>(B) * Ts;
   Buf D = c.alloc(static_cast<size_t>(M) * C * 2);
+  c.tag("enc.post.dw");
   add_dw5(c, e.post_dw, c.ptr<bf16>(A), nullptr, c.ptr<bf16>(D), nullptr, 1.f, Ts, C);
   c.release(A);
   plan.latent = c.alloc(static_cast<size_t>(M) * e.dim * 2);
   GemmArgs g = std_args(e.post_pw.bias, nullptr, c.ptr<bf16>(plan.latent), nullptr, 1.f, e.dim);
   g.l2_scale = std::sqrt(static_cast<float>(e.dim));                         // seanet.py:299
   g.f32_F = Ts;
+  c.tag("enc.latent");
   add_gemm(c, EPI_L2NORM, e.post_pw, c.ptr<bf16>(D), C, M, C, g);
   c.release(D);
 }
@@ -821,8 +890,10 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
   int Ts = F, C = d.pw0.N;
   long long M = static_cast<long long>(B) * Ts;
   Buf G = c.alloc(static_cast<size_t>(M) * C * 2);
+  c.tag("dec.pw0");
   add_gemm(c, EPI_STD, d.pw0, c.ptr<bf16>(Z), d.pw0.K, M, d.pw0.K, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, C));
   Buf A = c.alloc(static_cast<size_t>(M) * C * 2);
+  c.tag("dec.dw0");
   add_dw5(c, d.dw0, c.ptr<bf16>(G), nullptr, nullptr, c.ptr<bf16>(A), 1.f, Ts, C);   // ELU of stage 0
   c.release(G);
   for (size_t s = 0; s < d.stages.size(); ++s) {
@@ -835,7 +906,11 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
       op.in = c.ptr<bf16>(A); op.out0 = c.ptr<bf16>(U); op.w = st.up.w;
       op.i[0] = B; op.i[1] = Ts; op.i[2] = C; op.i[3] = st.r;
       op.grid = elem_grid(static_cast<long long>(B) * Ts * (C / 8));
-      c.ops->push_back(op);
+      op.flops = 4.0 * B * To * C;
+      op.bytes = 2.0 * B * (static_cast<double>(Ts) + To) * C;
+      op.out_bytes[0] = static_cast<size_t>(B) * To * C * 2;
+      c.tag("dec.u" + std::to_string(s) + ".up");
+      c.push(op);
     }
     c.release(A);
     Ts = To;
@@ -843,6 +918,7 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     const int Ch = C / 2;
     Buf X = c.alloc(static_cast<size_t>(M) * Ch * 2);
     A = c.alloc(static_cast<size_t>(M) * Ch * 2);
+    c.tag("dec.u" + std::to_string(s) + ".halve");
     add_gemm(c, EPI_STD, st.halve, c.ptr<bf16>(U), C, M, C,
              std_args(st.halve.bias, nullptr, c.ptr<bf16>(X), c.ptr<bf16>(A), st.res.empty() ? d.stage_scale : st.res[0].pre_scale, Ch));
     c.release(U);
@@ -851,7 +927,8 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     for (int j = 0; j < nres; ++j) {
       const bool last = j == nres - 1;
       Buf Xn, An;
-      plan_resblock(c, st.res[j], X, A, Ts, C, !last, true, last ? d.stage_scale : st.res[j + 1].pre_scale, Xn, An);
+      plan_resblock(c, st.res[j], X, A, Ts, C, !last, true, last ? d.stage_scale : st.res[j + 1].pre_scale, Xn, An,
+                    "dec.u" + std::to_string(s) + ".r" + std::to_string(j));
       X = Xn; A = An;
     }
     if (nres == 0) c.release(X);
@@ -862,7 +939,10 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     op.in = c.ptr<bf16>(A); op.w = d.last_w; op.fa = d.last_b;
     op.i[0] = B; op.i[1] = Ts; op.i[2] = T_out; op.i[3] = C;
     op.grid = B * ceil_div(T_out, CL_TILE);
-    c.ops->push_back(op);
+    op.flops = 2.0 * 5 * C * B * T_out;
+    op.bytes = static_cast<double>(B) * T_out * (2.0 * C + 12.0);
+    c.tag("dec.last");
+    c.push(op);
   }
   c.release(A);
 }
@@ -877,17 +957,20 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   g.bias = h.w.bias;
   g.partial = c.ptr<float>(partial);
   g.hop = h.hop; g.T = c.T; g.n_out = h.n_out; g.head_F = F;
+  c.tag("head.gemm");
   add_gemm(c, EPI_HEAD, h.w, c.ptr<bf16>(Z), h.w.K, M, h.w.K, g);
   {
     Op op;
     op.type = OP_BITS;
     op.in = c.ptr<float>(partial);
     op.i[0] = c.B; op.i[1] = F; op.i[2] = tiles_n; op.i[3] = h.hop / h.w.block_n; op.i[4] = c.T; op.i[5] = h.n_out;
-    c.ops->push_back(op);
+    c.tag("head.bits");
+    c.push(op);
     Op op2;
     op2.type = OP_CONF;
     op2.i[0] = c.B; op2.i[1] = h.n_out;
-    c.ops->push_back(op2);
+    c.tag("head.conf");
+    c.push(op2);
   }
   c.release(partial);
 }
@@ -904,6 +987,9 @@ void build_plan_pass(wv_net& n, Plan& plan, uint8_t* base) {
 
 void ensure_ws(wv_net& n, size_t bytes) {
   if (bytes <= n.ws_bytes) return;
+  n.last_plan = nullptr;
+  for (auto& kv : n.plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
+  for (auto& kv : n.dec_plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
   // the workspace moves: every cached plan holds pointers/tensor maps into the old one
   n.plans.clear();
   n.dec_plans.clear();
@@ -941,7 +1027,7 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
     op.out0 = c.ptr<bf16>(plan.latent);
     op.i[0] = B; op.i[1] = n.enc.dim; op.i[2] = F;
     op.grid = elem_grid(static_cast<long long>(B) * F * n.enc.dim);
-    c.ops->push_back(op);
+    c.push(op);
     plan_decoder(c, n, plan.latent, F, F * n.enc.hop);
     plan.ws_bytes = c.arena.high;
   };
@@ -964,8 +1050,20 @@ void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
   }
 }
 
-void run_plan(wv_net& n, const Plan& plan, const IoPtrs& io, cudaStream_t st) {
+void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop_after = -1) {
+  const bool prof = n.profile;
+  if (prof) {
+    while (plan.events.size() < plan.ops.size() + 1) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      plan.events.push_back(ev);
+    }
+    CK(cudaEventRecord(plan.events[0], st));
+    n.last_plan = &plan;
+  }
+  int op_index = -1;
   for (const Op& op : plan.ops) {
+    ++op_index;
     switch (op.type) {
       case OP_GEMM: {
         GemmArgs g = op.g;
@@ -1019,6 +1117,8 @@ void run_plan(wv_net& n, const Plan& plan, const IoPtrs& io, cudaStream_t st) {
         latent_in_kernel<<<op.grid, 256, 0, st>>>(io.z_in, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2]);
         break;
     }
+    if (prof) CK(cudaEventRecord(plan.events[op_index + 1], st));
+    if (op_index == stop_after) break;
   }
   CK(cudaGetLastError());
 }
@@ -1224,6 +1324,67 @@ int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8
     metrics_kernel<<<elem_grid(work), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         bits, valid, msg_bits, nb, pred_mask, gt_mask, n_mask, reinterpret_cast<unsigned long long*>(counters));
     CK(cudaGetLastError());
+  });
+}
+
+// ---- profiling / debugging -----------------------------------------------------------------
+int wv_net_set_profile(wv_net* net, int enable) {
+  if (!net) return fail(WV_ERR_INVALID, "null net");
+  net->profile = enable != 0;
+  return WV_OK;
+}
+
+// After a profiled forward (single sub-batch): per-op device time (ms), algorithmic flops/bytes,
+// op class (OpType, GEMMs: 100 + epilogue id).  Returns the number of ops, or a negative code.
+int wv_net_profile_read(wv_net* net, int max_ops, float* ms, double* flops, double* bytes, int* cls) {
+  if (!net || !net->last_plan) return fail(WV_ERR_INVALID, "no profiled run");
+  int count = 0;
+  int rc = guarded([&] {
+    const Plan& p = *net->last_plan;
+    CK(cudaEventSynchronize(p.events[p.ops.size()]));
+    count = static_cast<int>(std::min<size_t>(p.ops.size(), static_cast<size_t>(max_ops)));
+    for (int i = 0; i < count; ++i) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, p.events[i], p.events[i + 1]));
+      ms[i] = t;
+      flops[i] = p.ops[i].flops;
+      bytes[i] = p.ops[i].bytes;
+      cls[i] = p.ops[i].type == OP_GEMM ? 100 + p.ops[i].epi : static_cast<int>(p.ops[i].type);
+    }
+  });
+  return rc == WV_OK ? count : rc;
+}
+
+const char* wv_net_profile_tag(wv_net* net, int i) {
+  if (!net || !net->last_plan || i < 0 || i >= static_cast<int>(net->last_plan->ops.size())) return "";
+  return net->last_plan->ops[i].tag.c_str();
+}
+
+// Run the plan up to (and including) the op tagged `tag` and copy its output buffer `which`
+// (0 = raw, 1 = activated) to dst (device or host pointer).  Test / debug only.
+int wv_debug_tap(wv_net* net, const float* x, const float* msg, int B, int T, const char* tag, int which,
+                 void* dst, size_t dst_bytes, size_t* written) {
+  if (!net || !x || !tag || !dst) return fail(WV_ERR_INVALID, "bad arguments to wv_debug_tap");
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    const long long saved = net->chunk_samples;
+    net->chunk_samples = 0;
+    Plan& plan = get_plan(*net, B, T);
+    net->chunk_samples = saved;
+    int idx = -1;
+    for (size_t i = 0; i < plan.ops.size(); ++i)
+      if (plan.ops[i].tag == tag) idx = static_cast<int>(i);
+    if (idx < 0) WV_THROW(WV_ERR_INVALID, "no op tagged '%s'", tag);
+    const Op& op = plan.ops[idx];
+    const void* src = which ? op.out1 : op.out0;
+    const size_t nbytes = std::min(dst_bytes, op.out_bytes[which ? 1 : 0]);
+    if (!src || nbytes == 0) WV_THROW(WV_ERR_INVALID, "op '%s' has no output %d", tag, which);
+    IoPtrs io;
+    io.x = x; io.msg = msg;
+    run_plan(*net, plan, io, nullptr, idx);
+    CK(cudaStreamSynchronize(nullptr));
+    CK(cudaMemcpy(dst, src, nbytes, cudaMemcpyDefault));
+    if (written) *written = nbytes;
   });
 }
 

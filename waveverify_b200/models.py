@@ -158,6 +158,37 @@ class _B200Module(nn.Module):
         if self._net is not None:
             _lib.check(_lib.lib().wv_net_set_chunk(self._net.handle, int(n)), "set_chunk")
 
+    def set_profile(self, enable: bool):
+        _lib.check(_lib.lib().wv_net_set_profile(self._native().handle, int(bool(enable))), "set_profile")
+
+    def profile_read(self):
+        """Per-launch records of the last profiled forward: dict(tag, cls, ms, flops, bytes)."""
+        L = _lib.lib()
+        n = 4096
+        ms = (C.c_float * n)(); fl = (C.c_double * n)(); by = (C.c_double * n)(); cl = (C.c_int * n)()
+        k = L.wv_net_profile_read(self._native().handle, n, ms, fl, by, cl)
+        if k < 0:
+            _lib.check(k, "wv_net_profile_read")
+        h = self._native().handle
+        return [dict(tag=L.wv_net_profile_tag(h, i).decode(), cls=int(cl[i]), ms=float(ms[i]),
+                     flops=float(fl[i]), bytes=float(by[i])) for i in range(k)]
+
+    @torch.no_grad()
+    def debug_tap(self, audio: torch.Tensor, msg, tag: str, which: int, shape, dtype=torch.bfloat16):
+        """Run up to the launch tagged `tag` and return its output buffer (tests only)."""
+        x = self._check_audio(audio)
+        B, _, T = x.shape
+        m = None
+        if msg is not None:
+            m = msg.to(x.device).float().contiguous()
+        out = torch.empty(shape, dtype=dtype, device=x.device)
+        wr = C.c_size_t(0)
+        _lib.check(_lib.lib().wv_debug_tap(self._native().handle, _ptr(x), _ptr(m), B, T, tag.encode(), which,
+                                           _ptr(out), out.numel() * out.element_size(), C.byref(wr)), "wv_debug_tap")
+        if wr.value != out.numel() * out.element_size():
+            raise RuntimeError(f"tap '{tag}' holds {wr.value} bytes, expected {out.numel() * out.element_size()}")
+        return out
+
     def launches(self, B: int, T: int) -> int:
         return int(_lib.lib().wv_net_launches(self._native().handle, B, T))
 

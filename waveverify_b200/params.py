@@ -71,6 +71,8 @@ def config_from_kwargs(kind: str, kw: dict) -> NetConfig:
     """Map reference constructor kwargs (model/generator.py:63-106, model/detector.py:82-114,
     model/locator.py:84-115) to a NetConfig; reject options the CUDA path does not implement."""
     kw = dict(kw)
+    if kind == "locator" and "nbits" in kw:      # model/locator.py:84-115 has no such kwarg (SURVEY F5)
+        raise TypeError("Locator.__init__() got an unexpected keyword argument 'nbits'")
     for k, want in _UNSUPPORTED.items():
         if k in kw and kw[k] != want:
             raise NotImplementedError(
