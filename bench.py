@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the WaveVerify embed + detect (+ locate) hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of embed -> detect -> locate (+ BER/MIoU counters) over one batch of
+synthetic clips.  Default workload = BASELINE.json configs[1]: 64 x 1 s mono clips at 16 kHz per
+GPU (weak scaling: every rank processes its own 64 clips; no collective in the hot loop, one NCCL
+all-reduce of six int64 counters at the end).  One JSON line is printed by rank 0.
+
+--impl reference times the reference algorithm's CPU implementation (the oracle port of the
+reference's PyTorch path; the reference itself is Python and does not travel to the GPU box) on
+the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+METRIC = "audio-sec/sec embed+detect"
+UNIT = "audio-s/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--seconds", type=float, default=1.0, help="clip length")
+    ap.add_argument("--chunk-seconds", type=float, default=0.0,
+                    help="internal sub-batch size in audio-seconds (0 = whole batch)")
+    ap.add_argument("--cpu-sample-clips", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"{a.clips} x {a.seconds:g} s mono clips @16 kHz per GPU, embed+detect+locate (BASELINE configs[1])"
+
+
+def make_models(dev, seed=0):
+    """Random-init networks of the conf/base.yml architecture (non-degenerate fixture weights)."""
+    import torch
+    from waveverify_b200 import Detector, Generator, Locator, fixture_state_dict
+    loc_kw = dict(dimension=64, channels_enc=32, n_residual_enc=1, strides=[8, 4])
+    out = {}
+    for kind, cls, kw in (("generator", Generator, {}), ("detector", Detector, {}), ("locator", Locator, loc_kw)):
+        m = cls(**{**kw, "bias": True, "zero_init": False})
+        m.load_state_dict(fixture_state_dict(m.cfg, seed))
+        out[kind] = m.to(dev) if dev is not None else m
+    return out
+
+
+def synth(B, T, seed):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    x = (0.1 * rng.standard_normal((B, 1, T))).astype("float32")
+    msg = rng.randint(0, 2, size=(B, 16)).astype("int64")
+    # ground-truth presence mask per utils/localization_augmentation.py:35-37, 258-287 (revert branch):
+    # 0.1 s segments, 20 % of them reverted to the un-watermarked original
+    seg = 1600
+    nseg = (T + seg - 1) // seg
+    sel = rng.rand(B, nseg) < 0.2
+    gt = np.repeat(~sel, seg, axis=1)[:, :T].astype("uint8")[:, None, :]
+    return x, msg, gt
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_oracle_rate(n_clips, T, iters, warm, seed=0):
+    """audio-s/s of the oracle port (fp32 PyTorch restatement of the reference) on host cores."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import wv_oracle as O
+    mods = make_models(None, seed)
+    W = {k: O.fold_state_dict(m.state_dict()) for k, m in mods.items()}
+    cfg = {k: dict(strides=list(m.cfg.strides), n_residual_enc=m.cfg.n_residual_enc,
+                   n_residual_dec=m.cfg.n_residual_dec, res_scale=m.cfg.res_scale, dimension=m.cfg.dimension,
+                   embedding_layers=m.cfg.embedding_layers, freq_bands=m.cfg.freq_bands) for k, m in mods.items()}
+    x, msg, gt = synth(n_clips, T, 1)
+    x = torch.from_numpy(x); msg = torch.from_numpy(msg)
+
+    def step():
+        with torch.no_grad():
+            wm = O.generator_forward(x, msg, W["generator"], cfg["generator"])
+            y = x + wm
+            lg = O.detector_forward(y, W["detector"], cfg["detector"])
+            ll = O.locator_forward(y, W["locator"], cfg["locator"])
+            bits, avg, conf, valid = O.decode_bits(lg)
+            mask = O.locator_mask(ll)
+            return O.metric_counters(bits, valid, msg, mask, torch.from_numpy(gt))
+
+    for _ in range(warm):
+        step()
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    audio_s = n_clips * T / SR
+    return audio_s / (sum(times) / len(times)), torch.get_num_threads(), times
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = int(round(a.seconds * SR))
+    n = max(1, min(a.clips, a.cpu_sample_clips))
+    steps, warm = max(1, a.steps), max(0, a.warmup)
+    # bound the run to a few minutes: ~1 s of CPU per audio-second
+    while (steps + warm) * n * a.seconds > 120 and steps > 2:
+        steps -= 1
+    rate, cores, times = cpu_oracle_rate(n, T, steps, warm)
+    sample = f"{n} x {a.seconds:g} s clips per step (bounded sample of the {a.clips}-clip batch), embed+detect+locate, fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        busy = [s for s, p in zip(sm, power) if p > 250] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+CLS_NAMES = {100: "gemm_std", 101: "gemm_l2norm", 102: "gemm_stft", 103: "gemm_head", 1: "dw5", 2: "down", 3: "up",
+             4: "conv_pre", 5: "conv_last", 6: "wav_stage", 7: "frames", 8: "film", 9: "bits_finish", 10: "conf",
+             11: "latent_in"}
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from waveverify_b200 import ber_miou, metric_counters
+    from waveverify_b200.dist import allreduce_counters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T = int(round(a.seconds * SR))
+    B = a.clips
+    mods = make_models(dev)
+    if a.chunk_seconds > 0:
+        for m in mods.values():
+            m.set_chunk_samples(int(a.chunk_seconds * SR))
+    G, D, L = mods["generator"], mods["detector"], mods["locator"]
+    x_np, msg_np, gt_np = synth(B, T, 100 + rank)
+    x = torch.from_numpy(x_np).to(dev); msg = torch.from_numpy(msg_np).to(dev); gt = torch.from_numpy(gt_np).to(dev)
+    counters = torch.zeros(6, dtype=torch.int64, device=dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(xd, md, cnt):
+        wm, y, _ = G.embed_batch(xd, md, want_wm=False)
+        d = D.detect_batch(y)
+        l = L.locate_batch(y)
+        metric_counters(d["bits"], d["valid"], md, l["mask"], gt, counters=cnt)
+        return y, d, l
+
+    for _ in range(max(a.warmup, 3)):
+        step(x, msg, counters)
+    torch.cuda.synchronize()
+    launches_per_step = G.launches(B, T) + D.launches(B, T) + L.launches(B, T) + 1
+    counters.zero_()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: K steps, inputs resident in HBM, CUDA events on the launching stream ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s, e in evs:
+        flush_buf.zero_()                      # L2 flush between steps, outside the per-step events
+        s.record()
+        step(x, msg, counters)
+        e.record()
+    if world > 1:
+        allreduce_counters(counters)           # the path's only collective: 6 x int64
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [s.elapsed_time(e) for s, e in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    audio_s_per_step = B * T / SR * world
+    value = audio_s_per_step * a.steps / (total_ms / 1e3)
+    ber, miou = ber_miou(counters)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing ----
+    hx = torch.from_numpy(x_np).pin_memory(); hm = torch.from_numpy(msg_np.astype("float32")).pin_memory()
+    hy = torch.empty(B, 1, T, dtype=torch.float32).pin_memory()
+    hbits = torch.empty(B, 16, dtype=torch.uint8).pin_memory()
+    hconf = torch.empty(B, dtype=torch.float32).pin_memory()
+    hmask = torch.empty(B, 1, T, dtype=torch.uint8).pin_memory()
+    h2d = hx.numel() * 4 + hm.numel() * 4
+    d2h = hy.numel() * 4 + hbits.numel() + hconf.numel() * 4 + hmask.numel()
+    cnt2 = torch.zeros(6, dtype=torch.int64, device=dev)
+
+    def e2e_step():
+        xd = hx.to(dev, non_blocking=True); md = hm.to(dev, non_blocking=True)
+        y, d, l = step(xd, md, cnt2)
+        hy.copy_(y, non_blocking=True); hbits.copy_(d["bits"], non_blocking=True)
+        hconf.copy_(d["conf"], non_blocking=True); hmask.copy_(l["mask"], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e_steps = max(3, min(a.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = audio_s_per_step * e_steps / float(t_e2e.item())
+
+    line = None
+    if rank == 0:
+        # ---- per-kernel device times (CUDA events around every launch, same stream) -----------------
+        roofline = None
+        breakdown = {}
+        if not a.no_profile:
+            peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(pk):
+                j = json.load(open(pk))
+                peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                         "src": "measured"}
+            recs = []
+            for m in (G, D, L):
+                m.set_chunk_samples(0 if a.chunk_seconds <= 0 else int(a.chunk_seconds * SR))
+                m.set_profile(True)
+            flush_buf.zero_()
+            wm, y, _ = G.embed_batch(x, msg, want_wm=False); torch.cuda.synchronize(); recs += G.profile_read()
+            D.detect_batch(y); torch.cuda.synchronize(); recs += D.profile_read()
+            L.locate_batch(y); torch.cuda.synchronize(); recs += L.profile_read()
+            for m in (G, D, L):
+                m.set_profile(False)
+            n_sub = 1
+            if a.chunk_seconds > 0:
+                n_sub = max(1, -(-B // max(1, int(a.chunk_seconds * SR) // T)))
+            for r in recs:
+                c = breakdown.setdefault(CLS_NAMES.get(r["cls"], str(r["cls"])), {"launches": 0, "ms": 0.0, "gflop": 0.0, "mb": 0.0})
+                c["launches"] += 1; c["ms"] += r["ms"]; c["gflop"] += r["flops"] / 1e9; c["mb"] += r["bytes"] / 1e6
+            tot = sum(c["ms"] for c in breakdown.values()) or 1.0
+            for c in breakdown.values():
+                c["share"] = round(c["ms"] / tot, 4)
+                c["tflops"] = round(c["gflop"] / max(c["ms"], 1e-9), 2)
+                c["gbs"] = round(c["mb"] / max(c["ms"], 1e-9), 1)
+                c["ms"] = round(c["ms"], 4); c["gflop"] = round(c["gflop"], 3); c["mb"] = round(c["mb"], 2)
+            dom = max(breakdown.items(), key=lambda kv: kv[1]["ms"])
+            name, c = dom
+            f_t = c["tflops"] / peaks["bf16_tflops_sustained"]
+            f_h = c["gbs"] / peaks["hbm_gbs"]
+            traffic = None
+            tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tr):
+                traffic = json.load(open(tr)).get(name)
+            if f_t >= f_h:
+                roofline = {"kernel": name, "bound": "tensor", "achieved": c["tflops"], "peak": peaks["bf16_tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": round(f_t, 4), "traffic": traffic}
+            else:
+                roofline = {"kernel": name, "bound": "hbm", "achieved": c["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(f_h, 4), "traffic": traffic}
+            roofline["peak_src"] = peaks["src"] + (" (sustained)" if roofline["bound"] == "tensor" else "")
+            roofline["launches"] = c["launches"]
+            roofline["avg_launch_us"] = round(1e3 * c["ms"] / max(1, c["launches"]), 2)
+            roofline["note"] = ("aggregate over all launches of this kernel in one step (profiled sub-batch x%d); "
+                                "achieved = algorithmic work / CUDA-event time" % n_sub)
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            n = max(1, min(B, a.cpu_sample_clips))
+            rate, cores, times = cpu_oracle_rate(n, T, 3, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n} x {a.seconds:g} s clips, embed+detect+locate, fp32 oracle port, 1 warm-up + 3 timed"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(a), "clips_per_gpu": B, "clip_seconds": a.seconds,
+                       "l2": "flushed between steps (256 MiB memset outside the per-step events); per-step activations >> L2",
+                       "weights": "random-init conf/base.yml architecture (fixture weights)", "parallelism": f"dp{world} (clips sharded, no hot-loop collective)",
+                       "chunk_seconds": a.chunk_seconds},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * a.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_breakdown": breakdown, "wall_s_timed_region": t_wall,
+            "quality": {"ber": ber, "miou": miou, "note": "random-init weights: values are only a checksum of the counters path"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()
