@@ -132,6 +132,11 @@ int wv_debug_tap(wv_net* net, const float* x, const float* msg, int B, int T, co
 int wv_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                const float* bias, const void* residual, void* out_raw, void* out_act,
                float act_scale, int a_is_fp16, void* stream);
+/* A [B,T,K] bf16 -> 1x1 conv (W [N,K]) -> causal depthwise k=5 (dw_w5n [5][N], bias) fused in the
+ * GEMM epilogue (+ residual [B,T,N]) -> out_raw / out_act = ELU(v*act_scale), each [B,T,N] bf16. */
+int wv_op_gemm_dw5(const void* A, const void* W, int B, int T, int N, int K, const float* dw_w5n,
+                   const float* bias, const void* residual, void* out_raw, void* out_act,
+                   float act_scale, void* stream);
 int wv_op_dw5(const void* in, const float* w5c, const float* bias, const void* residual,
               void* out_raw, void* out_act, float act_scale, int B, int T, int C, void* stream);
 int wv_op_down(const void* in, const float* wkc, const float* bias, const float* film,

@@ -172,3 +172,30 @@ def test_up_conv_transposed(B, Tin, C, r):
     xq = xin.float().cpu().transpose(1, 2)
     ref = F.conv_transpose1d(xq, w, None, stride=r, groups=C)[..., : Tin * r]   # modules/conv.py:838-874
     bf16_close(out.cpu(), ref.transpose(1, 2), abs_=2e-3)
+
+
+@pytest.mark.parametrize("B,T,N,K", [(2, 1000, 64, 64), (1, 50, 1536, 128), (3, 401, 96, 96), (2, 124, 256, 256),
+                                     (1, 125, 192, 192), (2, 4097, 384, 384), (1, 3, 32, 32), (1, 16000, 128, 128)])
+@pytest.mark.parametrize("mode", ["act", "res_both"])
+def test_gemm_with_fused_depthwise_epilogue(B, T, N, K, mode):
+    """1x1 conv -> causal depthwise k=5 (+bias, +residual) -> raw / ELU outputs in ONE kernel;
+    per-clip tiles of 128 rows with a 4-row halo (first tile starts at t=-4: TMA zero fill)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T + N + K)
+    A = torch.randn(B, T, K, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    dw = (torch.randn(N, 1, 5, generator=g) * 0.4)
+    b = torch.randn(N, generator=g)
+    R = torch.randn(B, T, N, generator=g).to(torch.bfloat16).to(dev) if mode == "res_both" else None
+    wk = dw[:, 0, :].t().contiguous().to(dev)
+    out_raw = torch.full((B, T, N), float("nan"), dtype=torch.bfloat16, device=dev) if mode == "res_both" else None
+    out_act = torch.full((B, T, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    rc = _lib().wv_op_gemm_dw5(P(A), P(W), B, T, N, K, P(wk), P(b.to(dev)), P(R), P(out_raw), P(out_act), 0.75, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+    G = (A.double() @ W.double().t()).to(torch.bfloat16).float().cpu()      # the kernel stages the GEMM tile in bf16
+    ref = F.conv1d(F.pad(G.transpose(1, 2), (4, 0)), dw, b, groups=N).transpose(1, 2)
+    if R is not None:
+        ref = ref + R.float().cpu()
+        bf16_close(out_raw.cpu(), ref, abs_=4e-3)
+    bf16_close(out_act.cpu(), F.elu(ref * 0.75), abs_=4e-3)

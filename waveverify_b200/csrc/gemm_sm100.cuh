@@ -1,16 +1,23 @@
 // Pointwise-conv / STFT / head GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (16-bit in, fp32
-// accumulate in TMEM), persistent + warp specialised:
-//   warp 0     TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-stage mbarrier ring)
-//   warp 1     MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, K=16 per instr)
-//   warp 2     TMEM allocator (512 columns = 2 accumulator stages x 256)
-//   warps 4-7  epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+// accumulate in TMEM), persistent + warp specialised (384 threads):
+//   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier ring of 3-6 stages)
+//   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, K=16 per instr)
+//   warp 2      TMEM allocator (512 columns = 2 accumulator stages x 256)
+//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers -> ... -> global)
 // Activations are channels-last [clip, time, channel] so "time" is the MMA M dimension and the
 // channel contraction is K-major for both operands.  A is addressed through a 3-D tensor map
-// (k, row-in-clip, clip) so the same kernel serves the flattened [B*T, C] activations
-// (n_clips = 1) and the strided, overlapping STFT frame view of the padded waveform.
+// (k, row-in-clip, clip): flattened [B*T, C] activations use n_clips = 1; per-clip tiles (with
+// negative / overlapping row origins) serve the causal depthwise halo and the strided,
+// overlapping STFT frame view of the padded waveform.
 //
 // Epilogues (template EPI):
-//   STD     v = acc + bias[n] + residual[m,n];  out_raw = bf16(v);  out_act = bf16(ELU(v*s))
+//   STAGED  the fp32 accumulator tile is rounded to bf16 into a padded shared-memory tile, the
+//           TMEM stage is released (the next tile's MMAs overlap the rest), then all 256
+//           epilogue threads walk the tile in a coalesced (row, 8-channel) layout:
+//             v = bias[c] + sum_{j<taps} w[j][c] * S[r-taps+1+j][c]      taps = 1 or 5
+//             v += residual[m,c];  out_raw = bf16(v);  out_act = bf16(ELU(v*s))
+//           taps = 5 fuses the causal depthwise conv that follows every resblock 1x1
+//           (modules/seanet.py:85-109): tiles overlap by 4 rows (128 rows in, 124 out).
 //   L2NORM  v = acc + bias;  v *= scale / max(||v||_2 over N, 1e-12)      (modules/seanet.py:288)
 //   STFT    columns are (re,im) pairs: y = (0.5*ln(max(re^2+im^2, c)) - mu) / sigma
 //           (modules/conv.py:1076 + modules/seanet.py:482-494); pair 0 carries the two purely
@@ -25,32 +32,38 @@ namespace wv {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
+constexpr int GEMM_BAR_BYTES = 256;
 
-enum { EPI_STD = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3 };
+enum { EPI_STAGED = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3 };
 
 struct GemmArgs {
   int rows_per_clip;  // rows of A per clip (flat: total M)
   int n_clips;
   int N, K;
   int block_n;
+  int stages;         // smem ring depth (host computed from block_n)
   uint32_t idesc;
-  // STD / L2NORM
-  const float* bias;
+  // STAGED
+  int taps;           // 1, or 5 = fused causal depthwise conv over time
+  const float* dw_w;  // [taps][N] fp32 (taps == 5)
+  const float* bias;  // [N] (added after the depthwise taps), nullable
   const __nv_bfloat16* residual;
   __nv_bfloat16* out_raw;
   __nv_bfloat16* out_act;
   float act_scale;
   int ldo;
+  // L2NORM
   float l2_scale;
-  float* out_f32_t;  // [n_clips', N, F] fp32 (latent for the API), nullable
+  float* out_f32_t;  // [clips, N, F] fp32 (latent for the API), nullable
   int f32_F;         // frames per clip for out_f32_t (flat A: clip = m / f32_F)
   // STFT
   float log_offset, inv_sigma, clamp_sq;
@@ -59,10 +72,26 @@ struct GemmArgs {
   float* logits;
   uint8_t* mask_out;
   float* probs;
-  float* partial;  // [M, N / block_n]
+  float* partial;  // [M, 2 * N / block_n]
   const uint8_t* presence;
   int hop, T, n_out, head_F;
 };
+
+__host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n * 2 + 16; }
+__host__ inline int gemm_stage_count(int block_n, bool staged) {
+  const int fixed = 1024 + GEMM_BAR_BYTES + (staged ? BM * staged_pitch_bytes(block_n) : 0);
+  int s = (GEMM_SMEM_LIMIT - fixed) / (A_STAGE_BYTES + block_n * BK * 2);
+  return s > MAX_STAGES ? MAX_STAGES : s;
+}
+__host__ inline int gemm_smem_bytes(int block_n, bool staged) {
+  return 1024 + GEMM_BAR_BYTES + (staged ? BM * staged_pitch_bytes(block_n) : 0) +
+         gemm_stage_count(block_n, staged) * (A_STAGE_BYTES + block_n * BK * 2);
+}
+
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ void epi_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(EPI_THREADS) : "memory");
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -71,37 +100,43 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int b_stage_bytes = g.block_n * BK * 2;
   uint8_t* smemA = smem;
-  uint8_t* smemB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  uint64_t* full = bars;                      // [STAGES]
-  uint64_t* empty = bars + STAGES;            // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;     // [ACC_STAGES]
+  uint8_t* smemB = smem + g.stages * A_STAGE_BYTES;
+  uint8_t* after = smemB + g.stages * b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
+  uint64_t* full = bars;                          // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [ACC_STAGES]
   uint64_t* acc_empty = acc_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  uint8_t* stage_tile = after + GEMM_BAR_BYTES;   // [BM][pitch] bf16 (STAGED only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m_per_clip = (g.rows_per_clip + BM - 1) / BM;
+  // tile geometry: STAGED with taps>1 walks each clip in overlapping tiles (halo = taps-1 rows)
+  const int halo = (EPI == EPI_STAGED) ? g.taps - 1 : 0;
+  const int rows_out = BM - halo;
+  const int tiles_m_per_clip = (g.rows_per_clip + rows_out - 1) / rows_out;
   const int tiles_m = tiles_m_per_clip * g.n_clips;
   const int tiles_n = g.N / g.block_n;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (g.K + BK - 1) / BK;
-  const uint32_t stage_bytes = static_cast<uint32_t>((BM + g.block_n) * BK * 2);
+  const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < g.stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -119,14 +154,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / tiles_n, nt = tile % tiles_n;
         const int clip = mt / tiles_m_per_clip;
-        const int r0 = (mt % tiles_m_per_clip) * BM;
+        const int r0 = (mt % tiles_m_per_clip) * rows_out - halo;   // may be negative: zero fill
         const int n0 = nt * g.block_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
           tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, clip);
-          tma_load_2d(smemB + stage * B_STAGE_BYTES, &tmB, &full[stage], kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -145,7 +180,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         if (lane == 0) {
           const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * B_STAGE_BYTES));
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * b_stage_bytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr>>4) field
@@ -155,21 +190,22 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == num_kb - 1) umma_commit(&acc_full[as]);
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
       if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int q = warp - 4;  // TMEM lane quarter: this warp may touch lanes [32q, 32q+32)
+    // ------------------------------------------------------------ epilogue (8 warps)
+    const int e = warp - 4;
+    const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
+    const int h = e >> 2;   // column half: this warp takes chunks c with (c & 1) == h
+    const int et = threadIdx.x - 128;   // 0..255
     int as = 0;
     uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / tiles_n, nt = tile % tiles_n;
       const int clip = mt / tiles_m_per_clip;
-      const int r = (mt % tiles_m_per_clip) * BM + q * 32 + lane;
-      const bool row_ok = r < g.rows_per_clip;
-      const long long m = static_cast<long long>(clip) * g.rows_per_clip + r;
+      const int r_base = (mt % tiles_m_per_clip) * rows_out;   // first OUTPUT row of the tile
       const int n0 = nt * g.block_n;
       const int chunks = g.block_n / 32;
       mbar_wait(&acc_full[as], as_phase);
@@ -178,155 +214,245 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
       uint32_t v[32];
 
-      if constexpr (EPI == EPI_STD) {
-        for (int c = 0; c < chunks; ++c) {
-          const int n = n0 + c * 32;
-          uint4 rres[4];
-          if (g.residual != nullptr && row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(g.residual + m * g.ldo + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rres[i] = __ldg(rp + i);
-          }
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            if (g.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] += __ldg(g.bias + n + i);
-            }
-            if (g.residual != nullptr) {
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(rres);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float a, b;
-                unpack_bf16x2(rw[i], a, b);
-                f[2 * i] += a;
-                f[2 * i + 1] += b;
-              }
-            }
-            if (g.out_raw != nullptr) {
-              uint4* op = reinterpret_cast<uint4*>(g.out_raw + m * g.ldo + n);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                op[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
-                                   pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                   pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
-                                   pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
-            }
-            if (g.out_act != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = elu1(f[i] * g.act_scale);
-              uint4* op = reinterpret_cast<uint4*>(g.out_act + m * g.ldo + n);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                op[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
-                                   pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                   pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
-                                   pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
-            }
-          }
-        }
-      } else if constexpr (EPI == EPI_L2NORM) {
-        float ss = 0.f;
-        for (int c = 0; c < chunks; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n0 + c * 32 + i) : 0.f);
-            ss += x * x;
-          }
-        }
-        const float sc = g.l2_scale / fmaxf(sqrtf(ss), 1e-12f);
-        for (int c = 0; c < chunks; ++c) {
-          const int n = n0 + c * 32;
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              f[i] = (__uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n + i) : 0.f)) * sc;
-            uint4* op = reinterpret_cast<uint4*>(g.out_raw + m * g.ldo + n);
+      if constexpr (EPI == EPI_STAGED) {
+        const int pitch = staged_pitch_bytes(g.block_n);
+        // ---- phase 1: TMEM -> bf16 -> padded smem tile (row = TMEM lane)
+        {
+          uint8_t* rowp = stage_tile + (q * 32 + lane) * pitch;
+          for (int c = h; c < chunks; c += 2) {
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            uint4* sp = reinterpret_cast<uint4*>(rowp + c * 64);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              op[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
-                                 pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                 pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
-                                 pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
-            if (g.out_f32_t != nullptr) {
-              const long long b = m / g.f32_F, fr = m % g.f32_F;
-              float* tp = g.out_f32_t + (b * g.N + n) * g.f32_F + fr;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) tp[static_cast<long long>(i) * g.f32_F] = f[i];
-            }
+              sp[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                                 pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                                 pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                                 pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
           }
         }
-      } else if constexpr (EPI == EPI_STFT) {
-        for (int c = 0; c < chunks; ++c) {
-          const int p0 = (n0 + c * 32) >> 1;
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            float y[16];
+        tc_fence_before();
+        epi_bar_sync(1);                       // tile staged by all 8 warps
+        if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage is free: next MMAs may start
+        // ---- phase 2: coalesced walk, thread = (8-channel group, row segment)
+        {
+          const int cgs = g.block_n >> 3;
+          const int nseg = EPI_THREADS / cgs;
+          const int cg = et % cgs, seg = et / cgs;
+          if (seg < nseg) {
+            const int seg_len = (rows_out + nseg - 1) / nseg;
+            const int ro_begin = seg * seg_len;                       // output-row index in tile
+            const int ro_end = min(ro_begin + seg_len, rows_out);
+            const int c = n0 + cg * 8;
+            float bs[8];
+            if (g.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c) + 1);
+              bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+              bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-              y[i] = (0.5f * logf(fmaxf(re * re + im * im, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+              for (int i = 0; i < 8; ++i) bs[i] = 0.f;
             }
-            __nv_bfloat16* yp = g.out_raw + m * g.ldo;
-            if (p0 == 0) {
-              const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
-              y[0] = (0.5f * logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
-              const float yn = (0.5f * logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
-              yp[g.n_half] = __float2bfloat16_rn(yn);
-            }
-            uint4* op = reinterpret_cast<uint4*>(yp + p0);
+            const uint8_t* colp = stage_tile + cg * 16;
+            if (g.taps == 5) {
+              float wt[5][8];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-              op[i] = make_uint4(pack_bf16x2(y[8 * i], y[8 * i + 1]),
-                                 pack_bf16x2(y[8 * i + 2], y[8 * i + 3]),
-                                 pack_bf16x2(y[8 * i + 4], y[8 * i + 5]),
-                                 pack_bf16x2(y[8 * i + 6], y[8 * i + 7]));
-          }
-        }
-      } else {  // EPI_HEAD
-        const long long b = m / g.head_F;
-        const int fr = static_cast<int>(m % g.head_F);
-        const int o = n0 / g.hop;
-        const int j0 = n0 % g.hop;
-        const float bo = g.bias ? __ldg(g.bias + o) : 0.f;
-        float psum = 0.f;
-        for (int c = 0; c < chunks; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            const int t0 = fr * g.hop + j0 + c * 32;
-            const long long base = b * g.T + t0;
-            float* lp = g.logits ? g.logits + (b * g.n_out + o) * static_cast<long long>(g.T) + t0
-                                 : nullptr;
+              for (int j = 0; j < 5; ++j) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c) + 1);
+                wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
+                wt[j][4] = w1.x; wt[j][5] = w1.y; wt[j][6] = w1.z; wt[j][7] = w1.w;
+              }
+              uint4 win[5];
+              // tile row of output row ro is ro + 4; its window is tile rows ro .. ro+4
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (t0 + i < g.T) {
-                const float l = __uint_as_float(v[i]) + bo;
-                const float p = 1.f / (1.f + __expf(-l));
-                if (lp) lp[i] = l;
-                if (g.mask_out) g.mask_out[base + i] = l > 0.5f ? 1 : 0;
-                if (g.probs) g.probs[base + i] = p;
-                if (g.partial) psum += g.presence ? (g.presence[base + i] ? p : 0.f) : p;
+              for (int j = 0; j < 4; ++j)
+                win[j + 1] = *reinterpret_cast<const uint4*>(colp + (ro_begin + j) * pitch);
+              for (int ro = ro_begin; ro < ro_end; ++ro) {
+                const int r = r_base + ro;
+                if (r >= g.rows_per_clip) break;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) win[j] = win[j + 1];
+                win[4] = *reinterpret_cast<const uint4*>(colp + (ro + 4) * pitch);
+                const long long off = (static_cast<long long>(clip) * g.rows_per_clip + r) * g.ldo + c;
+                uint4 rres = make_uint4(0, 0, 0, 0);
+                if (g.residual != nullptr) rres = __ldg(reinterpret_cast<const uint4*>(g.residual + off));
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = bs[i];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                  const uint32_t* wu = reinterpret_cast<const uint32_t*>(&win[j]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float a, b;
+                    unpack_bf16x2(wu[i], a, b);
+                    o[2 * i] = fmaf(wt[j][2 * i], a, o[2 * i]);
+                    o[2 * i + 1] = fmaf(wt[j][2 * i + 1], b, o[2 * i + 1]);
+                  }
+                }
+                if (g.residual != nullptr) {
+                  const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rres);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float a, b;
+                    unpack_bf16x2(ru[i], a, b);
+                    o[2 * i] += a;
+                    o[2 * i + 1] += b;
+                  }
+                }
+                if (g.out_raw != nullptr)
+                  *reinterpret_cast<uint4*>(g.out_raw + off) =
+                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                if (g.out_act != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) o[i] = elu_fast(o[i] * g.act_scale);
+                  *reinterpret_cast<uint4*>(g.out_act + off) =
+                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                }
+              }
+            } else {
+              for (int ro = ro_begin; ro < ro_end; ++ro) {
+                const int r = r_base + ro;
+                if (r >= g.rows_per_clip) break;
+                const uint4 s = *reinterpret_cast<const uint4*>(colp + ro * pitch);
+                const long long off = (static_cast<long long>(clip) * g.rows_per_clip + r) * g.ldo + c;
+                uint4 rres = make_uint4(0, 0, 0, 0);
+                if (g.residual != nullptr) rres = __ldg(reinterpret_cast<const uint4*>(g.residual + off));
+                float o[8];
+                const uint32_t* su = reinterpret_cast<const uint32_t*>(&s);
+                const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rres);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float a, b, ra, rb;
+                  unpack_bf16x2(su[i], a, b);
+                  unpack_bf16x2(ru[i], ra, rb);
+                  o[2 * i] = a + bs[2 * i] + ra;
+                  o[2 * i + 1] = b + bs[2 * i + 1] + rb;
+                }
+                if (g.out_raw != nullptr)
+                  *reinterpret_cast<uint4*>(g.out_raw + off) =
+                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                if (g.out_act != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) o[i] = elu_fast(o[i] * g.act_scale);
+                  *reinterpret_cast<uint4*>(g.out_act + off) =
+                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                }
               }
             }
           }
         }
-        if (g.partial != nullptr && row_ok) g.partial[m * tiles_n + nt] = psum;
+        epi_bar_sync(2);                       // staging tile may be overwritten
+      } else {
+        const int r = r_base + q * 32 + lane;
+        const bool row_ok = r < g.rows_per_clip;
+        const long long m = static_cast<long long>(clip) * g.rows_per_clip + r;
+        if constexpr (EPI == EPI_L2NORM) {
+          if (h == 0) {
+            float ss = 0.f;
+            for (int c = 0; c < chunks; ++c) {
+              tmem_ld32(taddr + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float x = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n0 + c * 32 + i) : 0.f);
+                ss += x * x;
+              }
+            }
+            const float sc = g.l2_scale / fmaxf(sqrtf(ss), 1e-12f);
+            for (int c = 0; c < chunks; ++c) {
+              const int n = n0 + c * 32;
+              tmem_ld32(taddr + c * 32, v);
+              tmem_ld_wait();
+              if (row_ok) {
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  f[i] = (__uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n + i) : 0.f)) * sc;
+                uint4* op = reinterpret_cast<uint4*>(g.out_raw + m * g.ldo + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  op[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
+                                     pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                                     pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
+                                     pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+                if (g.out_f32_t != nullptr) {
+                  const long long b = m / g.f32_F, fr = m % g.f32_F;
+                  float* tp = g.out_f32_t + (b * g.N + n) * g.f32_F + fr;
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) tp[static_cast<long long>(i) * g.f32_F] = f[i];
+                }
+              }
+            }
+          }
+        } else if constexpr (EPI == EPI_STFT) {
+          for (int c = h; c < chunks; c += 2) {
+            const int p0 = (n0 + c * 32) >> 1;
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float y[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+                y[i] = (0.5f * __logf(fmaxf(re * re + im * im, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+              }
+              __nv_bfloat16* yp = g.out_raw + m * g.ldo;
+              if (p0 == 0) {
+                const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
+                y[0] = (0.5f * __logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                const float yn = (0.5f * __logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                yp[g.n_half] = __float2bfloat16_rn(yn);
+              }
+              uint4* op = reinterpret_cast<uint4*>(yp + p0);
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                op[i] = make_uint4(pack_bf16x2(y[8 * i], y[8 * i + 1]),
+                                   pack_bf16x2(y[8 * i + 2], y[8 * i + 3]),
+                                   pack_bf16x2(y[8 * i + 4], y[8 * i + 5]),
+                                   pack_bf16x2(y[8 * i + 6], y[8 * i + 7]));
+            }
+          }
+        } else {  // EPI_HEAD
+          const long long b = m / g.head_F;
+          const int fr = static_cast<int>(m % g.head_F);
+          const int o = n0 / g.hop;
+          const int j0 = n0 % g.hop;
+          const float bo = g.bias ? __ldg(g.bias + o) : 0.f;
+          float psum = 0.f;
+          for (int c = h; c < chunks; c += 2) {
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              const int t0 = fr * g.hop + j0 + c * 32;
+              const long long base = b * g.T + t0;
+              float* lp = g.logits ? g.logits + (b * g.n_out + o) * static_cast<long long>(g.T) + t0
+                                   : nullptr;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (t0 + i < g.T) {
+                  const float l = __uint_as_float(v[i]) + bo;
+                  const float p = 1.f / (1.f + __expf(-l));
+                  if (lp) lp[i] = l;
+                  if (g.mask_out) g.mask_out[base + i] = l > 0.5f ? 1 : 0;
+                  if (g.probs) g.probs[base + i] = p;
+                  if (g.partial) psum += g.presence ? (g.presence[base + i] ? p : 0.f) : p;
+                }
+              }
+            }
+          }
+          if (g.partial != nullptr && row_ok) g.partial[(m * tiles_n + nt) * 2 + h] = psum;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
-
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
     }
   }

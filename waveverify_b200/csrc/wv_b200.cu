@@ -107,10 +107,10 @@ void init_device_once() {
     WV_THROW(WV_ERR_UNSUPPORTED, "this library targets sm_100a (B200); device is sm_%d%d",
              prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
-  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   done = true;
 }
@@ -477,6 +477,11 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.K = K;
   g.block_n = w.block_n;
   g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
+  const bool staged = epi == EPI_STAGED;
+  if (staged && g.taps != 1 && g.taps != 5) WV_THROW(WV_ERR_INVALID, "taps must be 1 or 5");
+  g.stages = gemm_stage_count(w.block_n, staged);
+  if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
+  op.i[7] = gemm_smem_bytes(w.block_n, staged);
   if (custom_tmA) {
     g.rows_per_clip = rows_per_clip;
     g.n_clips = n_clips;
@@ -490,7 +495,8 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   op.g = g;
   op.out0 = g.out_raw;
   op.out1 = g.out_act;
-  const int tiles = ceil_div(g.rows_per_clip, BM) * g.n_clips * (w.N / w.block_n);
+  const int rows_out = BM - (staged ? g.taps - 1 : 0);
+  const int tiles = ceil_div(g.rows_per_clip, rows_out) * g.n_clips * (w.N / w.block_n);
   op.grid = std::min(tiles, g_num_sms);
   {
     const double Mt = static_cast<double>(g.rows_per_clip) * g.n_clips;
@@ -513,6 +519,7 @@ GemmArgs std_args(const float* bias, const bf16* res, bf16* out_raw, bf16* out_a
   memset(&g, 0, sizeof(g));
   g.bias = bias; g.residual = res; g.out_raw = out_raw; g.out_act = out_act;
   g.act_scale = act_scale; g.ldo = ldo;
+  g.taps = 1;
   return g;
 }
 
@@ -532,31 +539,43 @@ void add_dw5(PlanCtx& c, const DwW& w, const bf16* in, const bf16* res, bf16* ou
   c.push(op);
 }
 
+
+// 1x1 conv (tcgen05 GEMM) with the following causal depthwise k=5 conv fused into its epilogue:
+// per-clip overlapping tiles (128 rows in, 124 out).  A is [B, T, K] channels-last.
+void add_gemm_dw(PlanCtx& c, const GemmW& pw, const DwW& dw, const bf16* A, int T, int K, const bf16* res,
+                 bf16* out_raw, bf16* out_act, float act_scale) {
+  if (dw.k != 5 || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused depthwise conv must be k=5 over the GEMM's N");
+  GemmArgs g = std_args(dw.bias, res, out_raw, out_act, act_scale, pw.N);
+  g.taps = 5;
+  g.dw_w = dw.w;
+  CUtensorMap tm;
+  if (!c.dry()) tm = make_tmap(A, 3, K, T, c.B, K, static_cast<uint64_t>(K) * T, BK, BM, false);
+  add_gemm(c, EPI_STAGED, pw, nullptr, 0, 0, K, g, &tm, T, c.B);
+  Op& op = c.ops->back();
+  const double n = static_cast<double>(c.B) * T;
+  op.flops += 10.0 * n * pw.N;
+  op.bytes = n * 2.0 * (K + pw.N * ((res ? 1 : 0) + (out_raw ? 1 : 0) + (out_act ? 1 : 0))) + static_cast<double>(pw.N) * K * 2.0;
+}
+
 // One residual block (modules/seanet.py:245-281).  X raw (residual), A = ELU(X*pre_scale).
 // Produces Xn (raw, if need_raw) and An = ELU(Xn*next_act_scale) (if need_act); frees X and A.
 void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool need_raw, bool need_act,
                    float next_act_scale, Buf& Xn, Buf& An, const std::string& name) {
   const long long M = static_cast<long long>(c.B) * T;
   const size_t bytes = static_cast<size_t>(M) * C * 2;
-  Buf G1 = c.alloc(bytes);
-  c.tag(name + ".pw1");
-  add_gemm(c, EPI_STD, r.pw1, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G1), nullptr, 1.f, C));
-  c.release(A);
+  // half 1: A2 = ELU(dw5(W1 * A) + b1)
   Buf A2 = c.alloc(bytes);
-  c.tag(name + ".dw1");
-  add_dw5(c, r.dw1, c.ptr<bf16>(G1), nullptr, nullptr, c.ptr<bf16>(A2), 1.f, T, C);
-  c.release(G1);
-  Buf G2 = c.alloc(bytes);
-  c.tag(name + ".pw2");
-  add_gemm(c, EPI_STD, r.pw2, c.ptr<bf16>(A2), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G2), nullptr, 1.f, C));
-  c.release(A2);
+  c.tag(name + ".h1");
+  add_gemm_dw(c, r.pw1, r.dw1, c.ptr<bf16>(A), T, C, nullptr, nullptr, c.ptr<bf16>(A2), 1.f);
+  c.release(A);
+  // half 2: Xn = RS*(dw5(W2 * A2) + b2) + X ; An = ELU(Xn * next_scale)   (RS folded into dw2)
   Xn = Buf(); An = Buf();
   if (need_raw) Xn = c.alloc(bytes);
   if (need_act) An = c.alloc(bytes);
   c.tag(name + ".out");
-  add_dw5(c, r.dw2, c.ptr<bf16>(G2), c.ptr<bf16>(X), need_raw ? c.ptr<bf16>(Xn) : nullptr,
-          need_act ? c.ptr<bf16>(An) : nullptr, next_act_scale, T, C);
-  c.release(G2);
+  add_gemm_dw(c, r.pw2, r.dw2, c.ptr<bf16>(A2), T, C, c.ptr<bf16>(X), need_raw ? c.ptr<bf16>(Xn) : nullptr,
+              need_act ? c.ptr<bf16>(An) : nullptr, next_act_scale);
+  c.release(A2);
   c.release(X);
 }
 
@@ -771,7 +790,7 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
   }
   Aout = c.alloc(static_cast<size_t>(M) * C * 2);
   c.tag(name + ".out");
-  add_gemm(c, EPI_STD, s.layer, c.ptr<bf16>(Y), ldy, M, K2,
+  add_gemm(c, EPI_STAGED, s.layer, c.ptr<bf16>(Y), ldy, M, K2,
            std_args(nullptr, c.ptr<bf16>(X), nullptr, c.ptr<bf16>(Aout), act_scale, C));
   c.release(Y);
   c.release(X);
@@ -840,7 +859,7 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     const long long M = static_cast<long long>(B) * Ts;
     Buf G = c.alloc(static_cast<size_t>(M) * 2 * C * 2);
     c.tag("enc.s" + std::to_string(s) + ".down_pw");
-    add_gemm(c, EPI_STD, st.down_pw, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, 2 * C));
+    add_gemm(c, EPI_STAGED, st.down_pw, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, 2 * C));
     c.release(A);
     const int To = ceil_div(Ts, st.r);
     const bool last_stage = s == S - 1;
@@ -889,13 +908,9 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
   const int B = c.B;
   int Ts = F, C = d.pw0.N;
   long long M = static_cast<long long>(B) * Ts;
-  Buf G = c.alloc(static_cast<size_t>(M) * C * 2);
-  c.tag("dec.pw0");
-  add_gemm(c, EPI_STD, d.pw0, c.ptr<bf16>(Z), d.pw0.K, M, d.pw0.K, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, C));
   Buf A = c.alloc(static_cast<size_t>(M) * C * 2);
-  c.tag("dec.dw0");
-  add_dw5(c, d.dw0, c.ptr<bf16>(G), nullptr, nullptr, c.ptr<bf16>(A), 1.f, Ts, C);   // ELU of stage 0
-  c.release(G);
+  c.tag("dec.in");
+  add_gemm_dw(c, d.pw0, d.dw0, c.ptr<bf16>(Z), Ts, d.pw0.K, nullptr, nullptr, c.ptr<bf16>(A), 1.f);   // ELU of stage 0
   for (size_t s = 0; s < d.stages.size(); ++s) {
     const DecStageW& st = d.stages[s];
     const int To = Ts * st.r;
@@ -919,7 +934,7 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     Buf X = c.alloc(static_cast<size_t>(M) * Ch * 2);
     A = c.alloc(static_cast<size_t>(M) * Ch * 2);
     c.tag("dec.u" + std::to_string(s) + ".halve");
-    add_gemm(c, EPI_STD, st.halve, c.ptr<bf16>(U), C, M, C,
+    add_gemm(c, EPI_STAGED, st.halve, c.ptr<bf16>(U), C, M, C,
              std_args(st.halve.bias, nullptr, c.ptr<bf16>(X), c.ptr<bf16>(A), st.res.empty() ? d.stage_scale : st.res[0].pre_scale, Ch));
     c.release(U);
     C = Ch;
@@ -951,7 +966,7 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   const HeadW& h = n.head;
   const long long M = static_cast<long long>(c.B) * F;
   const int tiles_n = h.w.N / h.w.block_n;
-  Buf partial = c.alloc(static_cast<size_t>(M) * tiles_n * 4);
+  Buf partial = c.alloc(static_cast<size_t>(M) * tiles_n * 2 * 4);   // two column halves per tile
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.bias = h.w.bias;
@@ -963,7 +978,7 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
     Op op;
     op.type = OP_BITS;
     op.in = c.ptr<float>(partial);
-    op.i[0] = c.B; op.i[1] = F; op.i[2] = tiles_n; op.i[3] = h.hop / h.w.block_n; op.i[4] = c.T; op.i[5] = h.n_out;
+    op.i[0] = c.B; op.i[1] = F; op.i[2] = 2 * tiles_n; op.i[3] = 2 * (h.hop / h.w.block_n); op.i[4] = c.T; op.i[5] = h.n_out;
     c.tag("head.bits");
     c.push(op);
     Op op2;
@@ -1042,11 +1057,12 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
 }
 
 void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(op.i[7]);
   switch (op.epi) {
-    case EPI_STD: gemm_sm100_kernel<EPI_STD><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
-    case EPI_L2NORM: gemm_sm100_kernel<EPI_L2NORM><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
-    case EPI_STFT: gemm_sm100_kernel<EPI_STFT><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
-    default: gemm_sm100_kernel<EPI_HEAD><<<op.grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(op.tmA, op.tmB, g); break;
+    case EPI_STAGED: gemm_sm100_kernel<EPI_STAGED><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
+    case EPI_L2NORM: gemm_sm100_kernel<EPI_L2NORM><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
+    case EPI_STFT: gemm_sm100_kernel<EPI_STFT><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
+    default: gemm_sm100_kernel<EPI_HEAD><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
   }
 }
 
@@ -1401,8 +1417,30 @@ int wv_op_gemm(const void* A, int lda, const void* Wt, int ldw, int M, int N, in
     PlanCtx c;
     c.base = reinterpret_cast<uint8_t*>(16);   // non-null: encode tensor maps
     c.ops = &ops;
-    add_gemm(c, EPI_STD, w, A, lda, M, K,
+    add_gemm(c, EPI_STAGED, w, A, lda, M, K,
              std_args(bias, static_cast<const bf16*>(residual), static_cast<bf16*>(out_raw), static_cast<bf16*>(out_act), act_scale, N));
+    launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, const float* dw_w5n, const float* bias,
+                   const void* residual, void* out_raw, void* out_act, float act_scale, void* stream) {
+  return guarded([&] {
+    init_device_once();
+    GemmW w;
+    w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = K; w.fp16 = false;
+    w.block_n = pick_block_n(N);
+    w.tm = make_tmap(Wt, 2, K, N, 1, K, 0, BK, w.block_n, false);
+    DwW dw;
+    dw.w = const_cast<float*>(dw_w5n); dw.bias = const_cast<float*>(bias); dw.k = 5; dw.C = N;
+    std::vector<Op> ops;
+    PlanCtx c;
+    c.base = reinterpret_cast<uint8_t*>(16);
+    c.ops = &ops;
+    c.B = B;
+    add_gemm_dw(c, w, dw, static_cast<const bf16*>(A), T, K, static_cast<const bf16*>(residual),
+                static_cast<bf16*>(out_raw), static_cast<bf16*>(out_act), act_scale);
     launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
     CK(cudaGetLastError());
   });
