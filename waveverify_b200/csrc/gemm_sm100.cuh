@@ -88,7 +88,12 @@ __host__ inline int gemm_smem_bytes(int block_n, bool staged) {
          gemm_stage_count(block_n, staged) * (A_STAGE_BYTES + block_n * BK * 2);
 }
 
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// ELU(alpha=1): x > 0 ? x : e^x - 1 with one MUFU.EX2 (abs error ~1e-7, far below bf16 output ulp)
+__device__ __forceinline__ float elu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return x > 0.f ? x : e - 1.f;
+}
 __device__ __forceinline__ void epi_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(EPI_THREADS) : "memory");
 }
@@ -200,6 +205,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
     const int h = e >> 2;   // column half: this warp takes chunks c with (c & 1) == h
     const int et = threadIdx.x - 128;   // 0..255
+    // phase-2 work split (STAGED): thread = (8-channel group, 4-row group); 240 threads when the
+    // channel-group count (12, 20, 24) does not divide 256
+    const int p2_cgs = g.block_n >> 3;
+    const int p2_threads = (EPI_THREADS % p2_cgs == 0) ? EPI_THREADS : 240;
+    const int p2_cg = et % p2_cgs, p2_grp0 = et / p2_cgs, p2_gstride = p2_threads / p2_cgs;
+    int cached_nt = -1;
+    float wt[5][8], bs[8];
     int as = 0;
     uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -234,17 +246,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         epi_bar_sync(1);                       // tile staged by all 8 warps
         if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage is free: next MMAs may start
-        // ---- phase 2: coalesced walk, thread = (8-channel group, row segment)
-        {
-          const int cgs = g.block_n >> 3;
-          const int nseg = EPI_THREADS / cgs;
-          const int cg = et % cgs, seg = et / cgs;
-          if (seg < nseg) {
-            const int seg_len = (rows_out + nseg - 1) / nseg;
-            const int ro_begin = seg * seg_len;                       // output-row index in tile
-            const int ro_end = min(ro_begin + seg_len, rows_out);
-            const int c = n0 + cg * 8;
-            float bs[8];
+        // ---- phase 2: coalesced walk; unit = (8-channel group, 4 consecutive output rows)
+        if (et < p2_threads) {
+          const int c = n0 + p2_cg * 8;
+          if (nt != cached_nt) {              // per-CTA constant when N fits one tile
+            cached_nt = nt;
             if (g.bias != nullptr) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c) + 1);
@@ -254,9 +260,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 8; ++i) bs[i] = 0.f;
             }
-            const uint8_t* colp = stage_tile + cg * 16;
             if (g.taps == 5) {
-              float wt[5][8];
 #pragma unroll
               for (int j = 0; j < 5; ++j) {
                 const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
@@ -264,86 +268,85 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
                 wt[j][4] = w1.x; wt[j][5] = w1.y; wt[j][6] = w1.z; wt[j][7] = w1.w;
               }
-              uint4 win[5];
-              // tile row of output row ro is ro + 4; its window is tile rows ro .. ro+4
+            }
+          }
+          const uint8_t* colp = stage_tile + p2_cg * 16;
+          const int n_groups = rows_out >> 2;                         // 31 (taps 5) or 32 (taps 1)
+          const long long clip_off = static_cast<long long>(clip) * g.rows_per_clip;
+          for (int grp = p2_grp0; grp < n_groups; grp += p2_gstride) {
+            const int ro = grp * 4;                                   // tile-relative output row
+            const int r = r_base + ro;
+            if (r >= g.rows_per_clip) break;
+            const int nrow = min(4, g.rows_per_clip - r);
+            const long long off = (clip_off + r) * g.ldo + c;
+            uint4 rres[4];
+            if (g.residual != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                win[j + 1] = *reinterpret_cast<const uint4*>(colp + (ro_begin + j) * pitch);
-              for (int ro = ro_begin; ro < ro_end; ++ro) {
-                const int r = r_base + ro;
-                if (r >= g.rows_per_clip) break;
+              for (int i = 0; i < 4; ++i)
+                rres[i] = i < nrow ? __ldg(reinterpret_cast<const uint4*>(g.residual + off + static_cast<long long>(i) * g.ldo))
+                                   : make_uint4(0, 0, 0, 0);
+            }
+            float o[4][8];
+            if (g.taps == 5) {
+              float x[8][8];                                           // tile rows ro .. ro+7
 #pragma unroll
-                for (int j = 0; j < 4; ++j) win[j] = win[j + 1];
-                win[4] = *reinterpret_cast<const uint4*>(colp + (ro + 4) * pitch);
-                const long long off = (static_cast<long long>(clip) * g.rows_per_clip + r) * g.ldo + c;
-                uint4 rres = make_uint4(0, 0, 0, 0);
-                if (g.residual != nullptr) rres = __ldg(reinterpret_cast<const uint4*>(g.residual + off));
-                float o[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = bs[i];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                  const uint32_t* wu = reinterpret_cast<const uint32_t*>(&win[j]);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    float a, b;
-                    unpack_bf16x2(wu[i], a, b);
-                    o[2 * i] = fmaf(wt[j][2 * i], a, o[2 * i]);
-                    o[2 * i + 1] = fmaf(wt[j][2 * i + 1], b, o[2 * i + 1]);
-                  }
-                }
-                if (g.residual != nullptr) {
-                  const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rres);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    float a, b;
-                    unpack_bf16x2(ru[i], a, b);
-                    o[2 * i] += a;
-                    o[2 * i + 1] += b;
-                  }
-                }
-                if (g.out_raw != nullptr)
-                  *reinterpret_cast<uint4*>(g.out_raw + off) =
-                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                if (g.out_act != nullptr) {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] = elu_fast(o[i] * g.act_scale);
-                  *reinterpret_cast<uint4*>(g.out_act + off) =
-                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                }
+              for (int j = 0; j < 8; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + j) * pitch);
+                unpack_bf16x2(u.x, x[j][0], x[j][1]);
+                unpack_bf16x2(u.y, x[j][2], x[j][3]);
+                unpack_bf16x2(u.z, x[j][4], x[j][5]);
+                unpack_bf16x2(u.w, x[j][6], x[j][7]);
               }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  float a = bs[k];
+#pragma unroll
+                  for (int j = 0; j < 5; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
+                  o[i][k] = a;
+                }
             } else {
-              for (int ro = ro_begin; ro < ro_end; ++ro) {
-                const int r = r_base + ro;
-                if (r >= g.rows_per_clip) break;
-                const uint4 s = *reinterpret_cast<const uint4*>(colp + ro * pitch);
-                const long long off = (static_cast<long long>(clip) * g.rows_per_clip + r) * g.ldo + c;
-                uint4 rres = make_uint4(0, 0, 0, 0);
-                if (g.residual != nullptr) rres = __ldg(reinterpret_cast<const uint4*>(g.residual + off));
-                float o[8];
-                const uint32_t* su = reinterpret_cast<const uint32_t*>(&s);
-                const uint32_t* ru = reinterpret_cast<const uint32_t*>(&rres);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float a, b, ra, rb;
-                  unpack_bf16x2(su[i], a, b);
-                  unpack_bf16x2(ru[i], ra, rb);
-                  o[2 * i] = a + bs[2 * i] + ra;
-                  o[2 * i + 1] = b + bs[2 * i + 1] + rb;
-                }
-                if (g.out_raw != nullptr)
-                  *reinterpret_cast<uint4*>(g.out_raw + off) =
-                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                if (g.out_act != nullptr) {
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + i) * pitch);
+                unpack_bf16x2(u.x, o[i][0], o[i][1]);
+                unpack_bf16x2(u.y, o[i][2], o[i][3]);
+                unpack_bf16x2(u.z, o[i][4], o[i][5]);
+                unpack_bf16x2(u.w, o[i][6], o[i][7]);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) o[i] = elu_fast(o[i] * g.act_scale);
-                  *reinterpret_cast<uint4*>(g.out_act + off) =
-                      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                }
+                for (int k = 0; k < 8; ++k) o[i][k] += bs[k];
+              }
+            }
+            if (g.residual != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float ra[8];
+                unpack_bf16x2(rres[i].x, ra[0], ra[1]);
+                unpack_bf16x2(rres[i].y, ra[2], ra[3]);
+                unpack_bf16x2(rres[i].z, ra[4], ra[5]);
+                unpack_bf16x2(rres[i].w, ra[6], ra[7]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[i][k] += ra[k];
+              }
+            }
+            if (g.out_raw != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (i < nrow)
+                  *reinterpret_cast<uint4*>(g.out_raw + off + static_cast<long long>(i) * g.ldo) =
+                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
+                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
+            }
+            if (g.out_act != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[i][k] = elu_fast(o[i][k] * g.act_scale);
+                if (i < nrow)
+                  *reinterpret_cast<uint4*>(g.out_act + off + static_cast<long long>(i) * g.ldo) =
+                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
+                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
               }
             }
           }
