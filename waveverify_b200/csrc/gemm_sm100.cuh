@@ -1,9 +1,9 @@
 // Pointwise-conv / STFT / head GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (16-bit in, fp32
-// accumulate in TMEM), persistent + warp specialised (384 threads):
+// accumulate in TMEM), persistent + warp specialised (512 threads):
 //   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier ring of 3-6 stages)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, K=16 per instr)
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages x 256)
-//   warps 4-11  epilogue       (tcgen05.ld 32x32b -> registers -> ... -> global)
+//   warps 4-15  epilogue       (tcgen05.ld 32x32b -> registers -> ... -> global)
 // Activations are channels-last [clip, time, channel] so "time" is the MMA M dimension and the
 // channel contraction is K-major for both operands.  A is addressed through a 3-D tensor map
 // (k, row-in-clip, clip): flattened [B*T, C] activations use n_clips = 1; per-clip tiles (with
@@ -37,9 +37,16 @@ constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 12;
+constexpr int EPI_SPLIT = EPI_WARPS / 4;    // warps sharing one TMEM lane quarter split the columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 128 + EPI_THREADS;
+constexpr int P2_ROWS = 4;                  // output rows per phase-2 unit
+constexpr int P1_WARPS = 4;                 // STAGED: TMEM -> smem drain warps (one per lane quarter)
+constexpr int P2_WARPS = EPI_WARPS - P1_WARPS;   // STAGED: smem -> math -> global warps
+constexpr int P2_THREADS = P2_WARPS * 32;
+constexpr int STAGE_BUFS = 2;               // staging tiles (drain of tile i+1 overlaps math of tile i)
+constexpr int STAGED_MAX_BN = 128;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 256;
 
@@ -72,19 +79,19 @@ struct GemmArgs {
   float* logits;
   uint8_t* mask_out;
   float* probs;
-  float* partial;  // [M, 2 * N / block_n]
+  float* partial;  // [M, EPI_SPLIT * N / block_n]
   const uint8_t* presence;
   int hop, T, n_out, head_F;
 };
 
 __host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n * 2 + 16; }
 __host__ inline int gemm_stage_count(int block_n, bool staged) {
-  const int fixed = 1024 + GEMM_BAR_BYTES + (staged ? BM * staged_pitch_bytes(block_n) : 0);
+  const int fixed = 1024 + GEMM_BAR_BYTES + (staged ? STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0);
   int s = (GEMM_SMEM_LIMIT - fixed) / (A_STAGE_BYTES + block_n * BK * 2);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 __host__ inline int gemm_smem_bytes(int block_n, bool staged) {
-  return 1024 + GEMM_BAR_BYTES + (staged ? BM * staged_pitch_bytes(block_n) : 0) +
+  return 1024 + GEMM_BAR_BYTES + (staged ? STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0) +
          gemm_stage_count(block_n, staged) * (A_STAGE_BYTES + block_n * BK * 2);
 }
 
@@ -94,9 +101,18 @@ __device__ __forceinline__ float elu_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
   return x > 0.f ? x : e - 1.f;
 }
-__device__ __forceinline__ void epi_bar_sync(int id) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(EPI_THREADS) : "memory");
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+// 512 threads x 128 registers at launch; the STAGED kernel moves registers from the eight
+// TMA / MMA / drain warps (72 each) to the eight math warps (184 each).
+constexpr int REGS_LIGHT = 72;
+constexpr int REGS_MATH = 184;
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -114,8 +130,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
   uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [ACC_STAGES]
   uint64_t* acc_empty = acc_full + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
-  uint8_t* stage_tile = after + GEMM_BAR_BYTES;   // [BM][pitch] bf16 (STAGED only)
+  uint64_t* st_full = acc_empty + ACC_STAGES;     // [STAGE_BUFS] staging tile written
+  uint64_t* st_empty = st_full + STAGE_BUFS;      // [STAGE_BUFS] staging tile consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_empty + STAGE_BUFS);
+  uint8_t* stage_tiles = after + GEMM_BAR_BYTES;  // [STAGE_BUFS][BM][pitch] bf16 (STAGED only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,7 +159,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : EPI_WARPS);  // one arrive per draining warp
+    }
+    for (int i = 0; i < STAGE_BUFS; ++i) {
+      mbar_init(&st_full[i], P1_WARPS);
+      mbar_init(&st_empty[i], P2_WARPS);
     }
     fence_mbar_init();
   }
@@ -153,6 +175,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    if constexpr (EPI == EPI_STAGED) reg_dealloc<REGS_LIGHT>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -172,6 +195,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    if constexpr (EPI == EPI_STAGED) reg_dealloc<REGS_LIGHT>();
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -199,19 +223,178 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
     }
+  } else if (EPI == EPI_STAGED && warp < 4) {
+    reg_dealloc<REGS_LIGHT>();   // warps 2 (TMEM allocator) and 3: the whole warpgroup must take part
+  } else if (EPI == EPI_STAGED && warp >= 4) {
+    const int pitch = staged_pitch_bytes(g.block_n);
+    const int chunks = g.block_n / 32;
+    if (warp < 4 + P1_WARPS) {
+      // ---------------------------------------------------------- drain warps: TMEM -> bf16 -> smem
+      reg_dealloc<REGS_LIGHT>();
+      const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
+      int as = 0, sb = 0;
+      uint32_t as_phase = 0, sb_phase = 0;
+      uint32_t v[32];
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_full[as], as_phase);
+        mbar_wait(&st_empty[sb], sb_phase ^ 1);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
+        uint8_t* rowp = stage_tiles + sb * (BM * pitch) + (q * 32 + lane) * pitch;
+        for (int c = 0; c < chunks; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          uint4* sp = reinterpret_cast<uint4*>(rowp + c * 64);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sp[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                               pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                               pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                               pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
+          mbar_arrive(&st_full[sb]);     // release: this warp's 32 rows are staged
+        }
+        if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
+        if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+      }
+    } else {
+      // ---------------------------------------------------------- math warps: smem -> epilogue -> global
+      // thread = (8-channel group, P2_ROWS-row group); 240 of 256 threads when the group count
+      // (12, 20, 24) does not divide 256
+      reg_alloc<REGS_MATH>();
+      const int et = threadIdx.x - (128 + P1_WARPS * 32);
+      const int p2_cgs = g.block_n >> 3;
+      const int p2_threads = (P2_THREADS / p2_cgs) * p2_cgs;
+      const int p2_cg = et % p2_cgs, p2_grp0 = et / p2_cgs, p2_gstride = p2_threads / p2_cgs;
+      const int n_groups = rows_out / P2_ROWS;                      // 31 (taps 5) or 32 (taps 1)
+      int cached_nt = -1;
+      float wt[5][8], bs[8];
+      int sb = 0;
+      uint32_t sb_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / tiles_n, nt = tile % tiles_n;
+        const int clip = mt / tiles_m_per_clip;
+        const int r_base = (mt % tiles_m_per_clip) * rows_out;     // first OUTPUT row of the tile
+        const int n0 = nt * g.block_n;
+        const int c = n0 + p2_cg * 8;
+        if (et < p2_threads && nt != cached_nt) {                   // per-CTA constant when N fits one tile
+          cached_nt = nt;
+          if (g.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c) + 1);
+            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+            bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bs[i] = 0.f;
+          }
+          if (g.taps == 5) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c) + 1);
+              wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
+              wt[j][4] = w1.x; wt[j][5] = w1.y; wt[j][6] = w1.z; wt[j][7] = w1.w;
+            }
+          }
+        }
+        mbar_wait(&st_full[sb], sb_phase);
+        if (et < p2_threads) {
+          const uint8_t* colp = stage_tiles + sb * (BM * pitch) + p2_cg * 16;
+          const long long clip_off = static_cast<long long>(clip) * g.rows_per_clip;
+          for (int grp = p2_grp0; grp < n_groups; grp += p2_gstride) {
+            const int ro = grp * P2_ROWS;                             // tile-relative output row
+            const int r = r_base + ro;
+            if (r >= g.rows_per_clip) break;
+            const int nrow = min(P2_ROWS, g.rows_per_clip - r);
+            const long long off = (clip_off + r) * g.ldo + c;
+            uint4 rres[P2_ROWS];
+            if (g.residual != nullptr) {
+#pragma unroll
+              for (int i = 0; i < P2_ROWS; ++i)
+                rres[i] = i < nrow ? __ldg(reinterpret_cast<const uint4*>(g.residual + off + static_cast<long long>(i) * g.ldo))
+                                   : make_uint4(0, 0, 0, 0);
+            }
+            float o[P2_ROWS][8];
+            if (g.taps == 5) {
+              float x[P2_ROWS + 4][8];                                 // tile rows ro .. ro+P2_ROWS+3
+#pragma unroll
+              for (int j = 0; j < P2_ROWS + 4; ++j) {
+                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + j) * pitch);
+                unpack_bf16x2(u.x, x[j][0], x[j][1]);
+                unpack_bf16x2(u.y, x[j][2], x[j][3]);
+                unpack_bf16x2(u.z, x[j][4], x[j][5]);
+                unpack_bf16x2(u.w, x[j][6], x[j][7]);
+              }
+#pragma unroll
+              for (int i = 0; i < P2_ROWS; ++i)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  float a = bs[k];
+#pragma unroll
+                  for (int j = 0; j < 5; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
+                  o[i][k] = a;
+                }
+            } else {
+#pragma unroll
+              for (int i = 0; i < P2_ROWS; ++i) {
+                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + i) * pitch);
+                unpack_bf16x2(u.x, o[i][0], o[i][1]);
+                unpack_bf16x2(u.y, o[i][2], o[i][3]);
+                unpack_bf16x2(u.z, o[i][4], o[i][5]);
+                unpack_bf16x2(u.w, o[i][6], o[i][7]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[i][k] += bs[k];
+              }
+            }
+            if (g.residual != nullptr) {
+#pragma unroll
+              for (int i = 0; i < P2_ROWS; ++i) {
+                float ra[8];
+                unpack_bf16x2(rres[i].x, ra[0], ra[1]);
+                unpack_bf16x2(rres[i].y, ra[2], ra[3]);
+                unpack_bf16x2(rres[i].z, ra[4], ra[5]);
+                unpack_bf16x2(rres[i].w, ra[6], ra[7]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[i][k] += ra[k];
+              }
+            }
+            if (g.out_raw != nullptr) {
+#pragma unroll
+              for (int i = 0; i < P2_ROWS; ++i)
+                if (i < nrow)
+                  *reinterpret_cast<uint4*>(g.out_raw + off + static_cast<long long>(i) * g.ldo) =
+                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
+                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
+            }
+            if (g.out_act != nullptr) {
+#pragma unroll
+              for (int i = 0; i < P2_ROWS; ++i) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[i][k] = elu_fast(o[i][k] * g.act_scale);
+                if (i < nrow)
+                  *reinterpret_cast<uint4*>(g.out_act + off + static_cast<long long>(i) * g.ldo) =
+                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
+                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_empty[sb]);   // this warp no longer reads staging tile sb
+        if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+      }
+    }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------ epilogue (12 warps)
     const int e = warp - 4;
     const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
-    const int h = e >> 2;   // column half: this warp takes chunks c with (c & 1) == h
-    const int et = threadIdx.x - 128;   // 0..255
-    // phase-2 work split (STAGED): thread = (8-channel group, 4-row group); 240 threads when the
-    // channel-group count (12, 20, 24) does not divide 256
-    const int p2_cgs = g.block_n >> 3;
-    const int p2_threads = (EPI_THREADS % p2_cgs == 0) ? EPI_THREADS : 240;
-    const int p2_cg = et % p2_cgs, p2_grp0 = et / p2_cgs, p2_gstride = p2_threads / p2_cgs;
-    int cached_nt = -1;
-    float wt[5][8], bs[8];
+    const int h = e >> 2;   // column split: this warp takes chunks c with c % EPI_SPLIT == h
     int as = 0;
     uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -226,133 +409,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
       uint32_t v[32];
 
-      if constexpr (EPI == EPI_STAGED) {
-        const int pitch = staged_pitch_bytes(g.block_n);
-        // ---- phase 1: TMEM -> bf16 -> padded smem tile (row = TMEM lane)
-        {
-          uint8_t* rowp = stage_tile + (q * 32 + lane) * pitch;
-          for (int c = h; c < chunks; c += 2) {
-            tmem_ld32(taddr + c * 32, v);
-            tmem_ld_wait();
-            uint4* sp = reinterpret_cast<uint4*>(rowp + c * 64);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              sp[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                                 pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                                 pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                                 pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
-          }
-        }
-        tc_fence_before();
-        epi_bar_sync(1);                       // tile staged by all 8 warps
-        if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage is free: next MMAs may start
-        // ---- phase 2: coalesced walk; unit = (8-channel group, 4 consecutive output rows)
-        if (et < p2_threads) {
-          const int c = n0 + p2_cg * 8;
-          if (nt != cached_nt) {              // per-CTA constant when N fits one tile
-            cached_nt = nt;
-            if (g.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c) + 1);
-              bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
-              bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) bs[i] = 0.f;
-            }
-            if (g.taps == 5) {
-#pragma unroll
-              for (int j = 0; j < 5; ++j) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c) + 1);
-                wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
-                wt[j][4] = w1.x; wt[j][5] = w1.y; wt[j][6] = w1.z; wt[j][7] = w1.w;
-              }
-            }
-          }
-          const uint8_t* colp = stage_tile + p2_cg * 16;
-          const int n_groups = rows_out >> 2;                         // 31 (taps 5) or 32 (taps 1)
-          const long long clip_off = static_cast<long long>(clip) * g.rows_per_clip;
-          for (int grp = p2_grp0; grp < n_groups; grp += p2_gstride) {
-            const int ro = grp * 4;                                   // tile-relative output row
-            const int r = r_base + ro;
-            if (r >= g.rows_per_clip) break;
-            const int nrow = min(4, g.rows_per_clip - r);
-            const long long off = (clip_off + r) * g.ldo + c;
-            uint4 rres[4];
-            if (g.residual != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                rres[i] = i < nrow ? __ldg(reinterpret_cast<const uint4*>(g.residual + off + static_cast<long long>(i) * g.ldo))
-                                   : make_uint4(0, 0, 0, 0);
-            }
-            float o[4][8];
-            if (g.taps == 5) {
-              float x[8][8];                                           // tile rows ro .. ro+7
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + j) * pitch);
-                unpack_bf16x2(u.x, x[j][0], x[j][1]);
-                unpack_bf16x2(u.y, x[j][2], x[j][3]);
-                unpack_bf16x2(u.z, x[j][4], x[j][5]);
-                unpack_bf16x2(u.w, x[j][6], x[j][7]);
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  float a = bs[k];
-#pragma unroll
-                  for (int j = 0; j < 5; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
-                  o[i][k] = a;
-                }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + i) * pitch);
-                unpack_bf16x2(u.x, o[i][0], o[i][1]);
-                unpack_bf16x2(u.y, o[i][2], o[i][3]);
-                unpack_bf16x2(u.z, o[i][4], o[i][5]);
-                unpack_bf16x2(u.w, o[i][6], o[i][7]);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[i][k] += bs[k];
-              }
-            }
-            if (g.residual != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float ra[8];
-                unpack_bf16x2(rres[i].x, ra[0], ra[1]);
-                unpack_bf16x2(rres[i].y, ra[2], ra[3]);
-                unpack_bf16x2(rres[i].z, ra[4], ra[5]);
-                unpack_bf16x2(rres[i].w, ra[6], ra[7]);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[i][k] += ra[k];
-              }
-            }
-            if (g.out_raw != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (i < nrow)
-                  *reinterpret_cast<uint4*>(g.out_raw + off + static_cast<long long>(i) * g.ldo) =
-                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
-                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
-            }
-            if (g.out_act != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[i][k] = elu_fast(o[i][k] * g.act_scale);
-                if (i < nrow)
-                  *reinterpret_cast<uint4*>(g.out_act + off + static_cast<long long>(i) * g.ldo) =
-                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
-                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
-              }
-            }
-          }
-        }
-        epi_bar_sync(2);                       // staging tile may be overwritten
-      } else {
+      {
         const int r = r_base + q * 32 + lane;
         const bool row_ok = r < g.rows_per_clip;
         const long long m = static_cast<long long>(clip) * g.rows_per_clip + r;
@@ -395,7 +452,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         } else if constexpr (EPI == EPI_STFT) {
-          for (int c = h; c < chunks; c += 2) {
+          for (int c = h; c < chunks; c += EPI_SPLIT) {
             const int p0 = (n0 + c * 32) >> 1;
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
@@ -429,7 +486,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int j0 = n0 % g.hop;
           const float bo = g.bias ? __ldg(g.bias + o) : 0.f;
           float psum = 0.f;
-          for (int c = h; c < chunks; c += 2) {
+          for (int c = h; c < chunks; c += EPI_SPLIT) {
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
             if (row_ok) {
@@ -450,7 +507,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          if (g.partial != nullptr && row_ok) g.partial[(m * tiles_n + nt) * 2 + h] = psum;
+          if (g.partial != nullptr && row_ok) g.partial[(m * tiles_n + nt) * EPI_SPLIT + h] = psum;
         }
         tc_fence_before();
         __syncwarp();

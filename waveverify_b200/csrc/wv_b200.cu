@@ -88,10 +88,10 @@ CUtensorMap make_tmap(const void* base, int rank, uint64_t dim_k, uint64_t dim_r
   return m;
 }
 
-int pick_block_n(int N, int must_divide = 0) {
+int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
   static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
   for (int c : cands)
-    if (N % c == 0 && (must_divide == 0 || must_divide % c == 0)) return c;
+    if (c <= max_bn && N % c == 0 && (must_divide == 0 || must_divide % c == 0)) return c;
   WV_THROW(WV_ERR_UNSUPPORTED, "no tile width for N=%d", N);
 }
 
@@ -269,7 +269,8 @@ GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias) {
     bb.assign(b->data, b->data + N);
     for (auto& v : bb) v *= scale;
   }
-  return make_gemm_w(W, rows, N, K, false, pick_block_n(N), b ? bb.data() : nullptr, N);
+  // pointwise convs run through the STAGED epilogue (two staging tiles): tile width <= 128
+  return make_gemm_w(W, rows, N, K, false, pick_block_n(N, 0, STAGED_MAX_BN), b ? bb.data() : nullptr, N);
 }
 
 // depthwise [C,1,k] -> [k][C]; transposed conv weights have the same memory shape
@@ -966,7 +967,7 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   const HeadW& h = n.head;
   const long long M = static_cast<long long>(c.B) * F;
   const int tiles_n = h.w.N / h.w.block_n;
-  Buf partial = c.alloc(static_cast<size_t>(M) * tiles_n * 2 * 4);   // two column halves per tile
+  Buf partial = c.alloc(static_cast<size_t>(M) * tiles_n * EPI_SPLIT * 4);   // one slot per column split
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.bias = h.w.bias;
@@ -978,7 +979,7 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
     Op op;
     op.type = OP_BITS;
     op.in = c.ptr<float>(partial);
-    op.i[0] = c.B; op.i[1] = F; op.i[2] = 2 * tiles_n; op.i[3] = 2 * (h.hop / h.w.block_n); op.i[4] = c.T; op.i[5] = h.n_out;
+    op.i[0] = c.B; op.i[1] = F; op.i[2] = EPI_SPLIT * tiles_n; op.i[3] = EPI_SPLIT * (h.hop / h.w.block_n); op.i[4] = c.T; op.i[5] = h.n_out;
     c.tag("head.bits");
     c.push(op);
     Op op2;
@@ -1411,7 +1412,7 @@ int wv_op_gemm(const void* A, int lda, const void* Wt, int ldw, int M, int N, in
     init_device_once();
     GemmW w;
     w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = ldw; w.fp16 = a_is_fp16 != 0;
-    w.block_n = pick_block_n(N);
+    w.block_n = pick_block_n(N, 0, STAGED_MAX_BN);
     w.tm = make_tmap(Wt, 2, K, N, 1, ldw, 0, BK, w.block_n, w.fp16);
     std::vector<Op> ops;
     PlanCtx c;
@@ -1430,7 +1431,7 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
     init_device_once();
     GemmW w;
     w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = K; w.fp16 = false;
-    w.block_n = pick_block_n(N);
+    w.block_n = pick_block_n(N, 0, STAGED_MAX_BN);
     w.tm = make_tmap(Wt, 2, K, N, 1, K, 0, BK, w.block_n, false);
     DwW dw;
     dw.w = const_cast<float*>(dw_w5n); dw.bias = const_cast<float*>(bias); dw.k = 5; dw.C = N;
