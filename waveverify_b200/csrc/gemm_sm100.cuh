@@ -276,6 +276,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float wt[5][8], bs[8];
       int sb = 0;
       uint32_t sb_phase = 0;
+      int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / tiles_n, nt = tile % tiles_n;
         const int clip = mt / tiles_m_per_clip;
@@ -307,7 +308,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (et < p2_threads) {
           const uint8_t* colp = stage_tiles + sb * (BM * pitch) + p2_cg * 16;
           const long long clip_off = static_cast<long long>(clip) * g.rows_per_clip;
-          for (int grp = p2_grp0; grp < n_groups; grp += p2_gstride) {
+          int grp_first = p2_grp0 + rot;
+          if (grp_first >= p2_gstride) grp_first -= p2_gstride;
+          for (int grp = grp_first; grp < n_groups; grp += p2_gstride) {
             const int ro = grp * P2_ROWS;                             // tile-relative output row
             const int r = r_base + ro;
             if (r >= g.rows_per_clip) break;
@@ -388,6 +391,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&st_empty[sb]);   // this warp no longer reads staging tile sb
         if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+        rot += (p2_gstride + 1) >> 1;
+        if (rot >= p2_gstride) rot -= p2_gstride;
       }
     }
   } else if (warp >= 4) {
@@ -468,7 +473,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
                 y[0] = (0.5f * __logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
                 const float yn = (0.5f * __logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
-                yp[g.n_half] = __float2bfloat16_rn(yn);
+                // bin N/2 plus the 7 zero pad columns (ldo = n_half + 8): one 16-byte store
+                *reinterpret_cast<uint4*>(yp + g.n_half) = make_uint4(pack_bf16x2(yn, 0.f), 0u, 0u, 0u);
               }
               uint4* op = reinterpret_cast<uint4*>(yp + p0);
 #pragma unroll

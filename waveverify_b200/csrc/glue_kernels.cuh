@@ -9,6 +9,7 @@ namespace wv {
 struct F8 {
   float v[8];
 };
+// (elu1 comes from ptx_sm100.cuh)
 __device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   F8 r;
@@ -107,11 +108,12 @@ dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 // Causal strided depthwise down-conv k=2r, s=r (modules/seanet.py:759-770; left pad r zeros,
 // right zero padding up to a whole window, modules/conv.py:160-203) + FiLM (seanet.py:928-966):
 //   v[i,c] = bias[c] + sum_{j<2r} w[j][c] * in[i*r - r + j, c];  v = v*gamma[b,band] + beta
+template <int R>
 __global__ void __launch_bounds__(256)
 down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
             const float* __restrict__ bias, const float* __restrict__ film, int film_stride,
             int bands, __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
-            float act_scale, int B, int Tin, int Tout, int C, int r) {
+            float act_scale, int B, int Tin, int Tout, int C) {
   const int C8 = C >> 3;
   const long long total = static_cast<long long>(B) * Tout * C8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -121,21 +123,31 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     const int i = static_cast<int>(rr % Tout);
     const int b = static_cast<int>(rr / Tout);
     const int c = cg * 8;
+    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * Tin) * C + c;
+    const int tb = i * R - R;
+    uint4 xv[2 * R];                       // all 2R window rows in flight before any math
+#pragma unroll
+    for (int j = 0; j < 2 * R; ++j) {
+      const int t = tb + j;
+      xv[j] = (t >= 0 && t < Tin) ? __ldg(reinterpret_cast<const uint4*>(ip + static_cast<long long>(t) * C))
+                                  : make_uint4(0, 0, 0, 0);
+    }
     F8 o;
     if (bias != nullptr) o = ld_f32x8(bias + c);
     else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
     }
-    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * Tin) * C + c;
-    const int tb = i * r - r;
-    for (int j = 0; j < 2 * r; ++j) {
-      const int t = tb + j;
-      if (t < 0 || t >= Tin) continue;
-      const F8 x = ld_bf16x8(ip + static_cast<long long>(t) * C);
-      const F8 wj = ld_f32x8(w + j * C + c);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wj.v[k], x.v[k], o.v[k]);
+    for (int j = 0; j < 2 * R; ++j) {
+      const F8 wj = ld_f32x8(w + j * C + c);
+      float x[8];
+      unpack_bf16x2(xv[j].x, x[0], x[1]);
+      unpack_bf16x2(xv[j].y, x[2], x[3]);
+      unpack_bf16x2(xv[j].z, x[4], x[5]);
+      unpack_bf16x2(xv[j].w, x[6], x[7]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wj.v[k], x[k], o.v[k]);
     }
     if (film != nullptr) {
       const int band = c / (C / bands);
@@ -192,35 +204,48 @@ up_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 // ---------------------------------------------------------------------------------------
 // conv_pre: 1 -> C, k=5 causal, 1/wav_std folded into w (modules/seanet.py:657-664):
 //   v[t,c] = bias[c] + sum_j w[j][c] * x[t-4+j];  out_raw = v, out_act = ELU(v*act_scale)
+constexpr int PRE_TT = 4;   // consecutive time steps per thread (taps loaded once)
 __global__ void __launch_bounds__(256)
 conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_raw,
                 __nv_bfloat16* __restrict__ out_act, float act_scale, int B, int T, int C) {
   const int C8 = C >> 3;
-  const long long total = static_cast<long long>(B) * T * C8;
+  const int runs = (T + PRE_TT - 1) / PRE_TT;
+  const long long total = static_cast<long long>(B) * runs * C8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int cg = static_cast<int>(idx % C8);
     const long long rr = idx / C8;
-    const int t = static_cast<int>(rr % T);
-    const int b = static_cast<int>(rr / T);
+    const int t0 = static_cast<int>(rr % runs) * PRE_TT;
+    const int b = static_cast<int>(rr / runs);
     const int c = cg * 8;
-    F8 o = ld_f32x8(bias + c);
     const float* xp = x + static_cast<long long>(b) * T;
+    float xs[PRE_TT + 4];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const int tt = t - 4 + j;
-      const float xv = tt >= 0 ? __ldg(xp + tt) : 0.f;
-      const F8 wj = ld_f32x8(w + j * C + c);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wj.v[k], xv, o.v[k]);
+    for (int j = 0; j < PRE_TT + 4; ++j) {
+      const int tt = t0 - 4 + j;
+      xs[j] = (tt >= 0 && tt < T) ? __ldg(xp + tt) : 0.f;
     }
-    const long long off = (static_cast<long long>(b) * T + t) * C + c;
-    if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
-    if (out_act != nullptr) {
+    F8 wt[5];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = elu1(o.v[k] * act_scale);
-      st_bf16x8(out_act + off, o);
+    for (int j = 0; j < 5; ++j) wt[j] = ld_f32x8(w + j * C + c);
+    const F8 bs = ld_f32x8(bias + c);
+#pragma unroll
+    for (int s = 0; s < PRE_TT; ++s) {
+      const int t = t0 + s;
+      if (t >= T) break;
+      F8 o = bs;
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wt[j].v[k], xs[s + j], o.v[k]);
+      const long long off = (static_cast<long long>(b) * T + t) * C + c;
+      if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+      if (out_act != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = elu1(o.v[k] * act_scale);
+        st_bf16x8(out_act + off, o);
+      }
     }
   }
 }

@@ -252,7 +252,7 @@ GemmW make_gemm_w(Weights& W, const std::vector<float>& rows, int N, int K, bool
           fp16 ? f2h(rows[static_cast<size_t>(n) * K + k]) : f2bf(rows[static_cast<size_t>(n) * K + k]);
   g.w = W.dev.upload(h);
   if (bias) g.bias = W.dev.upload(std::vector<float>(bias, bias + n_bias));
-  g.tm = make_tmap(g.w, 2, K, N, 1, g.ldw, 0, BK, block_n, fp16);
+  g.tm = make_tmap(g.w, 2, g.ldw, N, 1, g.ldw, 0, BK, block_n, fp16);   // padded K (zeros)
   return g;
 }
 
@@ -791,7 +791,9 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
   }
   Aout = c.alloc(static_cast<size_t>(M) * C * 2);
   c.tag(name + ".out");
-  add_gemm(c, EPI_STAGED, s.layer, c.ptr<bf16>(Y), ldy, M, K2,
+  // contraction over the padded width ldy (pad columns of Y and of the weights are zero): a TMA
+  // inner extent of 33/65/.. elements is not a multiple of 16 B and loads slowly
+  add_gemm(c, EPI_STAGED, s.layer, c.ptr<bf16>(Y), ldy, M, ldy,
            std_args(nullptr, c.ptr<bf16>(X), nullptr, c.ptr<bf16>(Aout), act_scale, C));
   c.release(Y);
   c.release(X);
@@ -837,7 +839,7 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     op.w = e.conv_pre.w; op.bias = e.conv_pre.bias;
     op.fa = e.stages[0].res[0].pre_scale;
     op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
-    op.grid = elem_grid(static_cast<long long>(B) * Ts * (C / 8));
+    op.grid = elem_grid(static_cast<long long>(B) * ceil_div(Ts, PRE_TT) * (C / 8));
     op.flops = 10.0 * B * Ts * C;
     op.bytes = static_cast<double>(B) * Ts * (4.0 + 4.0 * C);
     op.out_bytes[0] = op.out_bytes[1] = static_cast<size_t>(B) * Ts * C * 2;
@@ -1057,6 +1059,21 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
   return ref;
 }
 
+void launch_down(int grid, cudaStream_t st, const bf16* in, const float* w, const float* bias, const float* film,
+                 int film_stride, int bands, bf16* out_raw, bf16* out_act, float act_scale, int B, int Tin, int Tout,
+                 int C, int r) {
+  switch (r) {
+#define WV_DOWN_CASE(R)                                                                                      \
+  case R:                                                                                                    \
+    down_kernel<R><<<grid, 256, 0, st>>>(in, w, bias, film, film_stride, bands, out_raw, out_act, act_scale, \
+                                         B, Tin, Tout, C);                                                   \
+    break;
+    WV_DOWN_CASE(2) WV_DOWN_CASE(3) WV_DOWN_CASE(4) WV_DOWN_CASE(5) WV_DOWN_CASE(6) WV_DOWN_CASE(8)
+#undef WV_DOWN_CASE
+    default: WV_THROW(WV_ERR_UNSUPPORTED, "stride %d is not supported (2, 3, 4, 5, 6, 8)", r);
+  }
+}
+
 void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(op.i[7]);
   switch (op.epi) {
@@ -1097,8 +1114,8 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
                                             static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
         break;
       case OP_DOWN:
-        down_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, op.bias, op.film, op.i[5], op.i[6],
-                                             static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]);
+        launch_down(op.grid, st, static_cast<const bf16*>(op.in), op.w, op.bias, op.film, op.i[5], op.i[6],
+                    static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]);
         break;
       case OP_UP:
         up_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3]);
@@ -1463,9 +1480,9 @@ int wv_op_down(const void* in, const float* wkc, const float* bias, const float*
   return guarded([&] {
     init_device_once();
     const int To = ceil_div(Tin, r);
-    down_kernel<<<elem_grid(static_cast<long long>(B) * To * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(in), wkc, bias, film, film_stride, bands, static_cast<bf16*>(out_raw),
-        static_cast<bf16*>(out_act), act_scale, B, Tin, To, C, r);
+    launch_down(elem_grid(static_cast<long long>(B) * To * (C / 8)), static_cast<cudaStream_t>(stream),
+                static_cast<const bf16*>(in), wkc, bias, film, film_stride, bands, static_cast<bf16*>(out_raw),
+                static_cast<bf16*>(out_act), act_scale, B, Tin, To, C, r);
     CK(cudaGetLastError());
   });
 }
