@@ -6,9 +6,12 @@ C ABI in include/wv_b200.h.  No CPU fallback.
 """
 from .audio import AudioSignal
 from .models import (AudioWatermarking, Detector, Generator, Locator, ber_miou, metric_counters)
+from .api import (WaveVerify, embed_streaming, load_audio, message_to_tensor, save_audio, tensor_to_message)
 from .params import NetConfig, config_from_kwargs, fixture_state_dict, param_spec
+from .watermark_id import WatermarkID
 
 __all__ = [
     "AudioSignal", "AudioWatermarking", "Detector", "Generator", "Locator", "NetConfig",
-    "ber_miou", "config_from_kwargs", "fixture_state_dict", "metric_counters", "param_spec",
+    "WaveVerify", "WatermarkID", "embed_streaming", "load_audio", "message_to_tensor", "save_audio",
+    "tensor_to_message", "ber_miou", "config_from_kwargs", "fixture_state_dict", "metric_counters", "param_spec",
 ]
