@@ -1,9 +1,9 @@
 // Pointwise-conv / STFT / head GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T  (16-bit in, fp32
-// accumulate in TMEM), persistent + warp specialised (512 threads):
+// accumulate in TMEM), persistent + warp specialised (640 threads, 1 CTA per SM):
 //   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier ring of 3-6 stages)
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1, M=128, N=block_n, K=16 per instr)
 //   warp 2      TMEM allocator (512 columns = 2 accumulator stages x 256)
-//   warps 4-15  epilogue       (tcgen05.ld 32x32b -> registers -> ... -> global)
+//   warps 4-19  epilogue       (tcgen05.ld 32x32b -> registers -> ... -> global)
 // Activations are channels-last [clip, time, channel] so "time" is the MMA M dimension and the
 // channel contraction is K-major for both operands.  A is addressed through a 3-D tensor map
 // (k, row-in-clip, clip): flattened [B*T, C] activations use n_clips = 1; per-clip tiles (with
@@ -11,13 +11,15 @@
 // overlapping STFT frame view of the padded waveform.
 //
 // Epilogues (template EPI):
-//   STAGED  the fp32 accumulator tile is rounded to bf16 into a padded shared-memory tile, the
-//           TMEM stage is released (the next tile's MMAs overlap the rest), then all 256
-//           epilogue threads walk the tile in a coalesced (row, 8-channel) layout:
+//   STAGED  warps 4-7 ("drain") round the fp32 accumulator tile to bf16 into one of two padded
+//           shared-memory tiles and release the TMEM stage; warps 8-19 ("math", 112 registers via
+//           setmaxnreg) walk the staged tile in a coalesced (4 rows x 4 channels) layout:
 //             v = bias[c] + sum_{j<taps} w[j][c] * S[r-taps+1+j][c]      taps = 1 or 5
 //             v += residual[m,c];  out_raw = bf16(v);  out_act = bf16(ELU(v*s))
 //           taps = 5 fuses the causal depthwise conv that follows every resblock 1x1
 //           (modules/seanet.py:85-109): tiles overlap by 4 rows (128 rows in, 124 out).
+//           The math loop is compiled per (taps, residual, raw, act) combination so the hot loop
+//           carries no runtime feature tests.
 //   L2NORM  v = acc + bias;  v *= scale / max(||v||_2 over N, 1e-12)      (modules/seanet.py:288)
 //   STFT    columns are (re,im) pairs: y = (0.5*ln(max(re^2+im^2, c)) - mu) / sigma
 //           (modules/conv.py:1076 + modules/seanet.py:482-494); pair 0 carries the two purely
@@ -37,11 +39,11 @@ constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_WARPS = 12;
+constexpr int EPI_WARPS = 16;
 constexpr int EPI_SPLIT = EPI_WARPS / 4;    // warps sharing one TMEM lane quarter split the columns
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 128 + EPI_THREADS;
-constexpr int P2_ROWS = 4;                  // output rows per phase-2 unit
+constexpr int P2_ROWS = 4;                  // output rows per math unit
 constexpr int P1_WARPS = 4;                 // STAGED: TMEM -> smem drain warps (one per lane quarter)
 constexpr int P2_WARPS = EPI_WARPS - P1_WARPS;   // STAGED: smem -> math -> global warps
 constexpr int P2_THREADS = P2_WARPS * 32;
@@ -59,6 +61,9 @@ struct GemmArgs {
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
   uint32_t idesc;
+  // tile -> (m tile, n tile, clip) without integer division (host computed)
+  int tiles_n, tiles_m_per_clip, num_tiles;
+  uint32_t magic_n, magic_m;   // floor(2^32 / d)
   // STAGED
   int taps;           // 1, or 5 = fused causal depthwise conv over time
   const float* dw_w;  // [taps][N] fp32 (taps == 5)
@@ -109,11 +114,181 @@ template <int N>
 __device__ __forceinline__ void reg_alloc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
-// 512 threads x 128 registers at launch; the STAGED kernel moves registers from the eight
-// TMA / MMA / drain warps (72 each) to the eight math warps (184 each).
-constexpr int REGS_LIGHT = 72;
-constexpr int REGS_MATH = 184;
+// 640 threads x 96 registers at launch = 61440 (only registers released by this CTA's own warps
+// can be re-acquired): the TMA / MMA warpgroup drops to 40, the drain warpgroup keeps 96, the
+// twelve math warps grow to 112:  128*40 + 128*96 + 384*112 = 60416 <= 61440.
+constexpr int REGS_LIGHT = 40;
+constexpr int REGS_DRAIN = 96;
+constexpr int REGS_MATH = 112;
+static_assert(128 * REGS_LIGHT + 128 * REGS_DRAIN + (GEMM_THREADS - 256) * REGS_MATH <= GEMM_THREADS * 96,
+              "setmaxnreg budget exceeds the CTA's launch allocation");
 
+// q = x / d, r = x % d with a host-computed magic = floor(2^32 / d): one mul.hi + one fix-up.
+__device__ __forceinline__ void fast_divmod(uint32_t x, uint32_t d, uint32_t magic, int& q, int& r) {
+  uint32_t qq = __umulhi(x, magic);
+  uint32_t rr = x - qq * d;
+  if (rr >= d) { ++qq; rr -= d; }
+  q = static_cast<int>(qq);
+  r = static_cast<int>(rr);
+}
+struct TileCoord {
+  int clip, mi, nt;   // clip, m tile inside the clip, n tile
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
+  TileCoord t;
+  int mt;
+  if (g.tiles_n == 1) { mt = tile; t.nt = 0; }
+  else fast_divmod(static_cast<uint32_t>(tile), static_cast<uint32_t>(g.tiles_n), g.magic_n, mt, t.nt);
+  if (g.n_clips == 1) { t.clip = 0; t.mi = mt; }
+  else fast_divmod(static_cast<uint32_t>(mt), static_cast<uint32_t>(g.tiles_m_per_clip), g.magic_m, t.clip, t.mi);
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// STAGED math warps.  thread = (4-channel group, 4-row group): 8-byte smem reads / global accesses
+// keep a warp on contiguous 256-byte row segments while the per-thread state stays under 112 regs.
+template <int TAPS, bool RES, bool RAW, bool ACT>
+__device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles,
+                                                 uint64_t* st_full, uint64_t* st_empty, int lane) {
+  constexpr int HALO = TAPS - 1;
+  constexpr int ROWS_OUT = BM - HALO;
+  constexpr int N_GROUPS = ROWS_OUT / P2_ROWS;                   // 31 (taps 5) or 32 (taps 1)
+  const int pitch = staged_pitch_bytes(g.block_n);
+  const int et = threadIdx.x - (128 + P1_WARPS * 32);
+  const int cgs = g.block_n >> 2;                                // 4-channel groups per row
+  const int gstride = P2_THREADS / cgs;                          // row groups per pass
+  const int cg = et % cgs, grp0 = et / cgs;
+  const bool active = grp0 < gstride;
+  const size_t row_bytes = static_cast<size_t>(g.ldo) * 2;
+  const float s_act = g.act_scale;
+  int cached_nt = -1;
+  float wt[TAPS][4], bs[4];
+  int sb = 0;
+  uint32_t sb_phase = 0;
+  int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
+  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+    const TileCoord tc = tile_coord(g, tile);
+    const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
+    const int c = tc.nt * g.block_n + cg * 4;
+    if (active && tc.nt != cached_nt) {                            // per-CTA constant when N fits one tile
+      cached_nt = tc.nt;
+      if (g.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+        bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+      } else {
+        bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
+      }
+      if constexpr (TAPS > 1) {
+#pragma unroll
+        for (int j = 0; j < TAPS; ++j) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
+          wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
+        }
+      }
+    }
+    mbar_wait(&st_full[sb], sb_phase);
+    if (active) {
+      const uint8_t* colp = stage_tiles + sb * (BM * pitch) + cg * 8;
+      const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base) * g.ldo + c;
+      const int rows_left = g.rows_per_clip - r_base;             // valid output rows from r_base on
+      int grp = grp0 + rot;
+      if (grp >= gstride) grp -= gstride;
+      for (; grp < N_GROUPS; grp += gstride) {
+        const int ro = grp * P2_ROWS;                              // tile-relative output row
+        if (ro >= rows_left) break;
+        const bool full = ro + P2_ROWS <= rows_left;
+        const size_t off = base + static_cast<size_t>(ro) * g.ldo;
+        uint2 rres[P2_ROWS];
+        if constexpr (RES) {
+          const char* rp = reinterpret_cast<const char*>(g.residual + off);
+#pragma unroll
+          for (int i = 0; i < P2_ROWS; ++i)
+            rres[i] = (full || ro + i < rows_left) ? __ldg(reinterpret_cast<const uint2*>(rp + i * row_bytes))
+                                                   : make_uint2(0u, 0u);
+        }
+        float o[P2_ROWS][4];
+        if constexpr (TAPS > 1) {
+          float x[P2_ROWS + HALO][4];                              // tile rows ro .. ro+P2_ROWS+HALO-1
+#pragma unroll
+          for (int j = 0; j < P2_ROWS + HALO; ++j) {
+            const uint2 u = *reinterpret_cast<const uint2*>(colp + (ro + j) * pitch);
+            unpack_bf16x2(u.x, x[j][0], x[j][1]);
+            unpack_bf16x2(u.y, x[j][2], x[j][3]);
+          }
+#pragma unroll
+          for (int i = 0; i < P2_ROWS; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float a = bs[k];
+#pragma unroll
+              for (int j = 0; j < TAPS; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
+              o[i][k] = a;
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < P2_ROWS; ++i) {
+            const uint2 u = *reinterpret_cast<const uint2*>(colp + (ro + i) * pitch);
+            unpack_bf16x2(u.x, o[i][0], o[i][1]);
+            unpack_bf16x2(u.y, o[i][2], o[i][3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[i][k] += bs[k];
+          }
+        }
+        if constexpr (RES) {
+#pragma unroll
+          for (int i = 0; i < P2_ROWS; ++i) {
+            float ra[4];
+            unpack_bf16x2(rres[i].x, ra[0], ra[1]);
+            unpack_bf16x2(rres[i].y, ra[2], ra[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[i][k] += ra[k];
+          }
+        }
+        if constexpr (RAW) {
+          char* op = reinterpret_cast<char*>(g.out_raw + off);
+#pragma unroll
+          for (int i = 0; i < P2_ROWS; ++i)
+            if (full || ro + i < rows_left)
+              *reinterpret_cast<uint2*>(op + i * row_bytes) =
+                  make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
+        }
+        if constexpr (ACT) {
+          char* op = reinterpret_cast<char*>(g.out_act + off);
+#pragma unroll
+          for (int i = 0; i < P2_ROWS; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[i][k] = elu_fast(o[i][k] * s_act);
+            if (full || ro + i < rows_left)
+              *reinterpret_cast<uint2*>(op + i * row_bytes) =
+                  make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&st_empty[sb]);   // this warp no longer reads staging tile sb
+    if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+    rot += (gstride + 1) >> 1;
+    if (rot >= gstride) rot -= gstride;
+  }
+}
+
+template <int TAPS>
+__device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const uint8_t* stage_tiles,
+                                                     uint64_t* st_full, uint64_t* st_empty, int lane) {
+  const bool res = g.residual != nullptr, raw = g.out_raw != nullptr, act = g.out_act != nullptr;
+  if (res) {
+    if (raw && act) staged_math_loop<TAPS, true, true, true>(g, stage_tiles, st_full, st_empty, lane);
+    else if (raw) staged_math_loop<TAPS, true, true, false>(g, stage_tiles, st_full, st_empty, lane);
+    else staged_math_loop<TAPS, true, false, true>(g, stage_tiles, st_full, st_empty, lane);
+  } else {
+    if (raw && act) staged_math_loop<TAPS, false, true, true>(g, stage_tiles, st_full, st_empty, lane);
+    else if (raw) staged_math_loop<TAPS, false, true, false>(g, stage_tiles, st_full, st_empty, lane);
+    else staged_math_loop<TAPS, false, false, true>(g, stage_tiles, st_full, st_empty, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -141,10 +316,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // tile geometry: STAGED with taps>1 walks each clip in overlapping tiles (halo = taps-1 rows)
   const int halo = (EPI == EPI_STAGED) ? g.taps - 1 : 0;
   const int rows_out = BM - halo;
-  const int tiles_m_per_clip = (g.rows_per_clip + rows_out - 1) / rows_out;
-  const int tiles_m = tiles_m_per_clip * g.n_clips;
-  const int tiles_n = g.N / g.block_n;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (g.K + BK - 1) / BK;
   const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
 
@@ -179,15 +350,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / tiles_n, nt = tile % tiles_n;
-        const int clip = mt / tiles_m_per_clip;
-        const int r0 = (mt % tiles_m_per_clip) * rows_out - halo;   // may be negative: zero fill
-        const int n0 = nt * g.block_n;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(g, tile);
+        const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
+        const int n0 = tc.nt * g.block_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
-          tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, clip);
+          tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
           tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
@@ -196,18 +366,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if constexpr (EPI == EPI_STAGED) reg_dealloc<REGS_LIGHT>();
-    int stage = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t as_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&acc_empty[as], as_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * MAX_BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t as_phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[as], as_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * MAX_BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + stage * A_STAGE_BYTES));
           const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * b_stage_bytes));
 #pragma unroll
@@ -217,11 +387,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&acc_full[as]);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
       }
-      if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
     }
   } else if (EPI == EPI_STAGED && warp < 4) {
     reg_dealloc<REGS_LIGHT>();   // warps 2 (TMEM allocator) and 3: the whole warpgroup must take part
@@ -230,12 +399,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int chunks = g.block_n / 32;
     if (warp < 4 + P1_WARPS) {
       // ---------------------------------------------------------- drain warps: TMEM -> bf16 -> smem
-      reg_dealloc<REGS_LIGHT>();
+      static_assert(REGS_DRAIN == 96, "drain warps keep their launch allocation (65536 / 640 -> 96)");
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
       int as = 0, sb = 0;
       uint32_t as_phase = 0, sb_phase = 0;
       uint32_t v[32];
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_full[as], as_phase);
         mbar_wait(&st_empty[sb], sb_phase ^ 1);
         tc_fence_after();
@@ -264,148 +433,21 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global
-      // thread = (8-channel group, P2_ROWS-row group); 240 of 256 threads when the group count
-      // (12, 20, 24) does not divide 256
       reg_alloc<REGS_MATH>();
-      const int et = threadIdx.x - (128 + P1_WARPS * 32);
-      const int p2_cgs = g.block_n >> 3;
-      const int p2_threads = (P2_THREADS / p2_cgs) * p2_cgs;
-      const int p2_cg = et % p2_cgs, p2_grp0 = et / p2_cgs, p2_gstride = p2_threads / p2_cgs;
-      const int n_groups = rows_out / P2_ROWS;                      // 31 (taps 5) or 32 (taps 1)
-      int cached_nt = -1;
-      float wt[5][8], bs[8];
-      int sb = 0;
-      uint32_t sb_phase = 0;
-      int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / tiles_n, nt = tile % tiles_n;
-        const int clip = mt / tiles_m_per_clip;
-        const int r_base = (mt % tiles_m_per_clip) * rows_out;     // first OUTPUT row of the tile
-        const int n0 = nt * g.block_n;
-        const int c = n0 + p2_cg * 8;
-        if (et < p2_threads && nt != cached_nt) {                   // per-CTA constant when N fits one tile
-          cached_nt = nt;
-          if (g.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + c) + 1);
-            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
-            bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bs[i] = 0.f;
-          }
-          if (g.taps == 5) {
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c) + 1);
-              wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
-              wt[j][4] = w1.x; wt[j][5] = w1.y; wt[j][6] = w1.z; wt[j][7] = w1.w;
-            }
-          }
-        }
-        mbar_wait(&st_full[sb], sb_phase);
-        if (et < p2_threads) {
-          const uint8_t* colp = stage_tiles + sb * (BM * pitch) + p2_cg * 16;
-          const long long clip_off = static_cast<long long>(clip) * g.rows_per_clip;
-          int grp_first = p2_grp0 + rot;
-          if (grp_first >= p2_gstride) grp_first -= p2_gstride;
-          for (int grp = grp_first; grp < n_groups; grp += p2_gstride) {
-            const int ro = grp * P2_ROWS;                             // tile-relative output row
-            const int r = r_base + ro;
-            if (r >= g.rows_per_clip) break;
-            const int nrow = min(P2_ROWS, g.rows_per_clip - r);
-            const long long off = (clip_off + r) * g.ldo + c;
-            uint4 rres[P2_ROWS];
-            if (g.residual != nullptr) {
-#pragma unroll
-              for (int i = 0; i < P2_ROWS; ++i)
-                rres[i] = i < nrow ? __ldg(reinterpret_cast<const uint4*>(g.residual + off + static_cast<long long>(i) * g.ldo))
-                                   : make_uint4(0, 0, 0, 0);
-            }
-            float o[P2_ROWS][8];
-            if (g.taps == 5) {
-              float x[P2_ROWS + 4][8];                                 // tile rows ro .. ro+P2_ROWS+3
-#pragma unroll
-              for (int j = 0; j < P2_ROWS + 4; ++j) {
-                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + j) * pitch);
-                unpack_bf16x2(u.x, x[j][0], x[j][1]);
-                unpack_bf16x2(u.y, x[j][2], x[j][3]);
-                unpack_bf16x2(u.z, x[j][4], x[j][5]);
-                unpack_bf16x2(u.w, x[j][6], x[j][7]);
-              }
-#pragma unroll
-              for (int i = 0; i < P2_ROWS; ++i)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  float a = bs[k];
-#pragma unroll
-                  for (int j = 0; j < 5; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
-                  o[i][k] = a;
-                }
-            } else {
-#pragma unroll
-              for (int i = 0; i < P2_ROWS; ++i) {
-                const uint4 u = *reinterpret_cast<const uint4*>(colp + (ro + i) * pitch);
-                unpack_bf16x2(u.x, o[i][0], o[i][1]);
-                unpack_bf16x2(u.y, o[i][2], o[i][3]);
-                unpack_bf16x2(u.z, o[i][4], o[i][5]);
-                unpack_bf16x2(u.w, o[i][6], o[i][7]);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[i][k] += bs[k];
-              }
-            }
-            if (g.residual != nullptr) {
-#pragma unroll
-              for (int i = 0; i < P2_ROWS; ++i) {
-                float ra[8];
-                unpack_bf16x2(rres[i].x, ra[0], ra[1]);
-                unpack_bf16x2(rres[i].y, ra[2], ra[3]);
-                unpack_bf16x2(rres[i].z, ra[4], ra[5]);
-                unpack_bf16x2(rres[i].w, ra[6], ra[7]);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[i][k] += ra[k];
-              }
-            }
-            if (g.out_raw != nullptr) {
-#pragma unroll
-              for (int i = 0; i < P2_ROWS; ++i)
-                if (i < nrow)
-                  *reinterpret_cast<uint4*>(g.out_raw + off + static_cast<long long>(i) * g.ldo) =
-                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
-                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
-            }
-            if (g.out_act != nullptr) {
-#pragma unroll
-              for (int i = 0; i < P2_ROWS; ++i) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[i][k] = elu_fast(o[i][k] * g.act_scale);
-                if (i < nrow)
-                  *reinterpret_cast<uint4*>(g.out_act + off + static_cast<long long>(i) * g.ldo) =
-                      make_uint4(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]),
-                                 pack_bf16x2(o[i][4], o[i][5]), pack_bf16x2(o[i][6], o[i][7]));
-              }
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st_empty[sb]);   // this warp no longer reads staging tile sb
-        if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
-        rot += (p2_gstride + 1) >> 1;
-        if (rot >= p2_gstride) rot -= p2_gstride;
-      }
+      if (g.taps == 5) staged_math_dispatch<5>(g, stage_tiles, st_full, st_empty, lane);
+      else staged_math_dispatch<1>(g, stage_tiles, st_full, st_empty, lane);
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (12 warps)
+    // ------------------------------------------------------------ epilogue (16 warps)
     const int e = warp - 4;
     const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
     const int h = e >> 2;   // column split: this warp takes chunks c with c % EPI_SPLIT == h
     int as = 0;
     uint32_t as_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / tiles_n, nt = tile % tiles_n;
-      const int clip = mt / tiles_m_per_clip;
-      const int r_base = (mt % tiles_m_per_clip) * rows_out;   // first OUTPUT row of the tile
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(g, tile);
+      const int nt = tc.nt, clip = tc.clip;
+      const int r_base = tc.mi * rows_out;   // first OUTPUT row of the tile
       const int n0 = nt * g.block_n;
       const int chunks = g.block_n / 32;
       mbar_wait(&acc_full[as], as_phase);
@@ -513,7 +555,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
           }
-          if (g.partial != nullptr && row_ok) g.partial[(m * tiles_n + nt) * EPI_SPLIT + h] = psum;
+          if (g.partial != nullptr && row_ok) g.partial[(m * g.tiles_n + nt) * EPI_SPLIT + h] = psum;
         }
         tc_fence_before();
         __syncwarp();

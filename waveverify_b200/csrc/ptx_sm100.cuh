@@ -40,11 +40,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap instead of hanging the GPU box.
+// Bounded wait: a protocol bug must trap within ~2 s instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if ((++spins & 0xFFF) == 0 && clock64() - t0 > 4000000000LL) {
       printf("wv: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -497,7 +497,17 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   op.out0 = g.out_raw;
   op.out1 = g.out_act;
   const int rows_out = BM - (staged ? g.taps - 1 : 0);
-  const int tiles = ceil_div(g.rows_per_clip, rows_out) * g.n_clips * (w.N / w.block_n);
+  g.tiles_n = w.N / w.block_n;
+  g.tiles_m_per_clip = ceil_div(g.rows_per_clip, rows_out);
+  g.magic_n = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(g.tiles_n));
+  g.magic_m = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(g.tiles_m_per_clip));
+  if (g.tiles_n == 1) g.magic_n = 0;            // 2^32 / 1 does not fit; the kernel special-cases 1
+  if (g.tiles_m_per_clip == 1) g.magic_m = 0xFFFFFFFFu;   // x * (2^32-1) >> 32 = x - 1, fixed up in-kernel
+  const long long tiles_ll = static_cast<long long>(g.tiles_m_per_clip) * g.n_clips * g.tiles_n;
+  if (tiles_ll >= (1ll << 31)) WV_THROW(WV_ERR_UNSUPPORTED, "too many tiles (%lld)", tiles_ll);
+  const int tiles = static_cast<int>(tiles_ll);
+  g.num_tiles = tiles;
+  op.g = g;
   op.grid = std::min(tiles, g_num_sms);
   {
     const double Mt = static_cast<double>(g.rows_per_clip) * g.n_clips;
