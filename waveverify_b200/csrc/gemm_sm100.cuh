@@ -145,6 +145,88 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// explicit shared-state accesses (32-bit addresses; generic pointers cost 64-bit address math)
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// One math unit: P2_ROWS output rows x 4 channels.  FULL = all rows valid (no predicates).
+template <int TAPS, bool RES, bool RAW, bool ACT, bool FULL>
+__device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*smem addr of tile row ro*/,
+                                            int pitch, size_t off, size_t row_bytes, int nrow,
+                                            const float (&wt)[TAPS][4], const float (&bs)[4], float s_act) {
+  constexpr int HALO = TAPS - 1;
+  uint2 rres[P2_ROWS];
+  if constexpr (RES) {
+    const char* rp = reinterpret_cast<const char*>(g.residual + off);
+#pragma unroll
+    for (int i = 0; i < P2_ROWS; ++i)
+      rres[i] = (FULL || i < nrow) ? __ldg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
+  }
+  float o[P2_ROWS][4];
+  if constexpr (TAPS > 1) {
+    float x[P2_ROWS + HALO][4];                              // tile rows ro .. ro+P2_ROWS+HALO-1
+#pragma unroll
+    for (int j = 0; j < P2_ROWS + HALO; ++j) {
+      const uint2 u = lds_u2(srow + j * pitch);
+      unpack_bf16x2(u.x, x[j][0], x[j][1]);
+      unpack_bf16x2(u.y, x[j][2], x[j][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < P2_ROWS; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float a = bs[k];
+#pragma unroll
+        for (int j = 0; j < TAPS; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
+        o[i][k] = a;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < P2_ROWS; ++i) {
+      const uint2 u = lds_u2(srow + i * pitch);
+      unpack_bf16x2(u.x, o[i][0], o[i][1]);
+      unpack_bf16x2(u.y, o[i][2], o[i][3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[i][k] += bs[k];
+    }
+  }
+  if constexpr (RES) {
+#pragma unroll
+    for (int i = 0; i < P2_ROWS; ++i) {
+      float ra[4];
+      unpack_bf16x2(rres[i].x, ra[0], ra[1]);
+      unpack_bf16x2(rres[i].y, ra[2], ra[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[i][k] += ra[k];
+    }
+  }
+  if constexpr (RAW) {
+    char* op = reinterpret_cast<char*>(g.out_raw + off);
+#pragma unroll
+    for (int i = 0; i < P2_ROWS; ++i)
+      if (FULL || i < nrow)
+        *reinterpret_cast<uint2*>(op + i * row_bytes) =
+            make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
+  }
+  if constexpr (ACT) {
+    char* op = reinterpret_cast<char*>(g.out_act + off);
+#pragma unroll
+    for (int i = 0; i < P2_ROWS; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[i][k] = elu_fast(o[i][k] * s_act);
+      if (FULL || i < nrow)
+        *reinterpret_cast<uint2*>(op + i * row_bytes) =
+            make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
+    }
+  }
+}
+
 // STAGED math warps.  thread = (4-channel group, 4-row group): 8-byte smem reads / global accesses
 // keep a warp on contiguous 256-byte row segments while the per-thread state stays under 112 regs.
 template <int TAPS, bool RES, bool RAW, bool ACT>
@@ -161,6 +243,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   const bool active = grp0 < gstride;
   const size_t row_bytes = static_cast<size_t>(g.ldo) * 2;
   const float s_act = g.act_scale;
+  const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
   int cached_nt = -1;
   float wt[TAPS][4], bs[4];
   int sb = 0;
@@ -188,7 +271,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     }
     mbar_wait(&st_full[sb], sb_phase);
     if (active) {
-      const uint8_t* colp = stage_tiles + sb * (BM * pitch) + cg * 8;
+      const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
       const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base) * g.ldo + c;
       const int rows_left = g.rows_per_clip - r_base;             // valid output rows from r_base on
       int grp = grp0 + rot;
@@ -196,73 +279,12 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       for (; grp < N_GROUPS; grp += gstride) {
         const int ro = grp * P2_ROWS;                              // tile-relative output row
         if (ro >= rows_left) break;
-        const bool full = ro + P2_ROWS <= rows_left;
         const size_t off = base + static_cast<size_t>(ro) * g.ldo;
-        uint2 rres[P2_ROWS];
-        if constexpr (RES) {
-          const char* rp = reinterpret_cast<const char*>(g.residual + off);
-#pragma unroll
-          for (int i = 0; i < P2_ROWS; ++i)
-            rres[i] = (full || ro + i < rows_left) ? __ldg(reinterpret_cast<const uint2*>(rp + i * row_bytes))
-                                                   : make_uint2(0u, 0u);
-        }
-        float o[P2_ROWS][4];
-        if constexpr (TAPS > 1) {
-          float x[P2_ROWS + HALO][4];                              // tile rows ro .. ro+P2_ROWS+HALO-1
-#pragma unroll
-          for (int j = 0; j < P2_ROWS + HALO; ++j) {
-            const uint2 u = *reinterpret_cast<const uint2*>(colp + (ro + j) * pitch);
-            unpack_bf16x2(u.x, x[j][0], x[j][1]);
-            unpack_bf16x2(u.y, x[j][2], x[j][3]);
-          }
-#pragma unroll
-          for (int i = 0; i < P2_ROWS; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float a = bs[k];
-#pragma unroll
-              for (int j = 0; j < TAPS; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
-              o[i][k] = a;
-            }
-        } else {
-#pragma unroll
-          for (int i = 0; i < P2_ROWS; ++i) {
-            const uint2 u = *reinterpret_cast<const uint2*>(colp + (ro + i) * pitch);
-            unpack_bf16x2(u.x, o[i][0], o[i][1]);
-            unpack_bf16x2(u.y, o[i][2], o[i][3]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[i][k] += bs[k];
-          }
-        }
-        if constexpr (RES) {
-#pragma unroll
-          for (int i = 0; i < P2_ROWS; ++i) {
-            float ra[4];
-            unpack_bf16x2(rres[i].x, ra[0], ra[1]);
-            unpack_bf16x2(rres[i].y, ra[2], ra[3]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[i][k] += ra[k];
-          }
-        }
-        if constexpr (RAW) {
-          char* op = reinterpret_cast<char*>(g.out_raw + off);
-#pragma unroll
-          for (int i = 0; i < P2_ROWS; ++i)
-            if (full || ro + i < rows_left)
-              *reinterpret_cast<uint2*>(op + i * row_bytes) =
-                  make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
-        }
-        if constexpr (ACT) {
-          char* op = reinterpret_cast<char*>(g.out_act + off);
-#pragma unroll
-          for (int i = 0; i < P2_ROWS; ++i) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[i][k] = elu_fast(o[i][k] * s_act);
-            if (full || ro + i < rows_left)
-              *reinterpret_cast<uint2*>(op + i * row_bytes) =
-                  make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
-          }
-        }
+        const uint32_t srow = tile_u32 + ro * pitch;
+        if (ro + P2_ROWS <= rows_left)
+          staged_unit<TAPS, RES, RAW, ACT, true>(g, srow, pitch, off, row_bytes, P2_ROWS, wt, bs, s_act);
+        else
+          staged_unit<TAPS, RES, RAW, ACT, false>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act);
       }
     }
     __syncwarp();
@@ -401,6 +423,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // ---------------------------------------------------------- drain warps: TMEM -> bf16 -> smem
       static_assert(REGS_DRAIN == 96, "drain warps keep their launch allocation (65536 / 640 -> 96)");
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
+      const uint32_t stage_u32 = smem_u32(stage_tiles);
       int as = 0, sb = 0;
       uint32_t as_phase = 0, sb_phase = 0;
       uint32_t v[32];
@@ -410,17 +433,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
-        uint8_t* rowp = stage_tiles + sb * (BM * pitch) + (q * 32 + lane) * pitch;
+        const uint32_t rowp = stage_u32 + sb * (BM * pitch) + (q * 32 + lane) * pitch;
         for (int c = 0; c < chunks; ++c) {
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
-          uint4* sp = reinterpret_cast<uint4*>(rowp + c * 64);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            sp[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                               pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                               pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                               pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+            sts_u4(rowp + c * 64 + i * 16,
+                   pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                   pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                   pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                   pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
         }
         tc_fence_before();
         __syncwarp();
