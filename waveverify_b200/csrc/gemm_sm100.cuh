@@ -51,11 +51,13 @@ constexpr int STAGE_BUFS = 2;               // staging tiles (drain of tile i+1 
 constexpr int STAGED_MAX_BN = 128;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 256;
+constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 4;   // staged down-conv taps [2r <= 16][block_n] fp32
 
 enum { EPI_STAGED = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3 };
 
 struct GemmArgs {
   int rows_per_clip;  // rows of A per clip (flat: total M)
+  int rows_per_clip_out;   // output rows per clip (== rows_per_clip unless the epilogue downsamples)
   int n_clips;
   int N, K;
   int block_n;
@@ -64,7 +66,12 @@ struct GemmArgs {
   // tile -> (m tile, n tile, clip) without integer division (host computed)
   int tiles_n, tiles_m_per_clip, num_tiles;
   uint32_t magic_n, magic_m;   // floor(2^32 / d)
+  int tile_stride;    // A rows between consecutive M tiles (128, 124 with the dw5 halo, outs*r for down)
+  int tile_halo;      // rows loaded before the first row a tile produces output for
   // STAGED
+  int down_r;         // > 0: fused strided depthwise down-conv k=2r, s=r (+ FiLM); taps unused
+  const float* film;  // [clips, film_stride] (gamma, beta) pairs per band, nullable
+  int film_stride, film_bands;
   int taps;           // 1, or 5 = fused causal depthwise conv over time
   const float* dw_w;  // [taps][N] fp32 (taps == 5)
   const float* bias;  // [N] (added after the depthwise taps), nullable
@@ -91,12 +98,12 @@ struct GemmArgs {
 
 __host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n * 2 + 16; }
 __host__ inline int gemm_stage_count(int block_n, bool staged) {
-  const int fixed = 1024 + GEMM_BAR_BYTES + (staged ? STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0);
+  const int fixed = 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0);
   int s = (GEMM_SMEM_LIMIT - fixed) / (A_STAGE_BYTES + block_n * BK * 2);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 __host__ inline int gemm_smem_bytes(int block_n, bool staged) {
-  return 1024 + GEMM_BAR_BYTES + (staged ? STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0) +
+  return 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0) +
          gemm_stage_count(block_n, staged) * (A_STAGE_BYTES + block_n * BK * 2);
 }
 
@@ -144,6 +151,31 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
   return t;
 }
 
+// Walks tile = blockIdx.x, blockIdx.x + gridDim.x, ... keeping (clip, mi, nt) up to date with adds
+// and compares only (the per-step deltas are decomposed once).
+struct TileWalker {
+  int tile, clip, mi, nt;
+  int d_nt, d_mi, d_clip;      // gridDim.x decomposed in the (clip, mi, nt) mixed radix
+  int tiles_n, tiles_m;
+  __device__ __forceinline__ TileWalker(const GemmArgs& g) {
+    tiles_n = g.tiles_n; tiles_m = g.tiles_m_per_clip;
+    tile = blockIdx.x;
+    const TileCoord t0 = tile_coord(g, tile);
+    clip = t0.clip; mi = t0.mi; nt = t0.nt;
+    const int step = gridDim.x;
+    int dm = step / tiles_n;
+    d_nt = step - dm * tiles_n;
+    if (g.n_clips == 1) { d_clip = 0; d_mi = dm; tiles_m = 0x7fffffff; }
+    else { d_clip = dm / tiles_m; d_mi = dm - d_clip * tiles_m; }
+  }
+  __device__ __forceinline__ void next() {
+    tile += gridDim.x;
+    nt += d_nt; mi += d_mi; clip += d_clip;
+    if (nt >= tiles_n) { nt -= tiles_n; ++mi; }
+    if (mi >= tiles_m) { mi -= tiles_m; ++clip; }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // explicit shared-state accesses (32-bit addresses; generic pointers cost 64-bit address math)
 __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
@@ -156,7 +188,7 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // One math unit: P2_ROWS output rows x 4 channels.  FULL = all rows valid (no predicates).
-template <int TAPS, bool RES, bool RAW, bool ACT, bool FULL>
+template <int TAPS, bool RES, bool RAW, bool ACT, bool FULL, bool SCALE>
 __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*smem addr of tile row ro*/,
                                             int pitch, size_t off, size_t row_bytes, int nrow,
                                             const float (&wt)[TAPS][4], const float (&bs)[4], float s_act) {
@@ -219,7 +251,7 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
 #pragma unroll
     for (int i = 0; i < P2_ROWS; ++i) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[i][k] = elu_fast(o[i][k] * s_act);
+      for (int k = 0; k < 4; ++k) o[i][k] = elu_fast(SCALE ? o[i][k] * s_act : o[i][k]);
       if (FULL || i < nrow)
         *reinterpret_cast<uint2*>(op + i * row_bytes) =
             make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
@@ -229,7 +261,7 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
 
 // STAGED math warps.  thread = (4-channel group, 4-row group): 8-byte smem reads / global accesses
 // keep a warp on contiguous 256-byte row segments while the per-thread state stays under 112 regs.
-template <int TAPS, bool RES, bool RAW, bool ACT>
+template <int TAPS, bool RES, bool RAW, bool ACT, bool SCALE>
 __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles,
                                                  uint64_t* st_full, uint64_t* st_empty, int lane) {
   constexpr int HALO = TAPS - 1;
@@ -249,8 +281,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   int sb = 0;
   uint32_t sb_phase = 0;
   int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
-  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-    const TileCoord tc = tile_coord(g, tile);
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
     const int c = tc.nt * g.block_n + cg * 4;
     if (active && tc.nt != cached_nt) {                            // per-CTA constant when N fits one tile
@@ -282,9 +313,9 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
         const size_t off = base + static_cast<size_t>(ro) * g.ldo;
         const uint32_t srow = tile_u32 + ro * pitch;
         if (ro + P2_ROWS <= rows_left)
-          staged_unit<TAPS, RES, RAW, ACT, true>(g, srow, pitch, off, row_bytes, P2_ROWS, wt, bs, s_act);
+          staged_unit<TAPS, RES, RAW, ACT, true, SCALE>(g, srow, pitch, off, row_bytes, P2_ROWS, wt, bs, s_act);
         else
-          staged_unit<TAPS, RES, RAW, ACT, false>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act);
+          staged_unit<TAPS, RES, RAW, ACT, false, SCALE>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act);
       }
     }
     __syncwarp();
@@ -295,19 +326,111 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// STAGED math warps, strided variant: the causal depthwise down-conv k=2R, s=R that follows the
+// encoder's channel-doubling 1x1 (modules/seanet.py:745-771) + FiLM (seanet.py:928-966):
+//   v[i,c] = bias[c] + sum_{j<2R} w[j][c] * S[i*R - R + j][c];  v = v*gamma + beta
+// A tile holds input rows [mi*OUTS*R - R, +128) and produces OUTS = 128/R - 1 output rows.
+// thread = (4-channel group, output row); taps are staged in shared memory (2R*4 floats per thread
+// would not fit in registers for R = 8).
+template <int R>
+__device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_t* stage_tiles, uint8_t* down_w,
+                                                 uint64_t* st_full, uint64_t* st_empty, int lane) {
+  constexpr int OUTS = BM / R - 1;
+  const int pitch = staged_pitch_bytes(g.block_n);
+  const int et = threadIdx.x - (128 + P1_WARPS * 32);
+  const int cgs = g.block_n >> 2;
+  const int gstride = P2_THREADS / cgs;                          // output rows per pass
+  const int cg = et % cgs, row0 = et / cgs;
+  const bool active = row0 < gstride;
+  const bool raw = g.out_raw != nullptr, act = g.out_act != nullptr;
+  const float s_act = g.act_scale;
+  const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
+  const uint32_t w_u32 = smem_u32(down_w) + cg * 16;
+  const int band_w = g.film != nullptr ? g.N / g.film_bands : 1;
+  int cached_nt = -1;
+  float bs[4];
+  int sb = 0;
+  uint32_t sb_phase = 0;
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
+    const int c = tc.nt * g.block_n + cg * 4;
+    if (tc.nt != cached_nt) {                                      // (re)stage taps for this N tile
+      cached_nt = tc.nt;
+      asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory");   // previous taps no longer read
+      for (int i = et; i < 2 * R * cgs; i += P2_THREADS) {
+        const int j = i / cgs, q = i % cgs;
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + tc.nt * g.block_n + q * 4));
+        *reinterpret_cast<float4*>(down_w + (j * g.block_n + q * 4) * 4) = w4;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory");
+      if (g.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+        bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+      } else {
+        bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
+      }
+    }
+    float gm = 1.f, bt = 0.f;
+    if (g.film != nullptr) {
+      const float* fp = g.film + static_cast<size_t>(tc.clip) * g.film_stride + (c / band_w) * 2;
+      gm = __ldg(fp);
+      bt = __ldg(fp + 1);
+    }
+    mbar_wait(&st_full[sb], sb_phase);
+    if (active) {
+      const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
+      const int i_base = tc.mi * OUTS;                              // first output row of the tile
+      const int outs_left = g.rows_per_clip_out - i_base;
+      const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip_out + i_base) * g.ldo + c;
+      for (int lo = row0; lo < OUTS && lo < outs_left; lo += gstride) {
+        float o[4] = {bs[0], bs[1], bs[2], bs[3]};
+        const uint32_t srow = tile_u32 + lo * R * pitch;
+#pragma unroll
+        for (int j = 0; j < 2 * R; ++j) {
+          const uint2 u = lds_u2(srow + j * pitch);
+          float4 w4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w) : "r"(w_u32 + j * g.block_n * 4));
+          float x0, x1, x2, x3;
+          unpack_bf16x2(u.x, x0, x1);
+          unpack_bf16x2(u.y, x2, x3);
+          o[0] = fmaf(w4.x, x0, o[0]); o[1] = fmaf(w4.y, x1, o[1]);
+          o[2] = fmaf(w4.z, x2, o[2]); o[3] = fmaf(w4.w, x3, o[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = fmaf(o[k], gm, bt);
+        const size_t off = base + static_cast<size_t>(lo) * g.ldo;
+        if (raw)
+          *reinterpret_cast<uint2*>(g.out_raw + off) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+        if (act) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[k] = elu_fast(o[k] * s_act);
+          *reinterpret_cast<uint2*>(g.out_act + off) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&st_empty[sb]);
+    if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+  }
+}
+
 template <int TAPS>
 __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const uint8_t* stage_tiles,
                                                      uint64_t* st_full, uint64_t* st_empty, int lane) {
   const bool res = g.residual != nullptr, raw = g.out_raw != nullptr, act = g.out_act != nullptr;
+  const bool scale = act && g.act_scale != 1.f;
+#define WV_MATH(R, W, A, S) staged_math_loop<TAPS, R, W, A, S>(g, stage_tiles, st_full, st_empty, lane)
   if (res) {
-    if (raw && act) staged_math_loop<TAPS, true, true, true>(g, stage_tiles, st_full, st_empty, lane);
-    else if (raw) staged_math_loop<TAPS, true, true, false>(g, stage_tiles, st_full, st_empty, lane);
-    else staged_math_loop<TAPS, true, false, true>(g, stage_tiles, st_full, st_empty, lane);
+    if (raw && act) { if (scale) WV_MATH(true, true, true, true); else WV_MATH(true, true, true, false); }
+    else if (raw) WV_MATH(true, true, false, false);
+    else { if (scale) WV_MATH(true, false, true, true); else WV_MATH(true, false, true, false); }
   } else {
-    if (raw && act) staged_math_loop<TAPS, false, true, true>(g, stage_tiles, st_full, st_empty, lane);
-    else if (raw) staged_math_loop<TAPS, false, true, false>(g, stage_tiles, st_full, st_empty, lane);
-    else staged_math_loop<TAPS, false, false, true>(g, stage_tiles, st_full, st_empty, lane);
+    if (raw && act) { if (scale) WV_MATH(false, true, true, true); else WV_MATH(false, true, true, false); }
+    else if (raw) WV_MATH(false, true, false, false);
+    else { if (scale) WV_MATH(false, false, true, true); else WV_MATH(false, false, true, false); }
   }
+#undef WV_MATH
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,14 +453,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* st_full = acc_empty + ACC_STAGES;     // [STAGE_BUFS] staging tile written
   uint64_t* st_empty = st_full + STAGE_BUFS;      // [STAGE_BUFS] staging tile consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_empty + STAGE_BUFS);
-  uint8_t* stage_tiles = after + GEMM_BAR_BYTES;  // [STAGE_BUFS][BM][pitch] bf16 (STAGED only)
+  uint8_t* down_w = after + GEMM_BAR_BYTES;       // [2r][block_n] fp32 (STAGED down-conv only)
+  uint8_t* stage_tiles = down_w + DOWN_W_BYTES;   // [STAGE_BUFS][BM][pitch] bf16 (STAGED only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile geometry: STAGED with taps>1 walks each clip in overlapping tiles (halo = taps-1 rows)
-  const int halo = (EPI == EPI_STAGED) ? g.taps - 1 : 0;
-  const int rows_out = BM - halo;
+  // tile geometry (host computed): overlapping per-clip tiles carry the depthwise halo
+  const int halo = g.tile_halo;
+  const int rows_out = g.tile_stride;
   const int num_kb = (g.K + BK - 1) / BK;
   const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
 
@@ -372,8 +496,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(g, tile);
+      for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -457,7 +580,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global
       reg_alloc<REGS_MATH>();
-      if (g.taps == 5) staged_math_dispatch<5>(g, stage_tiles, st_full, st_empty, lane);
+      if (g.down_r > 0) {
+        switch (g.down_r) {
+          case 2: staged_down_loop<2>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
+          case 4: staged_down_loop<4>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
+          case 5: staged_down_loop<5>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
+          default: staged_down_loop<8>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
+        }
+      } else if (g.taps == 5) staged_math_dispatch<5>(g, stage_tiles, st_full, st_empty, lane);
       else staged_math_dispatch<1>(g, stage_tiles, st_full, st_empty, lane);
     }
   } else if (warp >= 4) {

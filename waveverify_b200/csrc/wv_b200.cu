@@ -496,9 +496,19 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   op.g = g;
   op.out0 = g.out_raw;
   op.out1 = g.out_act;
-  const int rows_out = BM - (staged ? g.taps - 1 : 0);
+  int rows_out = BM - (staged ? g.taps - 1 : 0);
+  g.tile_halo = staged ? g.taps - 1 : 0;
+  g.rows_per_clip_out = g.rows_per_clip;
+  if (staged && g.down_r > 0) {
+    const int outs = BM / g.down_r - 1;
+    rows_out = outs * g.down_r;
+    g.tile_halo = g.down_r;
+    g.rows_per_clip_out = ceil_div(g.rows_per_clip, g.down_r);
+  }
+  g.tile_stride = rows_out;
   g.tiles_n = w.N / w.block_n;
-  g.tiles_m_per_clip = ceil_div(g.rows_per_clip, rows_out);
+  g.tiles_m_per_clip = (staged && g.down_r > 0) ? ceil_div(g.rows_per_clip_out, BM / g.down_r - 1)
+                                                 : ceil_div(g.rows_per_clip, rows_out);
   g.magic_n = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(g.tiles_n));
   g.magic_m = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(g.tiles_m_per_clip));
   if (g.tiles_n == 1) g.magic_n = 0;            // 2^32 / 1 does not fit; the kernel special-cases 1
@@ -519,8 +529,9 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     // the strided STFT frame view re-reads each sample n_fft/hop times from L2; algorithmic = once
     const double a_bytes = custom_tmA ? Mt * 2.0 * std::min<double>(K, 64) : Mt * K * 2.0;
     op.bytes = a_bytes + outs + (g.residual ? Mt * w.N * 2.0 : 0.0) + static_cast<double>(w.N) * K * 2.0;
-    op.out_bytes[0] = g.out_raw ? static_cast<size_t>(Mt) * g.ldo * 2 : 0;
-    op.out_bytes[1] = g.out_act ? static_cast<size_t>(Mt) * g.ldo * 2 : 0;
+    const double Mo = static_cast<double>(g.rows_per_clip_out) * g.n_clips;
+    op.out_bytes[0] = g.out_raw ? static_cast<size_t>(Mo) * g.ldo * 2 : 0;
+    op.out_bytes[1] = g.out_act ? static_cast<size_t>(Mo) * g.ldo * 2 : 0;
   }
   c.push(op);
 }
@@ -566,6 +577,25 @@ void add_gemm_dw(PlanCtx& c, const GemmW& pw, const DwW& dw, const bf16* A, int 
   const double n = static_cast<double>(c.B) * T;
   op.flops += 10.0 * n * pw.N;
   op.bytes = n * 2.0 * (K + pw.N * ((res ? 1 : 0) + (out_raw ? 1 : 0) + (out_act ? 1 : 0))) + static_cast<double>(pw.N) * K * 2.0;
+}
+
+// Encoder downsample (modules/seanet.py:745-771): 1x1 conv C -> 2C (tcgen05 GEMM) with the strided
+// depthwise conv k=2r, s=r, its bias and the FiLM affine fused into the epilogue.  A = [B, T, K].
+void add_gemm_down(PlanCtx& c, const GemmW& pw, const DwW& dw, int r, const bf16* A, int T, int K, const float* film,
+                   int film_stride, int bands, bf16* out_raw, bf16* out_act, float act_scale) {
+  if (dw.k != 2 * r || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused down-conv must be k=2r over the GEMM's N");
+  if (r != 2 && r != 4 && r != 5 && r != 8) WV_THROW(WV_ERR_UNSUPPORTED, "fused down-conv stride %d (2, 4, 5, 8)", r);
+  GemmArgs g = std_args(dw.bias, nullptr, out_raw, out_act, act_scale, pw.N);
+  g.down_r = r;
+  g.dw_w = dw.w;
+  g.film = film; g.film_stride = film_stride; g.film_bands = bands;
+  CUtensorMap tm;
+  if (!c.dry()) tm = make_tmap(A, 3, K, T, c.B, K, static_cast<uint64_t>(K) * T, BK, BM, false);
+  add_gemm(c, EPI_STAGED, pw, nullptr, 0, 0, K, g, &tm, T, c.B);
+  Op& op = c.ops->back();
+  const double n_in = static_cast<double>(c.B) * T, n_out = static_cast<double>(c.B) * ceil_div(T, r);
+  op.flops += 2.0 * 2 * r * n_out * pw.N;
+  op.bytes = n_in * K * 2.0 + n_out * pw.N * 2.0 * ((out_raw ? 1 : 0) + (out_act ? 1 : 0)) + static_cast<double>(pw.N) * K * 2.0;
 }
 
 // One residual block (modules/seanet.py:245-281).  X raw (residual), A = ELU(X*pre_scale).
@@ -869,32 +899,17 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
       X = Xn; A = An;
     }
     plan_spec(c, st.spec, wav16, pitch, lead, Ts, X, C, down_scale, A, "enc.s" + std::to_string(s) + ".spec");   // A = ELU((x+spec)*scale)
-    const long long M = static_cast<long long>(B) * Ts;
-    Buf G = c.alloc(static_cast<size_t>(M) * 2 * C * 2);
-    c.tag("enc.s" + std::to_string(s) + ".down_pw");
-    add_gemm(c, EPI_STAGED, st.down_pw, c.ptr<bf16>(A), C, M, C, std_args(nullptr, nullptr, c.ptr<bf16>(G), nullptr, 1.f, 2 * C));
-    c.release(A);
     const int To = ceil_div(Ts, st.r);
     const bool last_stage = s == S - 1;
+    Buf Ain = A;
     X = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2);
-    if (!last_stage) A = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2);
-    {
-      Op op;
-      op.type = OP_DOWN;
-      op.in = c.ptr<bf16>(G); op.out0 = c.ptr<bf16>(X); op.out1 = last_stage ? nullptr : c.ptr<bf16>(A);
-      op.w = st.down_dw.w; op.bias = st.down_dw.bias;
-      op.film = e.has_film ? c.ptr<float>(film) + static_cast<size_t>(s) * e.bands * 2 : nullptr;
-      op.fa = last_stage ? 1.f : e.stages[s + 1].res[0].pre_scale;
-      op.i[0] = B; op.i[1] = Ts; op.i[2] = To; op.i[3] = 2 * C; op.i[4] = st.r; op.i[5] = e.n_film * 2; op.i[6] = e.bands;
-      op.grid = elem_grid(static_cast<long long>(B) * To * (2 * C / 8));
-      op.flops = 2.0 * 2 * st.r * B * To * 2.0 * C;
-      op.bytes = 2.0 * (static_cast<double>(M) * 2 * C + static_cast<double>(B) * To * 2 * C * (last_stage ? 1 : 2));
-      op.out_bytes[0] = static_cast<size_t>(B) * To * 2 * C * 2;
-      op.out_bytes[1] = last_stage ? 0 : op.out_bytes[0];
-      c.tag("enc.s" + std::to_string(s) + ".down");
-      c.push(op);
-    }
-    c.release(G);
+    if (!last_stage) A = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2); else A = Buf();
+    c.tag("enc.s" + std::to_string(s) + ".down");
+    add_gemm_down(c, st.down_pw, st.down_dw, st.r, c.ptr<bf16>(Ain), Ts, C,
+                  e.has_film ? c.ptr<float>(film) + static_cast<size_t>(s) * e.bands * 2 : nullptr, e.n_film * 2, e.bands,
+                  c.ptr<bf16>(X), last_stage ? nullptr : c.ptr<bf16>(A),
+                  last_stage ? 1.f : e.stages[s + 1].res[0].pre_scale);
+    c.release(Ain);
     Ts = To; C *= 2;
   }
   plan.F = Ts;
