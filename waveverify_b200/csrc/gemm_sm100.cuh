@@ -11,9 +11,12 @@
 // overlapping STFT frame view of the padded waveform.
 //
 // Epilogues (template EPI):
-//   STAGED  warps 4-7 ("drain") round the fp32 accumulator tile to bf16 into one of two padded
-//           shared-memory tiles and release the TMEM stage; warps 8-19 ("math", 112 registers via
-//           setmaxnreg) walk the staged tile in a coalesced (4 rows x 4 channels) layout:
+//   STAGED  warps 4-7 ("drain") round the fp32 accumulator tile to fp16 (11-bit mantissa,
+//           saturating) into one of two padded shared-memory tiles and release the TMEM stage;
+//           warps 8-19 ("math", 112 registers via setmaxnreg) walk the staged tile in a coalesced
+//           (4 rows x 4 channels) layout.  The depthwise taps run as packed HFMA2 on the staged
+//           half2 pairs (two channels per instruction, no unpacking), everything after the taps
+//           (residual, ELU) in fp32:
 //             v = bias[c] + sum_{j<taps} w[j][c] * S[r-taps+1+j][c]      taps = 1 or 5
 //             v += residual[m,c];  out_raw = bf16(v);  out_act = bf16(ELU(v*s))
 //           taps = 5 fuses the causal depthwise conv that follows every resblock 1x1
@@ -51,7 +54,7 @@ constexpr int STAGE_BUFS = 2;               // staging tiles (drain of tile i+1 
 constexpr int STAGED_MAX_BN = 128;
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 256;
-constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 4;   // staged down-conv taps [2r <= 16][block_n] fp32
+constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [2r <= 16][block_n] fp16
 
 enum { EPI_STAGED = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3 };
 
@@ -187,46 +190,61 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ __half2 h2_from(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+
+// Residual rows of one unit (L2-coherent loads; issued one unit ahead of their use, see below).
+__device__ __forceinline__ void load_residual(const GemmArgs& g, size_t off, size_t row_bytes, int nrow,
+                                              uint2 (&r)[P2_ROWS]) {
+  const char* rp = reinterpret_cast<const char*>(g.residual + off);
+#pragma unroll
+  for (int i = 0; i < P2_ROWS; ++i)
+    r[i] = i < nrow ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
+}
+
 // One math unit: P2_ROWS output rows x 4 channels.  FULL = all rows valid (no predicates).
 template <int TAPS, bool RES, bool RAW, bool ACT, bool FULL, bool SCALE>
 __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*smem addr of tile row ro*/,
                                             int pitch, size_t off, size_t row_bytes, int nrow,
-                                            const float (&wt)[TAPS][4], const float (&bs)[4], float s_act) {
+                                            const __half2 (&wt)[TAPS][2], const __half2 (&bs)[2], float s_act,
+                                            const uint2 (&rres)[P2_ROWS]) {
   constexpr int HALO = TAPS - 1;
-  uint2 rres[P2_ROWS];
-  if constexpr (RES) {
-    const char* rp = reinterpret_cast<const char*>(g.residual + off);
-#pragma unroll
-    for (int i = 0; i < P2_ROWS; ++i)
-      rres[i] = (FULL || i < nrow) ? __ldg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
-  }
-  float o[P2_ROWS][4];
+  __half2 oh[P2_ROWS][2];
   if constexpr (TAPS > 1) {
-    float x[P2_ROWS + HALO][4];                              // tile rows ro .. ro+P2_ROWS+HALO-1
+    __half2 x[P2_ROWS + HALO][2];                            // tile rows ro .. ro+P2_ROWS+HALO-1
 #pragma unroll
     for (int j = 0; j < P2_ROWS + HALO; ++j) {
       const uint2 u = lds_u2(srow + j * pitch);
-      unpack_bf16x2(u.x, x[j][0], x[j][1]);
-      unpack_bf16x2(u.y, x[j][2], x[j][3]);
+      x[j][0] = as_h2(u.x);
+      x[j][1] = as_h2(u.y);
     }
 #pragma unroll
     for (int i = 0; i < P2_ROWS; ++i)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float a = bs[k];
+      for (int p = 0; p < 2; ++p) {
+        __half2 a = bs[p];
 #pragma unroll
-        for (int j = 0; j < TAPS; ++j) a = fmaf(wt[j][k], x[i + j][k], a);
-        o[i][k] = a;
+        for (int j = 0; j < TAPS; ++j) a = __hfma2(wt[j][p], x[i + j][p], a);
+        oh[i][p] = a;
       }
   } else {
 #pragma unroll
     for (int i = 0; i < P2_ROWS; ++i) {
       const uint2 u = lds_u2(srow + i * pitch);
-      unpack_bf16x2(u.x, o[i][0], o[i][1]);
-      unpack_bf16x2(u.y, o[i][2], o[i][3]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[i][k] += bs[k];
+      oh[i][0] = __hadd2(as_h2(u.x), bs[0]);
+      oh[i][1] = __hadd2(as_h2(u.y), bs[1]);
     }
+  }
+  float o[P2_ROWS][4];
+#pragma unroll
+  for (int i = 0; i < P2_ROWS; ++i) {
+    const float2 f0 = __half22float2(oh[i][0]), f1 = __half22float2(oh[i][1]);
+    o[i][0] = f0.x; o[i][1] = f0.y; o[i][2] = f1.x; o[i][3] = f1.y;
   }
   if constexpr (RES) {
 #pragma unroll
@@ -277,7 +295,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   const float s_act = g.act_scale;
   const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
   int cached_nt = -1;
-  float wt[TAPS][4], bs[4];
+  __half2 wt[TAPS][2], bs[2];
   int sb = 0;
   uint32_t sb_phase = 0;
   int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
@@ -288,35 +306,51 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       cached_nt = tc.nt;
       if (g.bias != nullptr) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-        bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+        bs[0] = h2_from(b0.x, b0.y); bs[1] = h2_from(b0.z, b0.w);
       } else {
-        bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
+        bs[0] = bs[1] = h2_from(0.f, 0.f);
       }
       if constexpr (TAPS > 1) {
 #pragma unroll
         for (int j = 0; j < TAPS; ++j) {
           const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
-          wt[j][0] = w0.x; wt[j][1] = w0.y; wt[j][2] = w0.z; wt[j][3] = w0.w;
+          wt[j][0] = h2_from(w0.x, w0.y); wt[j][1] = h2_from(w0.z, w0.w);
         }
       }
     }
+    // The residual rows of a unit do not depend on the staged tile: the first unit's are requested
+    // before waiting for the drain warps, the next unit's before the current unit's math, so their
+    // HBM latency overlaps the wait / the math instead of stalling every unit.
+    const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base) * g.ldo + c;
+    const int rows_left = g.rows_per_clip - r_base;               // valid output rows from r_base on
+    int grp = grp0 + rot;
+    if (grp >= gstride) grp -= gstride;
+    uint2 rres[P2_ROWS], rnext[P2_ROWS];
+    bool have = active && grp < N_GROUPS && grp * P2_ROWS < rows_left;
+    if constexpr (RES) {
+      if (have) load_residual(g, base + static_cast<size_t>(grp * P2_ROWS) * g.ldo, row_bytes, rows_left - grp * P2_ROWS, rres);
+    }
     mbar_wait(&st_full[sb], sb_phase);
-    if (active) {
-      const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
-      const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base) * g.ldo + c;
-      const int rows_left = g.rows_per_clip - r_base;             // valid output rows from r_base on
-      int grp = grp0 + rot;
-      if (grp >= gstride) grp -= gstride;
-      for (; grp < N_GROUPS; grp += gstride) {
-        const int ro = grp * P2_ROWS;                              // tile-relative output row
-        if (ro >= rows_left) break;
-        const size_t off = base + static_cast<size_t>(ro) * g.ldo;
-        const uint32_t srow = tile_u32 + ro * pitch;
-        if (ro + P2_ROWS <= rows_left)
-          staged_unit<TAPS, RES, RAW, ACT, true, SCALE>(g, srow, pitch, off, row_bytes, P2_ROWS, wt, bs, s_act);
-        else
-          staged_unit<TAPS, RES, RAW, ACT, false, SCALE>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act);
+    const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
+    while (have) {
+      const int ro = grp * P2_ROWS;                                // tile-relative output row
+      const int gn = grp + gstride;
+      const bool have_next = gn < N_GROUPS && gn * P2_ROWS < rows_left;
+      if constexpr (RES) {
+        if (have_next) load_residual(g, base + static_cast<size_t>(gn * P2_ROWS) * g.ldo, row_bytes, rows_left - gn * P2_ROWS, rnext);
       }
+      const size_t off = base + static_cast<size_t>(ro) * g.ldo;
+      const uint32_t srow = tile_u32 + ro * pitch;
+      if (ro + P2_ROWS <= rows_left)
+        staged_unit<TAPS, RES, RAW, ACT, true, SCALE>(g, srow, pitch, off, row_bytes, P2_ROWS, wt, bs, s_act, rres);
+      else
+        staged_unit<TAPS, RES, RAW, ACT, false, SCALE>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act, rres);
+      if constexpr (RES) {
+#pragma unroll
+        for (int i = 0; i < P2_ROWS; ++i) rres[i] = rnext[i];
+      }
+      grp = gn;
+      have = have_next;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&st_empty[sb]);   // this warp no longer reads staging tile sb
@@ -346,7 +380,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   const bool raw = g.out_raw != nullptr, act = g.out_act != nullptr;
   const float s_act = g.act_scale;
   const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
-  const uint32_t w_u32 = smem_u32(down_w) + cg * 16;
+  const uint32_t w_u32 = smem_u32(down_w) + cg * 8;              // taps staged as fp16 [2R][block_n]
   const int band_w = g.film != nullptr ? g.N / g.film_bands : 1;
   int cached_nt = -1;
   float bs[4];
@@ -360,7 +394,9 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       for (int i = et; i < 2 * R * cgs; i += P2_THREADS) {
         const int j = i / cgs, q = i % cgs;
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + tc.nt * g.block_n + q * 4));
-        *reinterpret_cast<float4*>(down_w + (j * g.block_n + q * 4) * 4) = w4;
+        const __half2 h0 = h2_from(w4.x, w4.y), h1 = h2_from(w4.z, w4.w);
+        *reinterpret_cast<uint2*>(down_w + (j * g.block_n + q * 4) * 2) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory");
       if (g.bias != nullptr) {
@@ -373,8 +409,8 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
     float gm = 1.f, bt = 0.f;
     if (g.film != nullptr) {
       const float* fp = g.film + static_cast<size_t>(tc.clip) * g.film_stride + (c / band_w) * 2;
-      gm = __ldg(fp);
-      bt = __ldg(fp + 1);
+      gm = __ldcg(fp);
+      bt = __ldcg(fp + 1);
     }
     mbar_wait(&st_full[sb], sb_phase);
     if (active) {
@@ -383,19 +419,29 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       const int outs_left = g.rows_per_clip_out - i_base;
       const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip_out + i_base) * g.ldo + c;
       for (int lo = row0; lo < OUTS && lo < outs_left; lo += gstride) {
-        float o[4] = {bs[0], bs[1], bs[2], bs[3]};
+        // two independent HFMA2 chains per channel pair (even / odd taps) keep the fp16 partial
+        // sums short; they are joined in fp32
+        __half2 a0[2] = {h2_from(0.f, 0.f), h2_from(0.f, 0.f)};
+        __half2 a1[2] = {h2_from(0.f, 0.f), h2_from(0.f, 0.f)};
         const uint32_t srow = tile_u32 + lo * R * pitch;
 #pragma unroll
         for (int j = 0; j < 2 * R; ++j) {
           const uint2 u = lds_u2(srow + j * pitch);
-          float4 w4;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w) : "r"(w_u32 + j * g.block_n * 4));
-          float x0, x1, x2, x3;
-          unpack_bf16x2(u.x, x0, x1);
-          unpack_bf16x2(u.y, x2, x3);
-          o[0] = fmaf(w4.x, x0, o[0]); o[1] = fmaf(w4.y, x1, o[1]);
-          o[2] = fmaf(w4.z, x2, o[2]); o[3] = fmaf(w4.w, x3, o[3]);
+          const uint2 w = lds_u2(w_u32 + j * g.block_n * 2);
+          if (j & 1) {
+            a1[0] = __hfma2(as_h2(w.x), as_h2(u.x), a1[0]);
+            a1[1] = __hfma2(as_h2(w.y), as_h2(u.y), a1[1]);
+          } else {
+            a0[0] = __hfma2(as_h2(w.x), as_h2(u.x), a0[0]);
+            a0[1] = __hfma2(as_h2(w.y), as_h2(u.y), a0[1]);
+          }
+        }
+        float o[4];
+        {
+          const float2 p0 = __half22float2(a0[0]), p1 = __half22float2(a0[1]);
+          const float2 q0 = __half22float2(a1[0]), q1 = __half22float2(a1[1]);
+          o[0] = bs[0] + p0.x + q0.x; o[1] = bs[1] + p0.y + q0.y;
+          o[2] = bs[2] + p1.x + q1.x; o[3] = bs[3] + p1.y + q1.y;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = fmaf(o[k], gm, bt);
@@ -489,6 +535,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlaps the previous kernel's tail (programmatic dependent launch)
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -543,7 +592,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pitch = staged_pitch_bytes(g.block_n);
     const int chunks = g.block_n / 32;
     if (warp < 4 + P1_WARPS) {
-      // ---------------------------------------------------------- drain warps: TMEM -> bf16 -> smem
+      // ---------------------------------------------------------- drain warps: TMEM -> fp16 -> smem
       static_assert(REGS_DRAIN == 96, "drain warps keep their launch allocation (65536 / 640 -> 96)");
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
       const uint32_t stage_u32 = smem_u32(stage_tiles);
@@ -563,10 +612,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             sts_u4(rowp + c * 64 + i * 16,
-                   pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                   pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                   pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                   pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+                   pack_f16x2_sat(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                   pack_f16x2_sat(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                   pack_f16x2_sat(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                   pack_f16x2_sat(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
         }
         tc_fence_before();
         __syncwarp();
@@ -703,7 +752,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   if (lp) lp[i] = l;
                   if (g.mask_out) g.mask_out[base + i] = l > 0.5f ? 1 : 0;
                   if (g.probs) g.probs[base + i] = p;
-                  if (g.partial) psum += g.presence ? (g.presence[base + i] ? p : 0.f) : p;
+                  if (g.partial) psum += g.presence ? (__ldcg(g.presence + base + i) ? p : 0.f) : p;
                 }
               }
             }

@@ -10,8 +10,8 @@ struct F8 {
   float v[8];
 };
 // (elu1 comes from ptx_sm100.cuh)
-__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {   // activations: L2-coherent load
+  const uint4 u = __ldcg(reinterpret_cast<const uint4*>(p));
   F8 r;
   unpack_bf16x2(u.x, r.v[0], r.v[1]);
   unpack_bf16x2(u.y, r.v[2], r.v[3]);
@@ -45,6 +45,8 @@ dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
            __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
            float act_scale, int B, int T, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C8 = C >> 3;
   const int runs = (T + DW_TT - 1) / DW_TT;
   const long long total = static_cast<long long>(B) * runs * C8;
@@ -114,6 +116,8 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
             const float* __restrict__ bias, const float* __restrict__ film, int film_stride,
             int bands, __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
             float act_scale, int B, int Tin, int Tout, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C8 = C >> 3;
   const long long total = static_cast<long long>(B) * Tout * C8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -129,7 +133,7 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 #pragma unroll
     for (int j = 0; j < 2 * R; ++j) {
       const int t = tb + j;
-      xv[j] = (t >= 0 && t < Tin) ? __ldg(reinterpret_cast<const uint4*>(ip + static_cast<long long>(t) * C))
+      xv[j] = (t >= 0 && t < Tin) ? __ldcg(reinterpret_cast<const uint4*>(ip + static_cast<long long>(t) * C))
                                   : make_uint4(0, 0, 0, 0);
     }
     F8 o;
@@ -151,8 +155,8 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     }
     if (film != nullptr) {
       const int band = c / (C / bands);
-      const float gm = __ldg(film + static_cast<long long>(b) * film_stride + band * 2);
-      const float bt = __ldg(film + static_cast<long long>(b) * film_stride + band * 2 + 1);
+      const float gm = __ldcg(film + static_cast<long long>(b) * film_stride + band * 2);
+      const float bt = __ldcg(film + static_cast<long long>(b) * film_stride + band * 2 + 1);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = fmaf(o.v[k], gm, bt);
     }
@@ -172,6 +176,8 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 __global__ void __launch_bounds__(256)
 up_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
           __nv_bfloat16* __restrict__ out, int B, int Tin, int C, int r) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C8 = C >> 3;
   const long long total = static_cast<long long>(B) * Tin * C8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -209,6 +215,8 @@ __global__ void __launch_bounds__(256)
 conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_raw,
                 __nv_bfloat16* __restrict__ out_act, float act_scale, int B, int T, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C8 = C >> 3;
   const int runs = (T + PRE_TT - 1) / PRE_TT;
   const long long total = static_cast<long long>(B) * runs * C8;
@@ -224,7 +232,7 @@ conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
 #pragma unroll
     for (int j = 0; j < PRE_TT + 4; ++j) {
       const int tt = t0 - 4 + j;
-      xs[j] = (tt >= 0 && tt < T) ? __ldg(xp + tt) : 0.f;
+      xs[j] = (tt >= 0 && tt < T) ? __ldcg(xp + tt) : 0.f;
     }
     F8 wt[5];
 #pragma unroll
@@ -262,6 +270,8 @@ __global__ void __launch_bounds__(CL_TILE)
 conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, float bias,
                  const float* __restrict__ x, float* __restrict__ wm_out,
                  float* __restrict__ y_out, int B, int Tp, int T, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ uint8_t cl_smem[];
   const int pitch = C * 2 + 16;  // bytes
   float* ws = reinterpret_cast<float*>(cl_smem);                        // [5][C]
@@ -276,7 +286,7 @@ conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
     const int t = t0 - 4 + row;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (t >= 0 && t < Tp)
-      u = __ldg(reinterpret_cast<const uint4*>(in + (static_cast<long long>(b) * Tp + t) * C) + cg);
+      u = __ldcg(reinterpret_cast<const uint4*>(in + (static_cast<long long>(b) * Tp + t) * C) + cg);
     *reinterpret_cast<uint4*>(tile + row * pitch + cg * 16) = u;
   }
   __syncthreads();
@@ -300,7 +310,7 @@ conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
   const float wm = tanhf(acc);
   const long long o = static_cast<long long>(b) * T + t;
   if (wm_out != nullptr) wm_out[o] = wm;
-  if (y_out != nullptr) y_out[o] = __ldg(x + o) + wm;
+  if (y_out != nullptr) y_out[o] = __ldcg(x + o) + wm;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -310,13 +320,15 @@ conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
 __global__ void __launch_bounds__(256)
 wav_stage_kernel(const float* __restrict__ x, __half* __restrict__ out, float scale, int B, int T,
                  int lead, int pitch) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = static_cast<long long>(B) * pitch;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int p = static_cast<int>(idx % pitch);
     const int b = static_cast<int>(idx / pitch);
     const int t = p - lead;
-    const float v = (t >= 0 && t < T) ? __ldg(x + static_cast<long long>(b) * T + t) * scale : 0.f;
+    const float v = (t >= 0 && t < T) ? __ldcg(x + static_cast<long long>(b) * T + t) * scale : 0.f;
     out[idx] = __float2half_rn(v);
   }
 }
@@ -326,6 +338,8 @@ wav_stage_kernel(const float* __restrict__ x, __half* __restrict__ out, float sc
 __global__ void __launch_bounds__(256)
 frames_kernel(const __half* __restrict__ wav16, __half* __restrict__ frames, int B, int F, int hop,
               int n_fft, int base, int pitch) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int N8 = n_fft >> 3;
   const long long total = static_cast<long long>(B) * F * N8;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -337,7 +351,7 @@ frames_kernel(const __half* __restrict__ wav16, __half* __restrict__ frames, int
     const __half* sp = wav16 + static_cast<long long>(b) * pitch + base + f * hop + n8 * 8;
     __half h[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h[k] = sp[k];
+    for (int k = 0; k < 8; ++k) h[k] = __ldcg(sp + k);
     *reinterpret_cast<uint4*>(frames + (rr * n_fft) + n8 * 8) = *reinterpret_cast<uint4*>(h);
   }
 }
@@ -356,13 +370,15 @@ struct FilmArgs {
   int msg_dim, E, n_film;
 };
 __global__ void film_kernel(const float* __restrict__ msg, float* __restrict__ film, FilmArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float fs[];
   float* e0 = fs;
   float* e1 = fs + a.E;
   const int b = blockIdx.x, i = threadIdx.x;
   if (i < a.E) {
     float s = a.b[0][i];
-    for (int k = 0; k < a.msg_dim; ++k) s = fmaf(a.w[0][i * a.msg_dim + k], msg[b * a.msg_dim + k], s);
+    for (int k = 0; k < a.msg_dim; ++k) s = fmaf(a.w[0][i * a.msg_dim + k], __ldcg(msg + b * a.msg_dim + k), s);
     e0[i] = s;
   }
   __syncthreads();
@@ -392,12 +408,14 @@ __global__ void bits_finish_kernel(const float* __restrict__ partial, int F, int
                                    int tiles_per_bit, const uint8_t* __restrict__ presence, int T,
                                    int nbits, uint8_t* __restrict__ bits, float* __restrict__ avg,
                                    uint8_t* __restrict__ valid) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x, o = blockIdx.y, lane = threadIdx.x;
   float s = 0.f;
   const int n = F * tiles_per_bit;
   for (int i = lane; i < n; i += 32) {
     const int f = i / tiles_per_bit, tl = i % tiles_per_bit;
-    s += partial[(static_cast<long long>(b) * F + f) * tiles_n + o * tiles_per_bit + tl];
+    s += __ldcg(partial + (static_cast<long long>(b) * F + f) * tiles_n + o * tiles_per_bit + tl);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -405,7 +423,7 @@ __global__ void bits_finish_kernel(const float* __restrict__ partial, int F, int
   bool ok = true;
   if (presence != nullptr) {
     int c = 0;
-    for (int t = lane; t < T; t += 32) c += presence[static_cast<long long>(b) * T + t] ? 1 : 0;
+    for (int t = lane; t < T; t += 32) c += __ldcg(presence + static_cast<long long>(b) * T + t) ? 1 : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     ok = c > 0;
@@ -420,10 +438,12 @@ __global__ void bits_finish_kernel(const float* __restrict__ partial, int F, int
 }
 __global__ void conf_kernel(const float* __restrict__ avg, float* __restrict__ conf, int B,
                             int nbits) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float s = 0.f;
-  for (int o = 0; o < nbits; ++o) s += avg[b * nbits + o];
+  for (int o = 0; o < nbits; ++o) s += __ldcg(avg + b * nbits + o);
   conf[b] = s / nbits;
 }
 
@@ -470,6 +490,8 @@ metrics_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ val
 // fp32 [B, C, F] -> bf16 [B, F, C] (Generator.decode entry, model/generator.py:334)
 __global__ void latent_in_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out,
                                  int B, int C, int F) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long total = static_cast<long long>(B) * F * C;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -477,7 +499,7 @@ __global__ void latent_in_kernel(const float* __restrict__ z, __nv_bfloat16* __r
     const long long rr = idx / C;
     const int f = static_cast<int>(rr % F);
     const int b = static_cast<int>(rr / F);
-    out[idx] = __float2bfloat16_rn(z[(static_cast<long long>(b) * C + c) * F + f]);
+    out[idx] = __float2bfloat16_rn(__ldcg(z + (static_cast<long long>(b) * C + c) * F + f));
   }
 }
 

@@ -12,6 +12,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of a plan is launched with programmaticStreamSerialization: its CTAs may be placed
+// (and run their prologue: barrier init, TMEM allocation, tap loads) while the previous kernel
+// drains.  pdl_wait() returns once the previous grid has completed and its writes are visible;
+// nothing produced by an earlier kernel is read, and no global write is issued, before it.
+// Activation data is read through L2 (ld.global.cg / TMA), never through the non-coherent path.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

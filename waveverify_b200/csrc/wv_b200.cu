@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -96,6 +97,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
+bool g_pdl = true;   // programmatic dependent launch for every plan kernel (WV_PDL=0 disables)
 void init_device_once() {
   static bool done = false;
   if (done) return;
@@ -107,6 +109,7 @@ void init_device_once() {
     WV_THROW(WV_ERR_UNSUPPORTED, "this library targets sm_100a (B200); device is sm_%d%d",
              prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("WV_PDL")) g_pdl = atoi(e) != 0;   // A/B switch for the profiling scripts
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
@@ -1087,14 +1090,29 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
   return ref;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel's prologue may overlap the tail of
+// the previous kernel in the stream; every kernel calls griddepcontrol.wait before touching data.
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+}
+
 void launch_down(int grid, cudaStream_t st, const bf16* in, const float* w, const float* bias, const float* film,
                  int film_stride, int bands, bf16* out_raw, bf16* out_act, float act_scale, int B, int Tin, int Tout,
                  int C, int r) {
   switch (r) {
 #define WV_DOWN_CASE(R)                                                                                      \
   case R:                                                                                                    \
-    down_kernel<R><<<grid, 256, 0, st>>>(in, w, bias, film, film_stride, bands, out_raw, out_act, act_scale, \
-                                         B, Tin, Tout, C);                                                   \
+    launch_k(down_kernel<R>, grid, 256, 0, st, in, w, bias, film, film_stride, bands, out_raw, out_act,      \
+             act_scale, B, Tin, Tout, C);                                                                    \
     break;
     WV_DOWN_CASE(2) WV_DOWN_CASE(3) WV_DOWN_CASE(4) WV_DOWN_CASE(5) WV_DOWN_CASE(6) WV_DOWN_CASE(8)
 #undef WV_DOWN_CASE
@@ -1105,10 +1123,10 @@ void launch_down(int grid, cudaStream_t st, const bf16* in, const float* w, cons
 void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(op.i[7]);
   switch (op.epi) {
-    case EPI_STAGED: gemm_sm100_kernel<EPI_STAGED><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
-    case EPI_L2NORM: gemm_sm100_kernel<EPI_L2NORM><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
-    case EPI_STFT: gemm_sm100_kernel<EPI_STFT><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
-    default: gemm_sm100_kernel<EPI_HEAD><<<op.grid, GEMM_THREADS, smem, st>>>(op.tmA, op.tmB, g); break;
+    case EPI_STAGED: launch_k(gemm_sm100_kernel<EPI_STAGED>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
+    case EPI_L2NORM: launch_k(gemm_sm100_kernel<EPI_L2NORM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
+    case EPI_STFT: launch_k(gemm_sm100_kernel<EPI_STFT>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
+    default: launch_k(gemm_sm100_kernel<EPI_HEAD>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
   }
 }
 
@@ -1138,45 +1156,45 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         break;
       }
       case OP_DW5:
-        dw5_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, op.bias, static_cast<const bf16*>(op.res),
-                                            static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        launch_k(dw5_kernel, op.grid, 256, 0, st, static_cast<const bf16*>(op.in), op.w, op.bias, static_cast<const bf16*>(op.res),
+                 static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
         break;
       case OP_DOWN:
         launch_down(op.grid, st, static_cast<const bf16*>(op.in), op.w, op.bias, op.film, op.i[5], op.i[6],
                     static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]);
         break;
       case OP_UP:
-        up_kernel<<<op.grid, 256, 0, st>>>(static_cast<const bf16*>(op.in), op.w, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3]);
+        launch_k(up_kernel, op.grid, 256, 0, st, static_cast<const bf16*>(op.in), op.w, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3]);
         break;
       case OP_CONV_PRE:
-        conv_pre_kernel<<<op.grid, 256, 0, st>>>(io.x, op.w, op.bias, static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        launch_k(conv_pre_kernel, op.grid, 256, 0, st, io.x, op.w, op.bias, static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
         break;
       case OP_CONV_LAST: {
         const int C = op.i[3];
         const size_t smem = ((5 * C * 4 + 15) & ~15) + static_cast<size_t>(CL_TILE + 4) * (C * 2 + 16);
-        conv_last_kernel<<<op.grid, CL_TILE, smem, st>>>(static_cast<const bf16*>(op.in), op.w, op.fa, io.x, io.wm, io.y, op.i[0], op.i[1], op.i[2], C);
+        launch_k(conv_last_kernel, op.grid, CL_TILE, smem, st, static_cast<const bf16*>(op.in), op.w, op.fa, io.x, io.wm, io.y, op.i[0], op.i[1], op.i[2], C);
         break;
       }
       case OP_WAV_STAGE:
-        wav_stage_kernel<<<op.grid, 256, 0, st>>>(io.x, static_cast<__half*>(op.out0), op.fa, op.i[0], op.i[1], op.i[2], op.i[3]);
+        launch_k(wav_stage_kernel, op.grid, 256, 0, st, io.x, static_cast<__half*>(op.out0), op.fa, op.i[0], op.i[1], op.i[2], op.i[3]);
         break;
       case OP_FRAMES:
-        frames_kernel<<<op.grid, 256, 0, st>>>(static_cast<const __half*>(op.in), static_cast<__half*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], op.i[5]);
+        launch_k(frames_kernel, op.grid, 256, 0, st, static_cast<const __half*>(op.in), static_cast<__half*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], op.i[5]);
         break;
       case OP_FILM:
-        film_kernel<<<op.i[0], std::max(64, op.fargs.E), 2 * op.fargs.E * sizeof(float), st>>>(io.msg, static_cast<float*>(op.out0), op.fargs);
+        launch_k(film_kernel, op.i[0], std::max(64, op.fargs.E), 2 * op.fargs.E * sizeof(float), st, io.msg, static_cast<float*>(op.out0), op.fargs);
         break;
       case OP_BITS:
         if (io.bits || io.avg || io.conf || io.valid) {
           // avg is needed for conf: use caller's buffer or skip conf when absent
-          bits_finish_kernel<<<dim3(op.i[0], op.i[5]), 32, 0, st>>>(static_cast<const float*>(op.in), op.i[1], op.i[2], op.i[3], io.presence, op.i[4], op.i[5], io.bits, io.avg, io.valid);
+          launch_k(bits_finish_kernel, dim3(op.i[0], op.i[5]), 32, 0, st, static_cast<const float*>(op.in), op.i[1], op.i[2], op.i[3], io.presence, op.i[4], op.i[5], io.bits, io.avg, io.valid);
         }
         break;
       case OP_CONF:
-        if (io.conf && io.avg) conf_kernel<<<ceil_div(op.i[0], 128), 128, 0, st>>>(io.avg, io.conf, op.i[0], op.i[1]);
+        if (io.conf && io.avg) launch_k(conf_kernel, ceil_div(op.i[0], 128), 128, 0, st, io.avg, io.conf, op.i[0], op.i[1]);
         break;
       case OP_LATENT_IN:
-        latent_in_kernel<<<op.grid, 256, 0, st>>>(io.z_in, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2]);
+        launch_k(latent_in_kernel, op.grid, 256, 0, st, io.z_in, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2]);
         break;
     }
     if (prof) CK(cudaEventRecord(plan.events[op_index + 1], st));
