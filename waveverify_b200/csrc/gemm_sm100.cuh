@@ -52,6 +52,9 @@ constexpr int P2_WARPS = EPI_WARPS - P1_WARPS;   // STAGED: smem -> math -> glob
 constexpr int P2_THREADS = P2_WARPS * 32;
 constexpr int STAGE_BUFS = 2;               // staging tiles (drain of tile i+1 overlaps math of tile i)
 constexpr int STAGED_MAX_BN = 128;
+constexpr int BAR_TAPS = 1;                // named barrier ids: 1 = down-conv tap staging,
+constexpr int BAR_ST_FULL = 2;             // 2,3 = staging tile written (drain arrive, math sync),
+constexpr int BAR_ST_EMPTY = 4;            // 4,5 = staging tile consumed (math arrive, drain sync)
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 256;
 constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [2r <= 16][block_n] fp16
@@ -297,7 +300,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   int cached_nt = -1;
   __half2 wt[TAPS][2], bs[2];
   int sb = 0;
-  uint32_t sb_phase = 0;
+  int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
@@ -330,7 +333,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     if constexpr (RES) {
       if (have) load_residual(g, base + static_cast<size_t>(grp * P2_ROWS) * g.ldo, row_bytes, rows_left - grp * P2_ROWS, rres);
     }
-    mbar_wait(&st_full[sb], sb_phase);
+    named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);                 // drain warps staged tile sb
     const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
     while (have) {
       const int ro = grp * P2_ROWS;                                // tile-relative output row
@@ -353,8 +356,8 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       have = have_next;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&st_empty[sb]);   // this warp no longer reads staging tile sb
-    if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+    if (--tiles_left >= STAGE_BUFS) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);   // tile sb may be refilled
+    if (++sb == STAGE_BUFS) sb = 0;
     rot += (gstride + 1) >> 1;
     if (rot >= gstride) rot -= gstride;
   }
@@ -385,12 +388,12 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   int cached_nt = -1;
   float bs[4];
   int sb = 0;
-  uint32_t sb_phase = 0;
+  int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
     const int c = tc.nt * g.block_n + cg * 4;
     if (tc.nt != cached_nt) {                                      // (re)stage taps for this N tile
       cached_nt = tc.nt;
-      asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory");   // previous taps no longer read
+      named_bar_sync(BAR_TAPS, P2_THREADS);                           // previous taps no longer read
       for (int i = et; i < 2 * R * cgs; i += P2_THREADS) {
         const int j = i / cgs, q = i % cgs;
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + tc.nt * g.block_n + q * 4));
@@ -398,7 +401,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
         *reinterpret_cast<uint2*>(down_w + (j * g.block_n + q * 4) * 2) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory");
+      named_bar_sync(BAR_TAPS, P2_THREADS);
       if (g.bias != nullptr) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
         bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
@@ -412,7 +415,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       gm = __ldcg(fp);
       bt = __ldcg(fp + 1);
     }
-    mbar_wait(&st_full[sb], sb_phase);
+    named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);
     if (active) {
       const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
       const int i_base = tc.mi * OUTS;                              // first output row of the tile
@@ -456,8 +459,8 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&st_empty[sb]);
-    if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+    if (--tiles_left >= STAGE_BUFS) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);
+    if (++sb == STAGE_BUFS) sb = 0;
   }
 }
 
@@ -596,12 +599,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       static_assert(REGS_DRAIN == 96, "drain warps keep their launch allocation (65536 / 640 -> 96)");
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
       const uint32_t stage_u32 = smem_u32(stage_tiles);
-      int as = 0, sb = 0;
-      uint32_t as_phase = 0, sb_phase = 0;
+      int as = 0, sb = 0, it = 0;
+      uint32_t as_phase = 0;
       uint32_t v[32];
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        if (it >= STAGE_BUFS) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
         mbar_wait(&acc_full[as], as_phase);
-        mbar_wait(&st_empty[sb], sb_phase ^ 1);
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
@@ -619,12 +622,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
-          mbar_arrive(&st_full[sb]);     // release: this warp's 32 rows are staged
-        }
+        if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
+        named_bar_arrive(BAR_ST_FULL + sb, EPI_THREADS);   // release: this warp's 32 rows are staged
         if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
-        if (++sb == STAGE_BUFS) { sb = 0; sb_phase ^= 1; }
+        if (++sb == STAGE_BUFS) sb = 0;
       }
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global

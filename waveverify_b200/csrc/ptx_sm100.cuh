@@ -36,30 +36,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
+// Bounded wait in five instructions per poll (try_wait, branch, count, compare, branch): the polls
+// of idle warps share issue slots with the epilogue math warps.  A protocol bug traps after 2^20
+// polls (>= 25 ms; every legitimate wait inside a kernel is microseconds) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"   // %3: suspend-time hint (ns)
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "WV_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // %2: suspend-time hint (ns)
+      "@p bra WV_WAIT_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, 1048576;\n"
+      "@p bra WV_WAIT_LOOP;\n"
+      "trap;\n"
+      "WV_WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(20000u)
       : "memory");
-  return ok != 0;
 }
-// Bounded wait: a protocol bug must trap within ~2 s instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFF) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("wv: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
+
+// Named CTA barriers (bar.sync / bar.arrive): a warp blocked in bar.sync issues nothing, unlike an
+// mbarrier poll.  Used for the drain <-> math hand-off of the STAGED epilogue.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
