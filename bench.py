@@ -145,7 +145,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
 
@@ -341,7 +341,7 @@ def run_ours(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "fp16", "data": "synthetic",
             "config": {"workload": workload_name(a), "clips_per_gpu": B, "clip_seconds": a.seconds,
                        "l2": "flushed between steps (256 MiB memset outside the per-step events); per-step activations >> L2",
                        "weights": "random-init conf/base.yml architecture (fixture weights)", "parallelism": f"dp{world} (clips sharded, no hot-loop collective)",

@@ -22,13 +22,16 @@ def S():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def bf16_close(out, ref, rel=2 ** -8, abs_=2e-3, mid=None):
-    """bf16 has 8 significant bits (half-ulp 2^-9 relative).  The staged epilogue rounds the GEMM
-    tile to bf16 before bias / residual / depthwise taps, so outputs carry two roundings."""
+def bf16_close(out, ref, rel=2 ** -9, abs_=2e-3, mid=None):
+    """Tolerance of the 16-bit path.  Activations are fp16 (11 significant bits, half-ulp 2^-12
+    relative); the staged epilogue rounds the GEMM tile to fp16, then taps / bias / residual / scale
+    each round once more (packed half2 arithmetic), and the half2 ELU carries <= 1e-3 absolute error
+    on its (-1, 0] branch: rel = 2^-9 and abs >= 2e-3 cover that chain with margin (and are still 2x
+    tighter than the bf16 tolerance this helper was first written for, hence the name)."""
     err = (out.float() - ref).abs()
     tol = rel * ref.abs() + abs_
-    if mid is not None:          # bf16 rounding of the staged accumulator, before bias / residual
-        tol = tol + 2 * rel * mid.abs()   # a full bf16 ulp when the staged value rounds the other way
+    if mid is not None:          # fp16 rounding of the staged accumulator, before bias / residual
+        tol = tol + 2 * rel * mid.abs()
     assert bool((err <= tol).all()), f"max err {err.max().item()} (ref max {ref.abs().max().item()})"
 
 
@@ -53,15 +56,15 @@ def test_gemm_tcgen05(M, N, K, bias, res, act):
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     lda = (K + 7) // 8 * 8
-    A = torch.zeros(M, lda, dtype=torch.bfloat16)
-    A[:, :K] = torch.randn(M, K, generator=g).to(torch.bfloat16)
-    W = torch.zeros(N, lda, dtype=torch.bfloat16)
-    W[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    A = torch.zeros(M, lda, dtype=torch.float16)
+    A[:, :K] = torch.randn(M, K, generator=g).to(torch.float16)
+    W = torch.zeros(N, lda, dtype=torch.float16)
+    W[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16)
     b = torch.randn(N, generator=g).to(dev) if bias else None
-    R = torch.randn(M, N, generator=g).to(torch.bfloat16).to(dev) if res else None
+    R = torch.randn(M, N, generator=g).to(torch.float16).to(dev) if res else None
     A, W = A.to(dev), W.to(dev)
-    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev)
-    outa = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev) if act else None
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device=dev)
+    outa = torch.full((M, N), float("nan"), dtype=torch.float16, device=dev) if act else None
     rc = _lib().wv_op_gemm(P(A), lda, P(W), lda, M, N, K, P(b), P(R), P(out), P(outa), 0.8, 0, S())
     assert rc == 0, _lib().wv_last_error()
     torch.cuda.synchronize()
@@ -83,15 +86,15 @@ def test_gemm_fp16_operands():
     M, N, K = 3000, 128, 128
     A = torch.randn(M, K, generator=g).half().to(dev)
     W = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(dev)
-    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(M, N, dtype=torch.float16, device=dev)
     rc = _lib().wv_op_gemm(P(A), K, P(W), K, M, N, K, None, None, P(out), None, 1.0, 1, S())
     assert rc == 0, _lib().wv_last_error()
     torch.cuda.synchronize()
     bf16_close(out, (A.double() @ W.double().t()).float())
 
 
-def _cl(x):  # [B,C,T] fp32 -> channels-last bf16 [B,T,C]
-    return x.transpose(1, 2).contiguous().to(torch.bfloat16)
+def _cl(x):  # [B,C,T] fp32 -> channels-last fp16 [B,T,C]
+    return x.transpose(1, 2).contiguous().to(torch.float16)
 
 
 @pytest.mark.parametrize("B,T,C", [(2, 1000, 64), (1, 7, 32), (3, 4097, 96), (1, 50, 1536), (2, 333, 384)])
@@ -105,8 +108,8 @@ def test_dw5(B, T, C, mode):
     r = torch.randn(B, C, T, generator=g) if mode == "res_both" else None
     xin = _cl(x).to(dev)
     wk = w[:, 0, :].t().contiguous().to(dev)             # [5][C]
-    out_raw = torch.empty(B, T, C, dtype=torch.bfloat16, device=dev) if mode != "act" else None
-    out_act = torch.empty(B, T, C, dtype=torch.bfloat16, device=dev) if mode != "raw_nobias" else None
+    out_raw = torch.empty(B, T, C, dtype=torch.float16, device=dev) if mode != "act" else None
+    out_act = torch.empty(B, T, C, dtype=torch.float16, device=dev) if mode != "raw_nobias" else None
     rin = _cl(r).to(dev) if r is not None else None
     rc = _lib().wv_op_dw5(P(xin), P(wk), P(b.to(dev)) if b is not None else None, P(rin), P(out_raw), P(out_act),
                           0.7, B, T, C, S())
@@ -135,8 +138,8 @@ def test_down_conv_film(B, Tin, C, r, film):
     wk = w[:, 0, :].t().contiguous().to(dev)
     To = -(-Tin // r)
     ft = torch.randn(B, 3, 4, 2, generator=g) if film else None    # [B, scales, bands, 2]; use scale 1
-    out_raw = torch.empty(B, To, C, dtype=torch.bfloat16, device=dev)
-    out_act = torch.empty(B, To, C, dtype=torch.bfloat16, device=dev)
+    out_raw = torch.empty(B, To, C, dtype=torch.float16, device=dev)
+    out_act = torch.empty(B, To, C, dtype=torch.float16, device=dev)
     ftd = ft.to(dev) if film else None
     fptr = C_void(ftd[:, 1]) if film else None
     rc = _lib().wv_op_down(P(xin), P(wk), P(b.to(dev)), fptr, 3 * 4 * 2, 4, P(out_raw), P(out_act), 0.9,
@@ -169,7 +172,7 @@ def test_up_conv_transposed(B, Tin, C, r):
     w = torch.randn(C, 1, 2 * r, generator=g) * 0.3
     xin = _cl(x).to(dev)
     wk = w[:, 0, :].t().contiguous().to(dev)
-    out = torch.empty(B, Tin * r, C, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B, Tin * r, C, dtype=torch.float16, device=dev)
     rc = _lib().wv_op_up(P(xin), P(wk), P(out), B, Tin, C, r, S())
     assert rc == 0, _lib().wv_last_error()
     torch.cuda.synchronize()
@@ -186,21 +189,21 @@ def test_gemm_with_fused_depthwise_epilogue(B, T, N, K, mode):
     per-clip tiles of 128 rows with a 4-row halo (first tile starts at t=-4: TMA zero fill)."""
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(T + N + K)
-    A = torch.randn(B, T, K, generator=g).to(torch.bfloat16).to(dev)
-    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    A = torch.randn(B, T, K, generator=g).to(torch.float16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.float16).to(dev)
     dw = (torch.randn(N, 1, 5, generator=g) * 0.4)
     b = torch.randn(N, generator=g)
-    R = torch.randn(B, T, N, generator=g).to(torch.bfloat16).to(dev) if mode == "res_both" else None
+    R = torch.randn(B, T, N, generator=g).to(torch.float16).to(dev) if mode == "res_both" else None
     wk = dw[:, 0, :].t().contiguous().to(dev)
-    out_raw = torch.full((B, T, N), float("nan"), dtype=torch.bfloat16, device=dev) if mode == "res_both" else None
-    out_act = torch.full((B, T, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    out_raw = torch.full((B, T, N), float("nan"), dtype=torch.float16, device=dev) if mode == "res_both" else None
+    out_act = torch.full((B, T, N), float("nan"), dtype=torch.float16, device=dev)
     rc = _lib().wv_op_gemm_dw5(P(A), P(W), B, T, N, K, P(wk), P(b.to(dev)), P(R), P(out_raw), P(out_act), 0.75, S())
     assert rc == 0, _lib().wv_last_error()
     torch.cuda.synchronize()
-    G = (A.double() @ W.double().t()).to(torch.bfloat16).float().cpu()      # the kernel stages the GEMM tile in bf16
+    G = (A.double() @ W.double().t()).to(torch.float16).float().cpu()      # the kernel stages the GEMM tile in fp16
     ref = F.conv1d(F.pad(G.transpose(1, 2), (4, 0)), dw, b, groups=N).transpose(1, 2)
     # a staged element may round the other way than the emulation (fp32 summation order): bound by
-    # one bf16 ulp of |G| pushed through |w|
+    # one fp16 ulp of |G| pushed through |w| (bound kept at the bf16 size)
     mid = F.conv1d(F.pad(G.abs().transpose(1, 2), (4, 0)), dw.abs(), None, groups=N).transpose(1, 2)
     if R is not None:
         ref = ref + R.float().cpu()

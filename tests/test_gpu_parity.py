@@ -2,14 +2,16 @@
 the reference itself (tests/golden) and (b) the CPU oracle on fresh inputs, plus
 size-independent properties at the benchmark sizes.
 
-Stated tolerances (bf16 activations, fp32 accumulation, fp16 STFT operands; cf. BASELINE.md
-section 4 - PyTorch's own bf16 autocast of the reference reaches 31.5 dB on the residual):
-  watermark residual / watermarked audio : SNR >= 40 dB, max-abs <= 2e-3
-  latent                                 : SNR >= 38 dB
-  detector logits                        : SNR >= 40 dB, max-abs <= 0.3 ; avg prob max-abs <= 1.5e-3
-  locator logits                         : SNR >= 40 dB, max-abs <= 0.12
-  decoded bits                           : exact wherever |avg_ref - 0.5| > 2e-3 (guard band)
-  locator mask                           : exact wherever |logit_ref - 0.5| > 0.08; inside the
+Stated tolerances (fp16 activations and weights on the tensor cores, fp32 accumulation, packed
+half2 epilogues; cf. BASELINE.md section 4 - PyTorch's own bf16 autocast of the reference reaches
+31.5 dB on the residual).  Measured values are in profiles/r01_parity_fp16.md (58-62 dB residual,
+57-65 dB logits; every differing mask sample lies within 0.004 of the threshold):
+  watermark residual / watermarked audio : SNR >= 46 dB, max-abs <= 4e-4
+  latent                                 : SNR >= 50 dB
+  detector logits                        : SNR >= 52 dB, max-abs <= 0.08 ; avg prob max-abs <= 2e-4
+  locator logits                         : SNR >= 52 dB, max-abs <= 0.08
+  decoded bits                           : exact wherever |avg_ref - 0.5| > 3e-4 (guard band)
+  locator mask                           : exact wherever |logit_ref - 0.5| > 0.01; inside the
                                            band at most 30 % of the in-band samples may differ
 """
 import os
@@ -42,18 +44,18 @@ def models(zero_init, seed):
 
 
 def check_wave(ref, got, what):
-    assert snr_db(ref, got) >= 40.0, f"{what}: snr {snr_db(ref, got):.1f} dB"
-    assert np.abs(ref - got).max() <= 2e-3, f"{what}: max-abs {np.abs(ref - got).max()}"
+    assert snr_db(ref, got) >= 46.0, f"{what}: snr {snr_db(ref, got):.1f} dB"
+    assert np.abs(ref - got).max() <= 4e-4, f"{what}: max-abs {np.abs(ref - got).max()}"
 
 
 def check_bits(avg_ref, bits_ref, avg, bits):
-    assert np.abs(avg - avg_ref).max() <= 1.5e-3
-    safe = np.abs(avg_ref - 0.5) > 2e-3
+    assert np.abs(avg - avg_ref).max() <= 2e-4
+    safe = np.abs(avg_ref - 0.5) > 3e-4
     assert (bits == bits_ref)[safe].all()
 
 
 def check_mask(logit_ref, mask_ref, mask):
-    safe = np.abs(logit_ref - 0.5) > 0.08
+    safe = np.abs(logit_ref - 0.5) > 0.01
     assert (mask == mask_ref)[safe].all(), "mask differs outside the guard band"
     band = ~safe
     if band.sum() > 50:
@@ -70,20 +72,20 @@ def test_cuda_path_matches_reference_golden(path):
     check_wave(z["wm"], wm.cpu().numpy(), "wm")
     check_wave(z["y"], y.cpu().numpy(), "y")
     assert torch.equal(y, x + wm)            # fused add is the same fp32 add
-    assert snr_db(z["latent"], lat.cpu().numpy()) >= 38.0
+    assert snr_db(z["latent"], lat.cpu().numpy()) >= 50.0
     yg = torch.from_numpy(z["y"]).to(dev)
     d = m["detector"][0].detect_batch(yg, want_logits=True)
     dd = int(z["det_decim"])
     lg = d["logits"][:, :, ::dd].cpu().numpy()
-    assert snr_db(z["det_logits_decim"], lg) >= 40.0
-    assert np.abs(lg - z["det_logits_decim"]).max() <= 0.3
+    assert snr_db(z["det_logits_decim"], lg) >= 52.0
+    assert np.abs(lg - z["det_logits_decim"]).max() <= 0.08
     check_bits(z["det_avg"], z["det_bits"], d["avg"].cpu().numpy(), d["bits"].cpu().numpy())
     np.testing.assert_allclose(d["conf"].cpu().numpy(), z["det_conf"], atol=1e-3)
     assert bool(d["valid"].all())
     l = m["locator"][0].locate_batch(yg, want_logits=True, want_probs=True)
     ll = l["logits"].cpu().numpy()
-    assert snr_db(z["loc_logits"], ll) >= 40.0
-    assert np.abs(ll - z["loc_logits"]).max() <= 0.12
+    assert snr_db(z["loc_logits"], ll) >= 52.0
+    assert np.abs(ll - z["loc_logits"]).max() <= 0.08
     check_mask(z["loc_logits"], z["loc_mask"], l["mask"].cpu().numpy())
     # fused outputs are consistent with the logits the same launch wrote
     assert torch.equal(l["mask"], (l["logits"] > 0.5).to(torch.uint8))
@@ -111,10 +113,10 @@ def test_cuda_path_matches_oracle_fresh_batch():
         ll_o = O.locator_forward(yc, m["locator"][1], m["locator"][2])
     bits_o, avg_o, conf_o, _ = O.decode_bits(lg_o)
     d = m["detector"][0].detect_batch(y, want_logits=True)
-    assert snr_db(lg_o.numpy(), d["logits"].cpu().numpy()) >= 40.0
+    assert snr_db(lg_o.numpy(), d["logits"].cpu().numpy()) >= 52.0
     check_bits(avg_o.numpy(), bits_o.numpy(), d["avg"].cpu().numpy(), d["bits"].cpu().numpy())
     l = m["locator"][0].locate_batch(y, want_logits=True)
-    assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 40.0
+    assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 52.0
     check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy())
 
 
@@ -230,7 +232,7 @@ def test_reference_api_surface():
     np.testing.assert_allclose(z.pow(2).sum(1).sqrt().cpu().numpy(), np.sqrt(128.0), rtol=2e-2)
     wav = G.decode(z)
     assert wav.shape == (2, 1, 13 * 320)
-    # decode(encode(x)) is forward() before the trim, up to bf16 rounding of z
+    # decode(encode(x)) is forward() before the trim, up to fp16 rounding of z
     assert snr_db(wm_sig.audio_data.cpu().numpy(), wav[:, :, :4000].cpu().numpy()) > 35
     with pytest.raises(RuntimeError):
         G.embed_batch(x.cpu(), msg)                          # no CPU fallback

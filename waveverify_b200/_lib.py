@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwv_b200.so")
+LIB_PATH = os.environ.get("WV_LIB_PATH") or os.path.join(HERE, "libwv_b200.so")   # override: A/B builds
 
 KIND = {"generator": 0, "detector": 1, "locator": 2}
 

@@ -14,11 +14,10 @@
 //   STAGED  warps 4-7 ("drain") round the fp32 accumulator tile to fp16 (11-bit mantissa,
 //           saturating) into one of two padded shared-memory tiles and release the TMEM stage;
 //           warps 8-19 ("math", 112 registers via setmaxnreg) walk the staged tile in a coalesced
-//           (4 rows x 4 channels) layout.  The depthwise taps run as packed HFMA2 on the staged
-//           half2 pairs (two channels per instruction, no unpacking), everything after the taps
-//           (residual, ELU) in fp32:
+//           (4 rows x 4 channels) layout.  Taps, bias, residual add and ELU all run on packed half2
+//           pairs (two channels per instruction; fp16 activations are loaded / stored as they are):
 //             v = bias[c] + sum_{j<taps} w[j][c] * S[r-taps+1+j][c]      taps = 1 or 5
-//             v += residual[m,c];  out_raw = bf16(v);  out_act = bf16(ELU(v*s))
+//             v += residual[m,c];  out_raw = v;  out_act = ELU(v*s)        (all packed half2)
 //           taps = 5 fuses the causal depthwise conv that follows every resblock 1x1
 //           (modules/seanet.py:85-109): tiles overlap by 4 rows (128 rows in, 124 out).
 //           The math loop is compiled per (taps, residual, raw, act) combination so the hot loop
@@ -35,6 +34,13 @@
 
 namespace wv {
 
+// Per-tile clock probes of CTA 0 (scripts/timeline.py); compiled in only with -DWV_TIMELINE.
+#ifdef WV_TIMELINE
+#define WV_DBG(slot, it) do { if (g.dbg != nullptr && blockIdx.x == 0 && (it) < 48) g.dbg[(it) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define WV_DBG(slot, it) do { } while (0)
+#endif
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 6;
@@ -42,14 +48,17 @@ constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_WARPS = 16;
+constexpr int EPI_WARPS = 16;               // L2NORM / STFT / HEAD epilogues (640-thread CTA)
 constexpr int EPI_SPLIT = EPI_WARPS / 4;    // warps sharing one TMEM lane quarter split the columns
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int GEMM_THREADS = 128 + EPI_THREADS;
-constexpr int P2_ROWS = 4;                  // output rows per math unit
-constexpr int P1_WARPS = 4;                 // STAGED: TMEM -> smem drain warps (one per lane quarter)
-constexpr int P2_WARPS = EPI_WARPS - P1_WARPS;   // STAGED: smem -> math -> global warps
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+// STAGED: 4 drain + 12 math warps.  (A 1024-thread CTA with 24 math warps at 64 registers was
+// measured: the math phase shortens but the drain slows by as much; no gain.)
+constexpr int P1_WARPS = 4;                 // TMEM -> smem drain warps (one per lane quarter)
+constexpr int P2_WARPS = 12;                // smem -> math -> global warps
 constexpr int P2_THREADS = P2_WARPS * 32;
+constexpr int EPI_THREADS = (P1_WARPS + P2_WARPS) * 32;   // participants of the drain <-> math barriers
+constexpr int STAGED_THREADS = 128 + EPI_THREADS;
+template <int EPI> constexpr int gemm_threads() { return EPI == 0 ? STAGED_THREADS : GEMM_THREADS; }
 constexpr int STAGE_BUFS = 2;               // staging tiles (drain of tile i+1 overlaps math of tile i)
 constexpr int STAGED_MAX_BN = 128;
 constexpr int BAR_TAPS = 1;                // named barrier ids: 1 = down-conv tap staging,
@@ -81,9 +90,9 @@ struct GemmArgs {
   int taps;           // 1, or 5 = fused causal depthwise conv over time
   const float* dw_w;  // [taps][N] fp32 (taps == 5)
   const float* bias;  // [N] (added after the depthwise taps), nullable
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out_raw;
-  __nv_bfloat16* out_act;
+  const act_t* residual;
+  act_t* out_raw;
+  act_t* out_act;
   float act_scale;
   int ldo;
   // L2NORM
@@ -100,6 +109,7 @@ struct GemmArgs {
   float* partial;  // [M, EPI_SPLIT * N / block_n]
   const uint8_t* presence;
   int hop, T, n_out, head_F;
+  long long* dbg;   // timeline probe (profiling builds of scripts/microbench only), nullptr otherwise
 };
 
 __host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n * 2 + 16; }
@@ -131,9 +141,8 @@ __device__ __forceinline__ void reg_alloc() {
 // can be re-acquired): the TMA / MMA warpgroup drops to 40, the drain warpgroup keeps 96, the
 // twelve math warps grow to 112:  128*40 + 128*96 + 384*112 = 60416 <= 61440.
 constexpr int REGS_LIGHT = 40;
-constexpr int REGS_DRAIN = 96;
 constexpr int REGS_MATH = 112;
-static_assert(128 * REGS_LIGHT + 128 * REGS_DRAIN + (GEMM_THREADS - 256) * REGS_MATH <= GEMM_THREADS * 96,
+static_assert(128 * REGS_LIGHT + 128 * 96 + P2_THREADS * REGS_MATH <= STAGED_THREADS * 96,
               "setmaxnreg budget exceeds the CTA's launch allocation");
 
 // q = x / d, r = x % d with a host-computed magic = floor(2^32 / d): one mul.hi + one fix-up.
@@ -193,41 +202,25 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ __half2 h2_from(float lo, float hi) { return __floats2half2_rn(lo, hi); }
-
-// Residual rows of one unit (L2-coherent loads; issued one unit ahead of their use, see below).
-__device__ __forceinline__ void load_residual(const GemmArgs& g, size_t off, size_t row_bytes, int nrow,
-                                              uint2 (&r)[P2_ROWS]) {
-  const char* rp = reinterpret_cast<const char*>(g.residual + off);
-#pragma unroll
-  for (int i = 0; i < P2_ROWS; ++i)
-    r[i] = i < nrow ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
-}
-
-// One math unit: P2_ROWS output rows x 4 channels.  FULL = all rows valid (no predicates).
-template <int TAPS, bool RES, bool RAW, bool ACT, bool FULL, bool SCALE>
+// One math unit: R output rows x 4 channels.  nrow < R only at the end of a tile / clip (FULL=false):
+// rows past nrow are neither read (they may lie beyond the staging tile) nor written.
+template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool FULL, bool SCALE>
 __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*smem addr of tile row ro*/,
                                             int pitch, size_t off, size_t row_bytes, int nrow,
                                             const __half2 (&wt)[TAPS][2], const __half2 (&bs)[2], float s_act,
-                                            const uint2 (&rres)[P2_ROWS]) {
+                                            const uint2 (&rres)[R]) {
   constexpr int HALO = TAPS - 1;
-  __half2 oh[P2_ROWS][2];
+  __half2 oh[R][2];
   if constexpr (TAPS > 1) {
-    __half2 x[P2_ROWS + HALO][2];                            // tile rows ro .. ro+P2_ROWS+HALO-1
+    __half2 x[R + HALO][2];                                  // tile rows ro .. ro+R+HALO-1
 #pragma unroll
-    for (int j = 0; j < P2_ROWS + HALO; ++j) {
-      const uint2 u = lds_u2(srow + j * pitch);
+    for (int j = 0; j < R + HALO; ++j) {
+      const uint2 u = (FULL || j < nrow + HALO) ? lds_u2(srow + j * pitch) : make_uint2(0u, 0u);
       x[j][0] = as_h2(u.x);
       x[j][1] = as_h2(u.y);
     }
 #pragma unroll
-    for (int i = 0; i < P2_ROWS; ++i)
+    for (int i = 0; i < R; ++i)
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         __half2 a = bs[p];
@@ -237,57 +230,46 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
       }
   } else {
 #pragma unroll
-    for (int i = 0; i < P2_ROWS; ++i) {
-      const uint2 u = lds_u2(srow + i * pitch);
+    for (int i = 0; i < R; ++i) {
+      const uint2 u = (FULL || i < nrow) ? lds_u2(srow + i * pitch) : make_uint2(0u, 0u);
       oh[i][0] = __hadd2(as_h2(u.x), bs[0]);
       oh[i][1] = __hadd2(as_h2(u.y), bs[1]);
     }
   }
-  float o[P2_ROWS][4];
-#pragma unroll
-  for (int i = 0; i < P2_ROWS; ++i) {
-    const float2 f0 = __half22float2(oh[i][0]), f1 = __half22float2(oh[i][1]);
-    o[i][0] = f0.x; o[i][1] = f0.y; o[i][2] = f1.x; o[i][3] = f1.y;
-  }
   if constexpr (RES) {
 #pragma unroll
-    for (int i = 0; i < P2_ROWS; ++i) {
-      float ra[4];
-      unpack_bf16x2(rres[i].x, ra[0], ra[1]);
-      unpack_bf16x2(rres[i].y, ra[2], ra[3]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[i][k] += ra[k];
+    for (int i = 0; i < R; ++i) {
+      oh[i][0] = __hadd2(oh[i][0], as_h2(rres[i].x));
+      oh[i][1] = __hadd2(oh[i][1], as_h2(rres[i].y));
     }
   }
   if constexpr (RAW) {
     char* op = reinterpret_cast<char*>(g.out_raw + off);
 #pragma unroll
-    for (int i = 0; i < P2_ROWS; ++i)
+    for (int i = 0; i < R; ++i)
       if (FULL || i < nrow)
-        *reinterpret_cast<uint2*>(op + i * row_bytes) =
-            make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
+        *reinterpret_cast<uint2*>(op + i * row_bytes) = make_uint2(as_u32(oh[i][0]), as_u32(oh[i][1]));
   }
   if constexpr (ACT) {
     char* op = reinterpret_cast<char*>(g.out_act + off);
+    const __half2 s2 = h2_from(s_act, s_act);
 #pragma unroll
-    for (int i = 0; i < P2_ROWS; ++i) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[i][k] = elu_fast(SCALE ? o[i][k] * s_act : o[i][k]);
+    for (int i = 0; i < R; ++i) {
+      const __half2 a0 = elu_h2(SCALE ? __hmul2(oh[i][0], s2) : oh[i][0]);
+      const __half2 a1 = elu_h2(SCALE ? __hmul2(oh[i][1], s2) : oh[i][1]);
       if (FULL || i < nrow)
-        *reinterpret_cast<uint2*>(op + i * row_bytes) =
-            make_uint2(pack_bf16x2(o[i][0], o[i][1]), pack_bf16x2(o[i][2], o[i][3]));
+        *reinterpret_cast<uint2*>(op + i * row_bytes) = make_uint2(as_u32(a0), as_u32(a1));
     }
   }
 }
 
-// STAGED math warps.  thread = (4-channel group, 4-row group): 8-byte smem reads / global accesses
-// keep a warp on contiguous 256-byte row segments while the per-thread state stays under 112 regs.
-template <int TAPS, bool RES, bool RAW, bool ACT, bool SCALE>
-__device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles,
-                                                 uint64_t* st_full, uint64_t* st_empty, int lane) {
+// STAGED math warps.  thread = (4-channel group, R-row group): 8-byte smem reads / global accesses
+// keep a warp on contiguous row segments; a thread walks its row groups in passes of 384 threads.
+template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE>
+__device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   constexpr int HALO = TAPS - 1;
   constexpr int ROWS_OUT = BM - HALO;
-  constexpr int N_GROUPS = ROWS_OUT / P2_ROWS;                   // 31 (taps 5) or 32 (taps 1)
+  constexpr int N_GROUPS = (ROWS_OUT + R - 1) / R;
   const int pitch = staged_pitch_bytes(g.block_n);
   const int et = threadIdx.x - (128 + P1_WARPS * 32);
   const int cgs = g.block_n >> 2;                                // 4-channel groups per row
@@ -301,7 +283,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   __half2 wt[TAPS][2], bs[2];
   int sb = 0;
   int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  int rot = 0;   // rotates which threads take the extra unit when units do not divide evenly
+  int dbg_it = 0;
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
     const int c = tc.nt * g.block_n + cg * 4;
@@ -321,45 +303,51 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
         }
       }
     }
-    // The residual rows of a unit do not depend on the staged tile: the first unit's are requested
-    // before waiting for the drain warps, the next unit's before the current unit's math, so their
-    // HBM latency overlaps the wait / the math instead of stalling every unit.
     const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base) * g.ldo + c;
-    const int rows_left = g.rows_per_clip - r_base;               // valid output rows from r_base on
-    int grp = grp0 + rot;
-    if (grp >= gstride) grp -= gstride;
-    uint2 rres[P2_ROWS], rnext[P2_ROWS];
-    bool have = active && grp < N_GROUPS && grp * P2_ROWS < rows_left;
+    const int rows_left = min(g.rows_per_clip - r_base, ROWS_OUT);   // valid output rows of this tile
+    // The residual rows do not depend on the staged tile: those of the first unit are requested
+    // (L2-resident thanks to the producer's prefetch) before waiting for the drain warps, those of a
+    // second unit before the first unit's math, so their latency overlaps the wait / the math.
+    uint2 rres[R], rnext[R];
+    auto load_res = [&](int ro, uint2 (&r)[R]) {
+      const char* rp = reinterpret_cast<const char*>(g.residual + base + static_cast<size_t>(ro) * g.ldo);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        r[i] = ro + i < rows_left ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
+    };
+    int grp = grp0;
+    bool have = active && grp < N_GROUPS && grp * R < rows_left;
     if constexpr (RES) {
-      if (have) load_residual(g, base + static_cast<size_t>(grp * P2_ROWS) * g.ldo, row_bytes, rows_left - grp * P2_ROWS, rres);
+      if (have) load_res(grp * R, rres);
     }
     named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);                 // drain warps staged tile sb
+    if (et == 0) WV_DBG(5, dbg_it);
     const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
     while (have) {
-      const int ro = grp * P2_ROWS;                                // tile-relative output row
+      const int ro = grp * R;                                      // tile-relative output row
       const int gn = grp + gstride;
-      const bool have_next = gn < N_GROUPS && gn * P2_ROWS < rows_left;
+      const bool have_next = gn < N_GROUPS && gn * R < rows_left;
       if constexpr (RES) {
-        if (have_next) load_residual(g, base + static_cast<size_t>(gn * P2_ROWS) * g.ldo, row_bytes, rows_left - gn * P2_ROWS, rnext);
+        if (have_next) load_res(gn * R, rnext);
       }
       const size_t off = base + static_cast<size_t>(ro) * g.ldo;
       const uint32_t srow = tile_u32 + ro * pitch;
-      if (ro + P2_ROWS <= rows_left)
-        staged_unit<TAPS, RES, RAW, ACT, true, SCALE>(g, srow, pitch, off, row_bytes, P2_ROWS, wt, bs, s_act, rres);
+      if (ro + R <= rows_left)
+        staged_unit<TAPS, R, RES, RAW, ACT, true, SCALE>(g, srow, pitch, off, row_bytes, R, wt, bs, s_act, rres);
       else
-        staged_unit<TAPS, RES, RAW, ACT, false, SCALE>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act, rres);
+        staged_unit<TAPS, R, RES, RAW, ACT, false, SCALE>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act, rres);
       if constexpr (RES) {
 #pragma unroll
-        for (int i = 0; i < P2_ROWS; ++i) rres[i] = rnext[i];
+        for (int i = 0; i < R; ++i) rres[i] = rnext[i];
       }
       grp = gn;
       have = have_next;
     }
     __syncwarp();
+    if (et == 0) WV_DBG(6, dbg_it);
+    ++dbg_it;
     if (--tiles_left >= STAGE_BUFS) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);   // tile sb may be refilled
     if (++sb == STAGE_BUFS) sb = 0;
-    rot += (gstride + 1) >> 1;
-    if (rot >= gstride) rot -= gstride;
   }
 }
 
@@ -371,8 +359,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
 // thread = (4-channel group, output row); taps are staged in shared memory (2R*4 floats per thread
 // would not fit in registers for R = 8).
 template <int R>
-__device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_t* stage_tiles, uint8_t* down_w,
-                                                 uint64_t* st_full, uint64_t* st_empty, int lane) {
+__device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_t* stage_tiles, uint8_t* down_w, int lane) {
   constexpr int OUTS = BM / R - 1;
   const int pitch = staged_pitch_bytes(g.block_n);
   const int et = threadIdx.x - (128 + P1_WARPS * 32);
@@ -386,7 +373,8 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   const uint32_t w_u32 = smem_u32(down_w) + cg * 8;              // taps staged as fp16 [2R][block_n]
   const int band_w = g.film != nullptr ? g.N / g.film_bands : 1;
   int cached_nt = -1;
-  float bs[4];
+  __half2 bs2[2];
+  const __half2 s2 = h2_from(s_act, s_act);
   int sb = 0;
   int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
@@ -404,16 +392,17 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       named_bar_sync(BAR_TAPS, P2_THREADS);
       if (g.bias != nullptr) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-        bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w;
+        bs2[0] = h2_from(b0.x, b0.y); bs2[1] = h2_from(b0.z, b0.w);
       } else {
-        bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
+        bs2[0] = bs2[1] = h2_from(0.f, 0.f);
       }
     }
-    float gm = 1.f, bt = 0.f;
+    __half2 gm2 = h2_from(1.f, 1.f), bt2 = h2_from(0.f, 0.f);
     if (g.film != nullptr) {
       const float* fp = g.film + static_cast<size_t>(tc.clip) * g.film_stride + (c / band_w) * 2;
-      gm = __ldcg(fp);
-      bt = __ldcg(fp + 1);
+      const float gm = __ldcg(fp), bt = __ldcg(fp + 1);
+      gm2 = h2_from(gm, gm);
+      bt2 = h2_from(bt, bt);
     }
     named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);
     if (active) {
@@ -423,7 +412,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip_out + i_base) * g.ldo + c;
       for (int lo = row0; lo < OUTS && lo < outs_left; lo += gstride) {
         // two independent HFMA2 chains per channel pair (even / odd taps) keep the fp16 partial
-        // sums short; they are joined in fp32
+        // sums short
         __half2 a0[2] = {h2_from(0.f, 0.f), h2_from(0.f, 0.f)};
         __half2 a1[2] = {h2_from(0.f, 0.f), h2_from(0.f, 0.f)};
         const uint32_t srow = tile_u32 + lo * R * pitch;
@@ -439,23 +428,15 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
             a0[1] = __hfma2(as_h2(w.y), as_h2(u.y), a0[1]);
           }
         }
-        float o[4];
-        {
-          const float2 p0 = __half22float2(a0[0]), p1 = __half22float2(a0[1]);
-          const float2 q0 = __half22float2(a1[0]), q1 = __half22float2(a1[1]);
-          o[0] = bs[0] + p0.x + q0.x; o[1] = bs[1] + p0.y + q0.y;
-          o[2] = bs[2] + p1.x + q1.x; o[3] = bs[3] + p1.y + q1.y;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = fmaf(o[k], gm, bt);
+        __half2 o0 = __hadd2(__hadd2(a0[0], a1[0]), bs2[0]);
+        __half2 o1 = __hadd2(__hadd2(a0[1], a1[1]), bs2[1]);
+        o0 = __hfma2(o0, gm2, bt2);                                // FiLM (identity when absent)
+        o1 = __hfma2(o1, gm2, bt2);
         const size_t off = base + static_cast<size_t>(lo) * g.ldo;
-        if (raw)
-          *reinterpret_cast<uint2*>(g.out_raw + off) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
-        if (act) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] = elu_fast(o[k] * s_act);
-          *reinterpret_cast<uint2*>(g.out_act + off) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
-        }
+        if (raw) *reinterpret_cast<uint2*>(g.out_raw + off) = make_uint2(as_u32(o0), as_u32(o1));
+        if (act)
+          *reinterpret_cast<uint2*>(g.out_act + off) =
+              make_uint2(as_u32(elu_h2(__hmul2(o0, s2))), as_u32(elu_h2(__hmul2(o1, s2))));
       }
     }
     __syncwarp();
@@ -464,12 +445,11 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   }
 }
 
-template <int TAPS>
-__device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const uint8_t* stage_tiles,
-                                                     uint64_t* st_full, uint64_t* st_empty, int lane) {
+template <int TAPS, int R>
+__device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   const bool res = g.residual != nullptr, raw = g.out_raw != nullptr, act = g.out_act != nullptr;
   const bool scale = act && g.act_scale != 1.f;
-#define WV_MATH(R, W, A, S) staged_math_loop<TAPS, R, W, A, S>(g, stage_tiles, st_full, st_empty, lane)
+#define WV_MATH(RS, W, A, S) staged_math_loop<TAPS, R, RS, W, A, S>(g, stage_tiles, lane)
   if (res) {
     if (raw && act) { if (scale) WV_MATH(true, true, true, true); else WV_MATH(true, true, true, false); }
     else if (raw) WV_MATH(true, true, false, false);
@@ -481,12 +461,16 @@ __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const ui
   }
 #undef WV_MATH
 }
+template <int TAPS>
+__device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
+  staged_math_dispatch<TAPS, 4>(g, stage_tiles, lane);   // 6- and 8-row units were measured: slower
+}
 
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const GemmArgs g) {
+                  const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -499,11 +483,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
   uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [ACC_STAGES]
   uint64_t* acc_empty = acc_full + ACC_STAGES;
-  uint64_t* st_full = acc_empty + ACC_STAGES;     // [STAGE_BUFS] staging tile written
-  uint64_t* st_empty = st_full + STAGE_BUFS;      // [STAGE_BUFS] staging tile consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_empty + STAGE_BUFS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
   uint8_t* down_w = after + GEMM_BAR_BYTES;       // [2r][block_n] fp32 (STAGED down-conv only)
-  uint8_t* stage_tiles = down_w + DOWN_W_BYTES;   // [STAGE_BUFS][BM][pitch] bf16 (STAGED only)
+  uint8_t* stage_tiles = down_w + DOWN_W_BYTES;   // [STAGE_BUFS][BM][pitch] fp16 (STAGED only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -514,9 +496,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_kb = (g.K + BK - 1) / BK;
   const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
 
+  const bool has_res = EPI == EPI_STAGED && g.residual != nullptr;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (has_res) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
@@ -526,10 +510,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : EPI_WARPS);  // one arrive per draining warp
-    }
-    for (int i = 0; i < STAGE_BUFS; ++i) {
-      mbar_init(&st_full[i], P1_WARPS);
-      mbar_init(&st_empty[i], P2_WARPS);
     }
     fence_mbar_init();
   }
@@ -548,11 +528,16 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
+      int dbg_it = 0;
+      for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(), ++dbg_it) {
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
+        // The residual rows of this tile are read by the math warps (plain loads) two to three tiles
+        // from now: pull them into L2 alongside the A operand so that those loads do not wait on HBM.
+        if (has_res) tma_prefetch_l2_3d(&tmR, n0, tc.mi * rows_out, tc.clip);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
           tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
           tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
@@ -568,12 +553,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int as = 0;
       uint32_t as_phase = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      int dbg_it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++dbg_it) {
         mbar_wait(&acc_empty[as], as_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * MAX_BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (kb == num_kb - 1) WV_DBG(1, dbg_it);
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + stage * A_STAGE_BYTES));
           const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * b_stage_bytes));
@@ -583,7 +570,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, g.idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&acc_full[as]);
+          if (kb == num_kb - 1) { umma_commit(&acc_full[as]); WV_DBG(2, dbg_it); }
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
         if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
@@ -596,7 +583,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int chunks = g.block_n / 32;
     if (warp < 4 + P1_WARPS) {
       // ---------------------------------------------------------- drain warps: TMEM -> fp16 -> smem
-      static_assert(REGS_DRAIN == 96, "drain warps keep their launch allocation (65536 / 640 -> 96)");
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
       const uint32_t stage_u32 = smem_u32(stage_tiles);
       int as = 0, sb = 0, it = 0;
@@ -605,6 +591,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
         if (it >= STAGE_BUFS) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
         mbar_wait(&acc_full[as], as_phase);
+        if (q == 0 && lane == 0) WV_DBG(3, it);
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
@@ -615,14 +602,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             sts_u4(rowp + c * 64 + i * 16,
-                   pack_f16x2_sat(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                   pack_f16x2_sat(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                   pack_f16x2_sat(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                   pack_f16x2_sat(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+                   pack_act2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                   pack_act2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                   pack_act2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                   pack_act2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
+        if (q == 0 && lane == 0) WV_DBG(4, it);
         named_bar_arrive(BAR_ST_FULL + sb, EPI_THREADS);   // release: this warp's 32 rows are staged
         if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
         if (++sb == STAGE_BUFS) sb = 0;
@@ -632,13 +620,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       reg_alloc<REGS_MATH>();
       if (g.down_r > 0) {
         switch (g.down_r) {
-          case 2: staged_down_loop<2>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
-          case 4: staged_down_loop<4>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
-          case 5: staged_down_loop<5>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
-          default: staged_down_loop<8>(g, stage_tiles, down_w, st_full, st_empty, lane); break;
+          case 2: staged_down_loop<2>(g, stage_tiles, down_w, lane); break;
+          case 4: staged_down_loop<4>(g, stage_tiles, down_w, lane); break;
+          case 5: staged_down_loop<5>(g, stage_tiles, down_w, lane); break;
+          default: staged_down_loop<8>(g, stage_tiles, down_w, lane); break;
         }
-      } else if (g.taps == 5) staged_math_dispatch<5>(g, stage_tiles, st_full, st_empty, lane);
-      else staged_math_dispatch<1>(g, stage_tiles, st_full, st_empty, lane);
+      } else if (g.taps == 5) staged_math_rows<5>(g, stage_tiles, lane);
+      else staged_math_rows<1>(g, stage_tiles, lane);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (16 warps)
@@ -688,10 +676,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint4* op = reinterpret_cast<uint4*>(g.out_raw + m * g.ldo + n);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  op[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
-                                     pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                     pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
-                                     pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+                  op[i] = make_uint4(pack_act2(f[8 * i], f[8 * i + 1]),
+                                     pack_act2(f[8 * i + 2], f[8 * i + 3]),
+                                     pack_act2(f[8 * i + 4], f[8 * i + 5]),
+                                     pack_act2(f[8 * i + 6], f[8 * i + 7]));
                 if (g.out_f32_t != nullptr) {
                   const long long b = m / g.f32_F, fr = m % g.f32_F;
                   float* tp = g.out_f32_t + (b * g.N + n) * g.f32_F + fr;
@@ -713,21 +701,21 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
                 y[i] = (0.5f * __logf(fmaxf(re * re + im * im, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
               }
-              __nv_bfloat16* yp = g.out_raw + m * g.ldo;
+              act_t* yp = g.out_raw + m * g.ldo;
               if (p0 == 0) {
                 const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
                 y[0] = (0.5f * __logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
                 const float yn = (0.5f * __logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
                 // bin N/2 plus the 7 zero pad columns (ldo = n_half + 8): one 16-byte store
-                *reinterpret_cast<uint4*>(yp + g.n_half) = make_uint4(pack_bf16x2(yn, 0.f), 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(yp + g.n_half) = make_uint4(pack_act2(yn, 0.f), 0u, 0u, 0u);
               }
               uint4* op = reinterpret_cast<uint4*>(yp + p0);
 #pragma unroll
               for (int i = 0; i < 2; ++i)
-                op[i] = make_uint4(pack_bf16x2(y[8 * i], y[8 * i + 1]),
-                                   pack_bf16x2(y[8 * i + 2], y[8 * i + 3]),
-                                   pack_bf16x2(y[8 * i + 4], y[8 * i + 5]),
-                                   pack_bf16x2(y[8 * i + 6], y[8 * i + 7]));
+                op[i] = make_uint4(pack_act2(y[8 * i], y[8 * i + 1]),
+                                   pack_act2(y[8 * i + 2], y[8 * i + 3]),
+                                   pack_act2(y[8 * i + 4], y[8 * i + 5]),
+                                   pack_act2(y[8 * i + 6], y[8 * i + 7]));
             }
           }
         } else {  // EPI_HEAD

@@ -1,4 +1,4 @@
-// Memory-bound kernels around the GEMMs.  Activations are channels-last bf16 [B, T, C]; every
+// Memory-bound kernels around the GEMMs.  Activations are channels-last fp16 [B, T, C]; every
 // thread owns 8 consecutive channels (one 128-bit vector) so a warp reads/writes whole rows
 // coalesced.  Depthwise weights are stored tap-major fp32 [k][C] for the same reason.
 #pragma once
@@ -10,19 +10,19 @@ struct F8 {
   float v[8];
 };
 // (elu1 comes from ptx_sm100.cuh)
-__device__ __forceinline__ F8 ld_bf16x8(const __nv_bfloat16* p) {   // activations: L2-coherent load
+__device__ __forceinline__ F8 ld_act8(const act_t* p) {   // activations: L2-coherent load
   const uint4 u = __ldcg(reinterpret_cast<const uint4*>(p));
   F8 r;
-  unpack_bf16x2(u.x, r.v[0], r.v[1]);
-  unpack_bf16x2(u.y, r.v[2], r.v[3]);
-  unpack_bf16x2(u.z, r.v[4], r.v[5]);
-  unpack_bf16x2(u.w, r.v[6], r.v[7]);
+  unpack_act2(u.x, r.v[0], r.v[1]);
+  unpack_act2(u.y, r.v[2], r.v[3]);
+  unpack_act2(u.z, r.v[4], r.v[5]);
+  unpack_act2(u.w, r.v[6], r.v[7]);
   return r;
 }
-__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const F8& r) {
+__device__ __forceinline__ void st_act8(act_t* p, const F8& r) {
   *reinterpret_cast<uint4*>(p) =
-      make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
-                 pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7]));
+      make_uint4(pack_act2(r.v[0], r.v[1]), pack_act2(r.v[2], r.v[3]),
+                 pack_act2(r.v[4], r.v[5]), pack_act2(r.v[6], r.v[7]));
 }
 __device__ __forceinline__ F8 ld_f32x8(const float* p) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -41,9 +41,9 @@ __device__ __forceinline__ F8 ld_f32x8(const float* p) {
 constexpr int DW_TT = 8;  // consecutive time steps per thread (sliding window in registers)
 
 __global__ void __launch_bounds__(256)
-dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-           const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-           __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
+dw5_kernel(const act_t* __restrict__ in, const float* __restrict__ w,
+           const float* __restrict__ bias, const act_t* __restrict__ residual,
+           act_t* __restrict__ out_raw, act_t* __restrict__ out_act,
            float act_scale, int B, int T, int C) {
   pdl_wait();
   pdl_launch_dependents();
@@ -67,12 +67,12 @@ dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 #pragma unroll
       for (int i = 0; i < 8; ++i) bs.v[i] = 0.f;
     }
-    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * T) * C + c;
+    const act_t* ip = in + (static_cast<long long>(b) * T) * C + c;
     F8 win[5];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int t = t0 - 4 + j;
-      if (t >= 0) win[j + 1] = ld_bf16x8(ip + static_cast<long long>(t) * C);
+      if (t >= 0) win[j + 1] = ld_act8(ip + static_cast<long long>(t) * C);
       else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) win[j + 1].v[i] = 0.f;
@@ -84,7 +84,7 @@ dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
       if (t >= T) break;
 #pragma unroll
       for (int j = 0; j < 4; ++j) win[j] = win[j + 1];
-      win[4] = ld_bf16x8(ip + static_cast<long long>(t) * C);
+      win[4] = ld_act8(ip + static_cast<long long>(t) * C);
       F8 o = bs;
 #pragma unroll
       for (int j = 0; j < 5; ++j)
@@ -92,15 +92,15 @@ dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
         for (int i = 0; i < 8; ++i) o.v[i] = fmaf(wt[j].v[i], win[j].v[i], o.v[i]);
       const long long off = (static_cast<long long>(b) * T + t) * C + c;
       if (residual != nullptr) {
-        const F8 rs = ld_bf16x8(residual + off);
+        const F8 rs = ld_act8(residual + off);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o.v[i] += rs.v[i];
       }
-      if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+      if (out_raw != nullptr) st_act8(out_raw + off, o);
       if (out_act != nullptr) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o.v[i] = elu1(o.v[i] * act_scale);
-        st_bf16x8(out_act + off, o);
+        st_act8(out_act + off, o);
       }
     }
   }
@@ -112,9 +112,9 @@ dw5_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 //   v[i,c] = bias[c] + sum_{j<2r} w[j][c] * in[i*r - r + j, c];  v = v*gamma[b,band] + beta
 template <int R>
 __global__ void __launch_bounds__(256)
-down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+down_kernel(const act_t* __restrict__ in, const float* __restrict__ w,
             const float* __restrict__ bias, const float* __restrict__ film, int film_stride,
-            int bands, __nv_bfloat16* __restrict__ out_raw, __nv_bfloat16* __restrict__ out_act,
+            int bands, act_t* __restrict__ out_raw, act_t* __restrict__ out_act,
             float act_scale, int B, int Tin, int Tout, int C) {
   pdl_wait();
   pdl_launch_dependents();
@@ -127,7 +127,7 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     const int i = static_cast<int>(rr % Tout);
     const int b = static_cast<int>(rr / Tout);
     const int c = cg * 8;
-    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * Tin) * C + c;
+    const act_t* ip = in + (static_cast<long long>(b) * Tin) * C + c;
     const int tb = i * R - R;
     uint4 xv[2 * R];                       // all 2R window rows in flight before any math
 #pragma unroll
@@ -146,10 +146,10 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     for (int j = 0; j < 2 * R; ++j) {
       const F8 wj = ld_f32x8(w + j * C + c);
       float x[8];
-      unpack_bf16x2(xv[j].x, x[0], x[1]);
-      unpack_bf16x2(xv[j].y, x[2], x[3]);
-      unpack_bf16x2(xv[j].z, x[4], x[5]);
-      unpack_bf16x2(xv[j].w, x[6], x[7]);
+      unpack_act2(xv[j].x, x[0], x[1]);
+      unpack_act2(xv[j].y, x[2], x[3]);
+      unpack_act2(xv[j].z, x[4], x[5]);
+      unpack_act2(xv[j].w, x[6], x[7]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wj.v[k], x[k], o.v[k]);
     }
@@ -161,11 +161,11 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
       for (int k = 0; k < 8; ++k) o.v[k] = fmaf(o.v[k], gm, bt);
     }
     const long long off = (static_cast<long long>(b) * Tout + i) * C + c;
-    if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+    if (out_raw != nullptr) st_act8(out_raw + off, o);
     if (out_act != nullptr) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = elu1(o.v[k] * act_scale);
-      st_bf16x8(out_act + off, o);
+      st_act8(out_act + off, o);
     }
   }
 }
@@ -174,8 +174,8 @@ down_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 // Causal depthwise transposed conv k=2r, s=r, right-trim r (modules/conv.py:838-874):
 //   out[i*r + j, c] = a[i,c]*w[j][c] + a[i-1,c]*w[j+r][c],  0 <= j < r,  a[-1] = 0
 __global__ void __launch_bounds__(256)
-up_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-          __nv_bfloat16* __restrict__ out, int B, int Tin, int C, int r) {
+up_kernel(const act_t* __restrict__ in, const float* __restrict__ w,
+          act_t* __restrict__ out, int B, int Tin, int C, int r) {
   pdl_wait();
   pdl_launch_dependents();
   const int C8 = C >> 3;
@@ -187,22 +187,22 @@ up_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     const int i = static_cast<int>(rr % Tin);
     const int b = static_cast<int>(rr / Tin);
     const int c = cg * 8;
-    const __nv_bfloat16* ip = in + (static_cast<long long>(b) * Tin + i) * C + c;
-    const F8 a0 = ld_bf16x8(ip);
+    const act_t* ip = in + (static_cast<long long>(b) * Tin + i) * C + c;
+    const F8 a0 = ld_act8(ip);
     F8 a1;
-    if (i > 0) a1 = ld_bf16x8(ip - C);
+    if (i > 0) a1 = ld_act8(ip - C);
     else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) a1.v[k] = 0.f;
     }
-    __nv_bfloat16* op = out + (static_cast<long long>(b) * Tin * r + static_cast<long long>(i) * r) * C + c;
+    act_t* op = out + (static_cast<long long>(b) * Tin * r + static_cast<long long>(i) * r) * C + c;
     for (int j = 0; j < r; ++j) {
       const F8 w0 = ld_f32x8(w + j * C + c);
       const F8 w1 = ld_f32x8(w + (j + r) * C + c);
       F8 o;
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = fmaf(a0.v[k], w0.v[k], a1.v[k] * w1.v[k]);
-      st_bf16x8(op + static_cast<long long>(j) * C, o);
+      st_act8(op + static_cast<long long>(j) * C, o);
     }
   }
 }
@@ -213,8 +213,8 @@ up_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 constexpr int PRE_TT = 4;   // consecutive time steps per thread (taps loaded once)
 __global__ void __launch_bounds__(256)
 conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                const float* __restrict__ bias, __nv_bfloat16* __restrict__ out_raw,
-                __nv_bfloat16* __restrict__ out_act, float act_scale, int B, int T, int C) {
+                const float* __restrict__ bias, act_t* __restrict__ out_raw,
+                act_t* __restrict__ out_act, float act_scale, int B, int T, int C) {
   pdl_wait();
   pdl_launch_dependents();
   const int C8 = C >> 3;
@@ -248,11 +248,11 @@ conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] = fmaf(wt[j].v[k], xs[s + j], o.v[k]);
       const long long off = (static_cast<long long>(b) * T + t) * C + c;
-      if (out_raw != nullptr) st_bf16x8(out_raw + off, o);
+      if (out_raw != nullptr) st_act8(out_raw + off, o);
       if (out_act != nullptr) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] = elu1(o.v[k] * act_scale);
-        st_bf16x8(out_act + off, o);
+        st_act8(out_act + off, o);
       }
     }
   }
@@ -267,7 +267,7 @@ conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
 // padded row pitch so that the 16-byte reads of consecutive rows hit distinct bank groups.
 constexpr int CL_TILE = 128;
 __global__ void __launch_bounds__(CL_TILE)
-conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, float bias,
+conv_last_kernel(const act_t* __restrict__ in, const float* __restrict__ w, float bias,
                  const float* __restrict__ x, float* __restrict__ wm_out,
                  float* __restrict__ y_out, int B, int Tp, int T, int C) {
   pdl_wait();
@@ -298,10 +298,10 @@ conv_last_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
     for (int cg = 0; cg < C8; ++cg) {
       const uint4 u = *reinterpret_cast<const uint4*>(rp + cg * 16);
       float a[8];
-      unpack_bf16x2(u.x, a[0], a[1]);
-      unpack_bf16x2(u.y, a[2], a[3]);
-      unpack_bf16x2(u.z, a[4], a[5]);
-      unpack_bf16x2(u.w, a[6], a[7]);
+      unpack_act2(u.x, a[0], a[1]);
+      unpack_act2(u.y, a[2], a[3]);
+      unpack_act2(u.z, a[4], a[5]);
+      unpack_act2(u.w, a[6], a[7]);
       const float* wp = ws + j * C + cg * 8;
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc = fmaf(a[k], wp[k], acc);
@@ -487,8 +487,8 @@ metrics_kernel(const uint8_t* __restrict__ bits, const uint8_t* __restrict__ val
     atomicAdd(&counters[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x]));
 }
 
-// fp32 [B, C, F] -> bf16 [B, F, C] (Generator.decode entry, model/generator.py:334)
-__global__ void latent_in_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ out,
+// fp32 [B, C, F] -> fp16 [B, F, C] (Generator.decode entry, model/generator.py:334)
+__global__ void latent_in_kernel(const float* __restrict__ z, act_t* __restrict__ out,
                                  int B, int C, int F) {
   pdl_wait();
   pdl_launch_dependents();
@@ -499,7 +499,7 @@ __global__ void latent_in_kernel(const float* __restrict__ z, __nv_bfloat16* __r
     const long long rr = idx / C;
     const int f = static_cast<int>(rr % F);
     const int b = static_cast<int>(rr / F);
-    out[idx] = __float2bfloat16_rn(__ldcg(z + (static_cast<long long>(b) * C + c) * F + f));
+    out[idx] = __float2half_rn(__ldcg(z + (static_cast<long long>(b) * C + c) * F + f));
   }
 }
 

@@ -2,7 +2,6 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld) and the UMMA
 // shared-memory / instruction descriptors.  Hand-written; no CUTLASS.
 #pragma once
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -88,6 +87,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// L2 prefetch of a tensor box (no shared-memory destination, no completion tracking): used for the
+// residual tile, which the epilogue math warps read with ordinary loads a couple of tiles later.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -166,20 +172,42 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool fp16_in
 }
 
 // ---------------------------------------------------------------- small math helpers
-// ELU(alpha=1): x > 0 ? x : e^x - 1 with one MUFU.EX2 (abs error ~1e-7, far below a bf16 ulp)
+// Activations and GEMM weights are IEEE fp16 (11 significant bits; conversions saturate at
+// +-65504 instead of producing inf): the epilogues run on packed half2 pairs (HFMA2 / HMNMX2,
+// two channels per instruction) with no unpacking, and the tensor cores take fp16 operands at the
+// bf16 rate with fp32 accumulation.
+typedef __half act_t;
+
+// ELU(alpha=1): x > 0 ? x : e^x - 1 with one MUFU.EX2 (abs error ~1e-7, far below an fp16 ulp)
 __device__ __forceinline__ float elu1(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
   return x > 0.f ? x : e - 1.f;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+__device__ __forceinline__ uint32_t pack_act2(float a, float b) {   // {lo = a, hi = b}, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
-__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& a, float& b) {
-  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
-  a = __bfloat162float(h.x);
-  b = __bfloat162float(h.y);
+__device__ __forceinline__ void unpack_act2(uint32_t u, float& a, float& b) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+  a = f.x;
+  b = f.y;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 h2_from(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+
+// ELU on a half2 pair:  max(x, min(2^(x*log2 e) - 1, 0)).  e^x - 1 >= x everywhere, so the outer max
+// selects the exponential branch exactly when x <= 0; the inner min discards it (and its overflow to
+// +inf) for x > 0.  MUFU.EX2.F16 has ~2^-10 relative error on e^x, i.e. <= 1e-3 absolute on the
+// (-1, 0] branch; the identity branch is exact.
+__device__ __forceinline__ __half2 elu_h2(__half2 x) {
+  const __half2 t = __hmul2(x, h2_from(1.4426950408889634f, 1.4426950408889634f));
+  uint32_t e;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(as_u32(t)));
+  const __half2 m = __hadd2(as_h2(e), h2_from(-1.f, -1.f));
+  return __hmax2(x, __hmin2(m, h2_from(0.f, 0.f)));
 }
 
 }  // namespace wv

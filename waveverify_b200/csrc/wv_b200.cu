@@ -23,7 +23,7 @@
 namespace {
 
 using namespace wv;
-typedef __nv_bfloat16 bf16;
+typedef act_t h16;   // fp16 activations / weights (ptx_sm100.cuh)
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) {
@@ -71,7 +71,8 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 16-bit tensor map over (k, row, clip): element strides in ELEMENTS for row / clip.
 CUtensorMap make_tmap(const void* base, int rank, uint64_t dim_k, uint64_t dim_row, uint64_t dim_clip,
-                      uint64_t row_stride, uint64_t clip_stride, int box_k, int box_row, bool fp16) {
+                      uint64_t row_stride, uint64_t clip_stride, int box_k, int box_row, bool /*fp16*/,
+                      bool swizzle = true) {
   CUtensorMap m;
   cuuint64_t dims[3] = {dim_k, dim_row, dim_clip};
   cuuint64_t strides[2] = {row_stride * 2, clip_stride * 2};
@@ -81,9 +82,9 @@ CUtensorMap make_tmap(const void* base, int rank, uint64_t dim_k, uint64_t dim_r
     WV_THROW(WV_ERR_INVALID, "TMA alignment violated (base %p, strides %llu %llu)", base,
              (unsigned long long)strides[0], (unsigned long long)strides[1]);
   CUresult r = get_encode_fn()(
-      &m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+      &m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,   // every 16-bit tensor of the path is fp16
       const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) WV_THROW(WV_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
   return m;
@@ -97,7 +98,8 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
-bool g_pdl = true;   // programmatic dependent launch for every plan kernel (WV_PDL=0 disables)
+bool g_pdl = false;  // programmatic dependent launch for every plan kernel (WV_PDL=1 enables; measured
+                     // 1-2 % slower on the 64-clip batch, where launch gaps are already hidden)
 void init_device_once() {
   static bool done = false;
   if (done) return;
@@ -153,7 +155,7 @@ struct GemmW {          // B operand of a GEMM: 16-bit [N, ldw] K-major, zero pa
   void* w = nullptr;
   float* bias = nullptr;
   int N = 0, K = 0, ldw = 0, block_n = 0;
-  bool fp16 = false;
+  bool fp16 = true;
   CUtensorMap tm;
 };
 struct DwW {            // depthwise taps fp32 [k][C]
@@ -168,7 +170,7 @@ struct ResW {
 };
 struct SpecW {
   GemmW dft;             // fp16 [n_fft, n_fft] (re,im) interleaved rows
-  GemmW layer;           // bf16 [C, n_fft/2+1] * RS * scale_param
+  GemmW layer;           // h16 [C, n_fft/2+1] * RS * scale_param
   int n_fft, hop;
   float mean, stdv;
 };
@@ -228,12 +230,6 @@ struct Weights {
   }
 };
 
-uint16_t f2bf(float f) {
-  __nv_bfloat16 h = __float2bfloat16_rn(f);
-  uint16_t u;
-  memcpy(&u, &h, 2);
-  return u;
-}
 uint16_t f2h(float f) {
   __half h = __float2half_rn(f);
   uint16_t u;
@@ -245,14 +241,17 @@ uint16_t f2h(float f) {
 GemmW make_gemm_w(Weights& W, const std::vector<float>& rows, int N, int K, bool fp16, int block_n,
                   const float* bias, int n_bias) {
   GemmW g;
+  fp16 = true;   // activations and weights are fp16 throughout (bf16 packing is no longer used)
   g.N = N; g.K = K; g.fp16 = fp16;
+  for (float v : rows)
+    if (!(std::fabs(v) <= 65504.f)) WV_THROW(WV_ERR_UNSUPPORTED, "weight %g does not fit fp16", v);
   g.ldw = static_cast<int>(round_up(K, 8));
   g.block_n = block_n;
   std::vector<uint16_t> h(static_cast<size_t>(N) * g.ldw, 0);
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k)
       h[static_cast<size_t>(n) * g.ldw + k] =
-          fp16 ? f2h(rows[static_cast<size_t>(n) * K + k]) : f2bf(rows[static_cast<size_t>(n) * K + k]);
+          f2h(rows[static_cast<size_t>(n) * K + k]);
   g.w = W.dev.upload(h);
   if (bias) g.bias = W.dev.upload(std::vector<float>(bias, bias + n_bias));
   g.tm = make_tmap(g.w, 2, g.ldw, N, 1, g.ldw, 0, BK, block_n, fp16);   // padded K (zeros)
@@ -404,7 +403,7 @@ struct Op {
   OpType type;
   // GEMM
   int epi = 0;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmR;   // tmR: residual tile view for the L2 prefetch (else a copy of tmB)
   GemmArgs g;
   int grid = 0;
   // generic
@@ -429,7 +428,7 @@ struct Plan {
   std::vector<Op> ops;
   std::vector<cudaEvent_t> events;   // profiling: ops.size() + 1 events
   size_t ws_bytes = 0;
-  Buf latent;          // bf16 [B*F, dim]
+  Buf latent;          // h16 [B*F, dim]
   int F = 0;
 };
 
@@ -496,6 +495,10 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     if (!c.dry()) op.tmA = make_tmap(A, 3, K, M, 1, lda, static_cast<uint64_t>(lda) * M, BK, BM, w.fp16);
   }
   op.tmB = w.tm;
+  op.tmR = w.tm;
+  if (staged && g.residual != nullptr && !c.dry())   // residual shares the output's [clip, row, ldo] layout
+    op.tmR = make_tmap(g.residual, 3, g.ldo, g.rows_per_clip, g.n_clips, g.ldo,
+                       static_cast<uint64_t>(g.ldo) * g.rows_per_clip, w.block_n, BM, false, false);
   op.g = g;
   op.out0 = g.out_raw;
   op.out1 = g.out_act;
@@ -539,7 +542,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   c.push(op);
 }
 
-GemmArgs std_args(const float* bias, const bf16* res, bf16* out_raw, bf16* out_act, float act_scale, int ldo) {
+GemmArgs std_args(const float* bias, const h16* res, h16* out_raw, h16* out_act, float act_scale, int ldo) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.bias = bias; g.residual = res; g.out_raw = out_raw; g.out_act = out_act;
@@ -548,7 +551,7 @@ GemmArgs std_args(const float* bias, const bf16* res, bf16* out_raw, bf16* out_a
   return g;
 }
 
-void add_dw5(PlanCtx& c, const DwW& w, const bf16* in, const bf16* res, bf16* out_raw, bf16* out_act,
+void add_dw5(PlanCtx& c, const DwW& w, const h16* in, const h16* res, h16* out_raw, h16* out_act,
              float act_scale, int T, int C) {
   Op op;
   op.type = OP_DW5;
@@ -567,8 +570,8 @@ void add_dw5(PlanCtx& c, const DwW& w, const bf16* in, const bf16* res, bf16* ou
 
 // 1x1 conv (tcgen05 GEMM) with the following causal depthwise k=5 conv fused into its epilogue:
 // per-clip overlapping tiles (128 rows in, 124 out).  A is [B, T, K] channels-last.
-void add_gemm_dw(PlanCtx& c, const GemmW& pw, const DwW& dw, const bf16* A, int T, int K, const bf16* res,
-                 bf16* out_raw, bf16* out_act, float act_scale) {
+void add_gemm_dw(PlanCtx& c, const GemmW& pw, const DwW& dw, const h16* A, int T, int K, const h16* res,
+                 h16* out_raw, h16* out_act, float act_scale) {
   if (dw.k != 5 || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused depthwise conv must be k=5 over the GEMM's N");
   GemmArgs g = std_args(dw.bias, res, out_raw, out_act, act_scale, pw.N);
   g.taps = 5;
@@ -584,8 +587,8 @@ void add_gemm_dw(PlanCtx& c, const GemmW& pw, const DwW& dw, const bf16* A, int 
 
 // Encoder downsample (modules/seanet.py:745-771): 1x1 conv C -> 2C (tcgen05 GEMM) with the strided
 // depthwise conv k=2r, s=r, its bias and the FiLM affine fused into the epilogue.  A = [B, T, K].
-void add_gemm_down(PlanCtx& c, const GemmW& pw, const DwW& dw, int r, const bf16* A, int T, int K, const float* film,
-                   int film_stride, int bands, bf16* out_raw, bf16* out_act, float act_scale) {
+void add_gemm_down(PlanCtx& c, const GemmW& pw, const DwW& dw, int r, const h16* A, int T, int K, const float* film,
+                   int film_stride, int bands, h16* out_raw, h16* out_act, float act_scale) {
   if (dw.k != 2 * r || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused down-conv must be k=2r over the GEMM's N");
   if (r != 2 && r != 4 && r != 5 && r != 8) WV_THROW(WV_ERR_UNSUPPORTED, "fused down-conv stride %d (2, 4, 5, 8)", r);
   GemmArgs g = std_args(dw.bias, nullptr, out_raw, out_act, act_scale, pw.N);
@@ -610,15 +613,15 @@ void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool
   // half 1: A2 = ELU(dw5(W1 * A) + b1)
   Buf A2 = c.alloc(bytes);
   c.tag(name + ".h1");
-  add_gemm_dw(c, r.pw1, r.dw1, c.ptr<bf16>(A), T, C, nullptr, nullptr, c.ptr<bf16>(A2), 1.f);
+  add_gemm_dw(c, r.pw1, r.dw1, c.ptr<h16>(A), T, C, nullptr, nullptr, c.ptr<h16>(A2), 1.f);
   c.release(A);
   // half 2: Xn = RS*(dw5(W2 * A2) + b2) + X ; An = ELU(Xn * next_scale)   (RS folded into dw2)
   Xn = Buf(); An = Buf();
   if (need_raw) Xn = c.alloc(bytes);
   if (need_act) An = c.alloc(bytes);
   c.tag(name + ".out");
-  add_gemm_dw(c, r.pw2, r.dw2, c.ptr<bf16>(A2), T, C, c.ptr<bf16>(X), need_raw ? c.ptr<bf16>(Xn) : nullptr,
-              need_act ? c.ptr<bf16>(An) : nullptr, next_act_scale);
+  add_gemm_dw(c, r.pw2, r.dw2, c.ptr<h16>(A2), T, C, c.ptr<h16>(X), need_raw ? c.ptr<h16>(Xn) : nullptr,
+              need_act ? c.ptr<h16>(An) : nullptr, next_act_scale);
   c.release(A2);
   c.release(X);
 }
@@ -807,7 +810,7 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
   Buf Y = c.alloc(static_cast<size_t>(M) * ldy * 2);
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  g.out_raw = c.ptr<bf16>(Y);
+  g.out_raw = c.ptr<h16>(Y);
   g.ldo = ldy;
   g.log_offset = s.mean + std::log(WAV_FP16_SCALE);
   g.inv_sigma = 1.f / s.stdv;
@@ -839,13 +842,13 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
   c.tag(name + ".out");
   // contraction over the padded width ldy (pad columns of Y and of the weights are zero): a TMA
   // inner extent of 33/65/.. elements is not a multiple of 16 B and loads slowly
-  add_gemm(c, EPI_STAGED, s.layer, c.ptr<bf16>(Y), ldy, M, ldy,
-           std_args(nullptr, c.ptr<bf16>(X), nullptr, c.ptr<bf16>(Aout), act_scale, C));
+  add_gemm(c, EPI_STAGED, s.layer, c.ptr<h16>(Y), ldy, M, ldy,
+           std_args(nullptr, c.ptr<h16>(X), nullptr, c.ptr<h16>(Aout), act_scale, C));
   c.release(Y);
   c.release(X);
 }
 
-// SEANetEncoder.forward (modules/seanet.py:883-976).  Leaves the latent bf16 [B*F, dim].
+// SEANetEncoder.forward (modules/seanet.py:883-976).  Leaves the latent h16 [B*F, dim].
 void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
   const EncoderW& e = n.enc;
   const int B = c.B, T = c.T;
@@ -881,7 +884,7 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
   {
     Op op;
     op.type = OP_CONV_PRE;
-    op.out0 = c.ptr<bf16>(X); op.out1 = c.ptr<bf16>(A);
+    op.out0 = c.ptr<h16>(X); op.out1 = c.ptr<h16>(A);
     op.w = e.conv_pre.w; op.bias = e.conv_pre.bias;
     op.fa = e.stages[0].res[0].pre_scale;
     op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
@@ -911,9 +914,9 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     X = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2);
     if (!last_stage) A = c.alloc(static_cast<size_t>(B) * To * 2 * C * 2); else A = Buf();
     c.tag("enc.s" + std::to_string(s) + ".down");
-    add_gemm_down(c, st.down_pw, st.down_dw, st.r, c.ptr<bf16>(Ain), Ts, C,
+    add_gemm_down(c, st.down_pw, st.down_dw, st.r, c.ptr<h16>(Ain), Ts, C,
                   e.has_film ? c.ptr<float>(film) + static_cast<size_t>(s) * e.bands * 2 : nullptr, e.n_film * 2, e.bands,
-                  c.ptr<bf16>(X), last_stage ? nullptr : c.ptr<bf16>(A),
+                  c.ptr<h16>(X), last_stage ? nullptr : c.ptr<h16>(A),
                   last_stage ? 1.f : e.stages[s + 1].res[0].pre_scale);
     c.release(Ain);
     Ts = To; C *= 2;
@@ -925,14 +928,14 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
   const long long M = static_cast<long long>(B) * Ts;
   Buf D = c.alloc(static_cast<size_t>(M) * C * 2);
   c.tag("enc.post.dw");
-  add_dw5(c, e.post_dw, c.ptr<bf16>(A), nullptr, c.ptr<bf16>(D), nullptr, 1.f, Ts, C);
+  add_dw5(c, e.post_dw, c.ptr<h16>(A), nullptr, c.ptr<h16>(D), nullptr, 1.f, Ts, C);
   c.release(A);
   plan.latent = c.alloc(static_cast<size_t>(M) * e.dim * 2);
-  GemmArgs g = std_args(e.post_pw.bias, nullptr, c.ptr<bf16>(plan.latent), nullptr, 1.f, e.dim);
+  GemmArgs g = std_args(e.post_pw.bias, nullptr, c.ptr<h16>(plan.latent), nullptr, 1.f, e.dim);
   g.l2_scale = std::sqrt(static_cast<float>(e.dim));                         // seanet.py:299
   g.f32_F = Ts;
   c.tag("enc.latent");
-  add_gemm(c, EPI_L2NORM, e.post_pw, c.ptr<bf16>(D), C, M, C, g);
+  add_gemm(c, EPI_L2NORM, e.post_pw, c.ptr<h16>(D), C, M, C, g);
   c.release(D);
 }
 
@@ -944,7 +947,7 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
   long long M = static_cast<long long>(B) * Ts;
   Buf A = c.alloc(static_cast<size_t>(M) * C * 2);
   c.tag("dec.in");
-  add_gemm_dw(c, d.pw0, d.dw0, c.ptr<bf16>(Z), Ts, d.pw0.K, nullptr, nullptr, c.ptr<bf16>(A), 1.f);   // ELU of stage 0
+  add_gemm_dw(c, d.pw0, d.dw0, c.ptr<h16>(Z), Ts, d.pw0.K, nullptr, nullptr, c.ptr<h16>(A), 1.f);   // ELU of stage 0
   for (size_t s = 0; s < d.stages.size(); ++s) {
     const DecStageW& st = d.stages[s];
     const int To = Ts * st.r;
@@ -952,7 +955,7 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     {
       Op op;
       op.type = OP_UP;
-      op.in = c.ptr<bf16>(A); op.out0 = c.ptr<bf16>(U); op.w = st.up.w;
+      op.in = c.ptr<h16>(A); op.out0 = c.ptr<h16>(U); op.w = st.up.w;
       op.i[0] = B; op.i[1] = Ts; op.i[2] = C; op.i[3] = st.r;
       op.grid = elem_grid(static_cast<long long>(B) * Ts * (C / 8));
       op.flops = 4.0 * B * To * C;
@@ -968,8 +971,8 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     Buf X = c.alloc(static_cast<size_t>(M) * Ch * 2);
     A = c.alloc(static_cast<size_t>(M) * Ch * 2);
     c.tag("dec.u" + std::to_string(s) + ".halve");
-    add_gemm(c, EPI_STAGED, st.halve, c.ptr<bf16>(U), C, M, C,
-             std_args(st.halve.bias, nullptr, c.ptr<bf16>(X), c.ptr<bf16>(A), st.res.empty() ? d.stage_scale : st.res[0].pre_scale, Ch));
+    add_gemm(c, EPI_STAGED, st.halve, c.ptr<h16>(U), C, M, C,
+             std_args(st.halve.bias, nullptr, c.ptr<h16>(X), c.ptr<h16>(A), st.res.empty() ? d.stage_scale : st.res[0].pre_scale, Ch));
     c.release(U);
     C = Ch;
     const int nres = static_cast<int>(st.res.size());
@@ -985,7 +988,7 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
   {
     Op op;
     op.type = OP_CONV_LAST;
-    op.in = c.ptr<bf16>(A); op.w = d.last_w; op.fa = d.last_b;
+    op.in = c.ptr<h16>(A); op.w = d.last_w; op.fa = d.last_b;
     op.i[0] = B; op.i[1] = Ts; op.i[2] = T_out; op.i[3] = C;
     op.grid = B * ceil_div(T_out, CL_TILE);
     op.flops = 2.0 * 5 * C * B * T_out;
@@ -1007,7 +1010,7 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   g.partial = c.ptr<float>(partial);
   g.hop = h.hop; g.T = c.T; g.n_out = h.n_out; g.head_F = F;
   c.tag("head.gemm");
-  add_gemm(c, EPI_HEAD, h.w, c.ptr<bf16>(Z), h.w.K, M, h.w.K, g);
+  add_gemm(c, EPI_HEAD, h.w, c.ptr<h16>(Z), h.w.K, M, h.w.K, g);
   {
     Op op;
     op.type = OP_BITS;
@@ -1073,7 +1076,7 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
     plan.latent = c.alloc(static_cast<size_t>(B) * F * n.enc.dim * 2);
     Op op;
     op.type = OP_LATENT_IN;
-    op.out0 = c.ptr<bf16>(plan.latent);
+    op.out0 = c.ptr<h16>(plan.latent);
     op.i[0] = B; op.i[1] = n.enc.dim; op.i[2] = F;
     op.grid = elem_grid(static_cast<long long>(B) * F * n.enc.dim);
     c.push(op);
@@ -1105,8 +1108,8 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
   CK(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
 }
 
-void launch_down(int grid, cudaStream_t st, const bf16* in, const float* w, const float* bias, const float* film,
-                 int film_stride, int bands, bf16* out_raw, bf16* out_act, float act_scale, int B, int Tin, int Tout,
+void launch_down(int grid, cudaStream_t st, const h16* in, const float* w, const float* bias, const float* film,
+                 int film_stride, int bands, h16* out_raw, h16* out_act, float act_scale, int B, int Tin, int Tout,
                  int C, int r) {
   switch (r) {
 #define WV_DOWN_CASE(R)                                                                                      \
@@ -1123,10 +1126,10 @@ void launch_down(int grid, cudaStream_t st, const bf16* in, const float* w, cons
 void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(op.i[7]);
   switch (op.epi) {
-    case EPI_STAGED: launch_k(gemm_sm100_kernel<EPI_STAGED>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
-    case EPI_L2NORM: launch_k(gemm_sm100_kernel<EPI_L2NORM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
-    case EPI_STFT: launch_k(gemm_sm100_kernel<EPI_STFT>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
-    default: launch_k(gemm_sm100_kernel<EPI_HEAD>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, g); break;
+    case EPI_STAGED: launch_k(gemm_sm100_kernel<EPI_STAGED>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    case EPI_L2NORM: launch_k(gemm_sm100_kernel<EPI_L2NORM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    case EPI_STFT: launch_k(gemm_sm100_kernel<EPI_STFT>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    default: launch_k(gemm_sm100_kernel<EPI_HEAD>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
   }
 }
 
@@ -1156,23 +1159,23 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         break;
       }
       case OP_DW5:
-        launch_k(dw5_kernel, op.grid, 256, 0, st, static_cast<const bf16*>(op.in), op.w, op.bias, static_cast<const bf16*>(op.res),
-                 static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        launch_k(dw5_kernel, op.grid, 256, 0, st, static_cast<const h16*>(op.in), op.w, op.bias, static_cast<const h16*>(op.res),
+                 static_cast<h16*>(op.out0), static_cast<h16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
         break;
       case OP_DOWN:
-        launch_down(op.grid, st, static_cast<const bf16*>(op.in), op.w, op.bias, op.film, op.i[5], op.i[6],
-                    static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]);
+        launch_down(op.grid, st, static_cast<const h16*>(op.in), op.w, op.bias, op.film, op.i[5], op.i[6],
+                    static_cast<h16*>(op.out0), static_cast<h16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4]);
         break;
       case OP_UP:
-        launch_k(up_kernel, op.grid, 256, 0, st, static_cast<const bf16*>(op.in), op.w, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3]);
+        launch_k(up_kernel, op.grid, 256, 0, st, static_cast<const h16*>(op.in), op.w, static_cast<h16*>(op.out0), op.i[0], op.i[1], op.i[2], op.i[3]);
         break;
       case OP_CONV_PRE:
-        launch_k(conv_pre_kernel, op.grid, 256, 0, st, io.x, op.w, op.bias, static_cast<bf16*>(op.out0), static_cast<bf16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        launch_k(conv_pre_kernel, op.grid, 256, 0, st, io.x, op.w, op.bias, static_cast<h16*>(op.out0), static_cast<h16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
         break;
       case OP_CONV_LAST: {
         const int C = op.i[3];
         const size_t smem = ((5 * C * 4 + 15) & ~15) + static_cast<size_t>(CL_TILE + 4) * (C * 2 + 16);
-        launch_k(conv_last_kernel, op.grid, CL_TILE, smem, st, static_cast<const bf16*>(op.in), op.w, op.fa, io.x, io.wm, io.y, op.i[0], op.i[1], op.i[2], C);
+        launch_k(conv_last_kernel, op.grid, CL_TILE, smem, st, static_cast<const h16*>(op.in), op.w, op.fa, io.x, io.wm, io.y, op.i[0], op.i[1], op.i[2], C);
         break;
       }
       case OP_WAV_STAGE:
@@ -1194,7 +1197,7 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         if (io.conf && io.avg) launch_k(conf_kernel, ceil_div(op.i[0], 128), 128, 0, st, io.avg, io.conf, op.i[0], op.i[1]);
         break;
       case OP_LATENT_IN:
-        launch_k(latent_in_kernel, op.grid, 256, 0, st, io.z_in, static_cast<bf16*>(op.out0), op.i[0], op.i[1], op.i[2]);
+        launch_k(latent_in_kernel, op.grid, 256, 0, st, io.z_in, static_cast<h16*>(op.out0), op.i[0], op.i[1], op.i[2]);
         break;
     }
     if (prof) CK(cudaEventRecord(plan.events[op_index + 1], st));
@@ -1474,7 +1477,7 @@ int wv_op_gemm(const void* A, int lda, const void* Wt, int ldw, int M, int N, in
   return guarded([&] {
     init_device_once();
     GemmW w;
-    w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = ldw; w.fp16 = a_is_fp16 != 0;
+    w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = ldw; w.fp16 = true; (void)a_is_fp16;
     w.block_n = pick_block_n(N, 0, STAGED_MAX_BN);
     w.tm = make_tmap(Wt, 2, K, N, 1, ldw, 0, BK, w.block_n, w.fp16);
     std::vector<Op> ops;
@@ -1482,7 +1485,7 @@ int wv_op_gemm(const void* A, int lda, const void* Wt, int ldw, int M, int N, in
     c.base = reinterpret_cast<uint8_t*>(16);   // non-null: encode tensor maps
     c.ops = &ops;
     add_gemm(c, EPI_STAGED, w, A, lda, M, K,
-             std_args(bias, static_cast<const bf16*>(residual), static_cast<bf16*>(out_raw), static_cast<bf16*>(out_act), act_scale, N));
+             std_args(bias, static_cast<const h16*>(residual), static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale, N));
     launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
     CK(cudaGetLastError());
   });
@@ -1493,7 +1496,7 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
   return guarded([&] {
     init_device_once();
     GemmW w;
-    w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = K; w.fp16 = false;
+    w.w = const_cast<void*>(Wt); w.N = N; w.K = K; w.ldw = K; w.fp16 = true;
     w.block_n = pick_block_n(N, 0, STAGED_MAX_BN);
     w.tm = make_tmap(Wt, 2, K, N, 1, K, 0, BK, w.block_n, false);
     DwW dw;
@@ -1503,8 +1506,27 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
     c.base = reinterpret_cast<uint8_t*>(16);
     c.ops = &ops;
     c.B = B;
-    add_gemm_dw(c, w, dw, static_cast<const bf16*>(A), T, K, static_cast<const bf16*>(residual),
-                static_cast<bf16*>(out_raw), static_cast<bf16*>(out_act), act_scale);
+    add_gemm_dw(c, w, dw, static_cast<const h16*>(A), T, K, static_cast<const h16*>(residual),
+                static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale);
+    if (getenv("WV_TIMELINE")) {   // per-tile clock probes of CTA 0 (scripts/microbench_scale.py --timeline)
+      long long* d = nullptr;
+      CK(cudaMalloc(&d, 48 * 8 * sizeof(long long)));
+      CK(cudaMemset(d, 0, 48 * 8 * sizeof(long long)));
+      ops[0].g.dbg = d;
+      launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> h(48 * 8);
+      CK(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      CK(cudaFree(d));
+      const long long t0 = h[0];
+      printf("tile: tma_issue  data_in  mma_commit  drain_start drain_end  math_start math_end   (cycles from first TMA)\n");
+      for (int i = 0; i < 40; ++i) {
+        printf("%3d:", i);
+        for (int k = 0; k < 7; ++k) printf(" %9lld", h[i * 8 + k] ? h[i * 8 + k] - t0 : -1);
+        printf("\n");
+      }
+      return;
+    }
     launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
     CK(cudaGetLastError());
   });
@@ -1515,8 +1537,8 @@ int wv_op_dw5(const void* in, const float* w5c, const float* bias, const void* r
   return guarded([&] {
     init_device_once();
     dw5_kernel<<<elem_grid(static_cast<long long>(B) * ceil_div(T, DW_TT) * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(in), w5c, bias, static_cast<const bf16*>(residual), static_cast<bf16*>(out_raw),
-        static_cast<bf16*>(out_act), act_scale, B, T, C);
+        static_cast<const h16*>(in), w5c, bias, static_cast<const h16*>(residual), static_cast<h16*>(out_raw),
+        static_cast<h16*>(out_act), act_scale, B, T, C);
     CK(cudaGetLastError());
   });
 }
@@ -1527,8 +1549,8 @@ int wv_op_down(const void* in, const float* wkc, const float* bias, const float*
     init_device_once();
     const int To = ceil_div(Tin, r);
     launch_down(elem_grid(static_cast<long long>(B) * To * (C / 8)), static_cast<cudaStream_t>(stream),
-                static_cast<const bf16*>(in), wkc, bias, film, film_stride, bands, static_cast<bf16*>(out_raw),
-                static_cast<bf16*>(out_act), act_scale, B, Tin, To, C, r);
+                static_cast<const h16*>(in), wkc, bias, film, film_stride, bands, static_cast<h16*>(out_raw),
+                static_cast<h16*>(out_act), act_scale, B, Tin, To, C, r);
     CK(cudaGetLastError());
   });
 }
@@ -1537,7 +1559,7 @@ int wv_op_up(const void* in, const float* wkc, void* out, int B, int Tin, int C,
   return guarded([&] {
     init_device_once();
     up_kernel<<<elem_grid(static_cast<long long>(B) * Tin * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(in), wkc, static_cast<bf16*>(out), B, Tin, C, r);
+        static_cast<const h16*>(in), wkc, static_cast<h16*>(out), B, Tin, C, r);
     CK(cudaGetLastError());
   });
 }

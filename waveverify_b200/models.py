@@ -174,7 +174,7 @@ class _B200Module(nn.Module):
                      flops=float(fl[i]), bytes=float(by[i])) for i in range(k)]
 
     @torch.no_grad()
-    def debug_tap(self, audio: torch.Tensor, msg, tag: str, which: int, shape, dtype=torch.bfloat16):
+    def debug_tap(self, audio: torch.Tensor, msg, tag: str, which: int, shape, dtype=torch.float16):
         """Run up to the launch tagged `tag` and return its output buffer (tests only)."""
         x = self._check_audio(audio)
         B, _, T = x.shape
