@@ -317,10 +317,15 @@ def run_ours(a):
             name, c = dom
             f_t = c["tflops"] / peaks["bf16_tflops_sustained"]
             f_h = c["gbs"] / peaks["hbm_gbs"]
+            # DRAM bytes per launch of this kernel from the committed ncu capture of the same step
+            # (profiles/ncu_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum), next to the
+            # algorithmic bytes per launch that `achieved` is computed from
             traffic = None
             tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-            if os.path.exists(tr):
-                traffic = json.load(open(tr)).get(name)
+            if os.path.exists(tr) and B == 64 and T == SR:
+                ent = json.load(open(tr)).get(name)
+                if isinstance(ent, dict) and ent.get("dram_bytes_per_launch"):
+                    traffic = ent["dram_bytes_per_launch"]
             if f_t >= f_h:
                 roofline = {"kernel": name, "bound": "tensor", "achieved": c["tflops"], "peak": peaks["bf16_tflops_sustained"],
                             "unit": "TFLOP/s", "frac": round(f_t, 4), "traffic": traffic}
@@ -330,6 +335,8 @@ def run_ours(a):
             roofline["peak_src"] = peaks["src"] + (" (sustained)" if roofline["bound"] == "tensor" else "")
             roofline["launches"] = c["launches"]
             roofline["avg_launch_us"] = round(1e3 * c["ms"] / max(1, c["launches"]), 2)
+            roofline["alg_bytes_per_launch"] = round(1e6 * c["mb"] / max(1, c["launches"]))
+            roofline["alg_gflop_per_launch"] = round(c["gflop"] / max(1, c["launches"]), 3)
             roofline["note"] = ("aggregate over all launches of this kernel in one step (profiled sub-batch x%d); "
                                 "achieved = algorithmic work / CUDA-event time" % n_sub)
         cpu = None

@@ -306,7 +306,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     const size_t base = (static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base) * g.ldo + c;
     const int rows_left = min(g.rows_per_clip - r_base, ROWS_OUT);   // valid output rows of this tile
     // The residual rows do not depend on the staged tile: those of the first unit are requested
-    // (L2-resident thanks to the producer's prefetch) before waiting for the drain warps, those of a
+    // before waiting for the drain warps, those of a
     // second unit before the first unit's math, so their latency overlaps the wait / the math.
     uint2 rres[R], rnext[R];
     auto load_res = [&](int ro, uint2 (&r)[R]) {
@@ -496,11 +496,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_kb = (g.K + BK - 1) / BK;
   const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
 
-  const bool has_res = EPI == EPI_STAGED && g.residual != nullptr;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (has_res) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
@@ -532,9 +530,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(), ++dbg_it) {
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
-        // The residual rows of this tile are read by the math warps (plain loads) two to three tiles
-        // from now: pull them into L2 alongside the A operand so that those loads do not wait on HBM.
-        if (has_res) tma_prefetch_l2_3d(&tmR, n0, tc.mi * rows_out, tc.clip);
+        // (An L2 prefetch of the tile's residual rows from here - cp.async.bulk.prefetch.tensor through
+        // tmR - was measured: +30 % DRAM reads on the residual kernels for no gain in time.)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (kb == 0) WV_DBG(0, dbg_it);

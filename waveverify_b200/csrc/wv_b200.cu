@@ -1007,11 +1007,11 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.bias = h.w.bias;
-  g.partial = c.ptr<float>(partial);
+  g.partial = n.cfg.kind == WV_KIND_DETECTOR ? c.ptr<float>(partial) : nullptr;
   g.hop = h.hop; g.T = c.T; g.n_out = h.n_out; g.head_F = F;
   c.tag("head.gemm");
   add_gemm(c, EPI_HEAD, h.w, c.ptr<h16>(Z), h.w.K, M, h.w.K, g);
-  {
+  if (n.cfg.kind == WV_KIND_DETECTOR) {   // bit decode exists for the detector only
     Op op;
     op.type = OP_BITS;
     op.in = c.ptr<float>(partial);
