@@ -366,10 +366,18 @@ def run_ours(a):
 
 def main():
     a = parse_args()
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version banner to stdout when
+    # NCCL_DEBUG is set) write to fd 1 behind Python's back, so fd 1 points at stderr while the bench
+    # runs and the real stdout is used for the result line alone.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
