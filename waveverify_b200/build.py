@@ -26,7 +26,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, SRC]
+    extra = ["-DWV_TIMELINE"] if os.environ.get("WV_TIMELINE_BUILD") else []   # scripts/timeline.py probes
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -36,14 +36,16 @@ namespace wv {
 
 // Per-tile clock probes of CTA 0 (scripts/timeline.py); compiled in only with -DWV_TIMELINE.
 #ifdef WV_TIMELINE
-#define WV_DBG(slot, it) do { if (g.dbg != nullptr && blockIdx.x == 0 && (it) < 48) g.dbg[(it) * 8 + (slot)] = clock64(); } while (0)
+#define WV_DBG_MODE(m) ((g.dbg_mode & (m)) != 0)   // bit 1: no global stores, 2: no units, 4: no drain
+#define WV_DBG(slot, it) do { if (g.dbg != nullptr && blockIdx.x == 0 && (it) < 48) g.dbg[(it) * 40 + (slot)] = clock64(); } while (0)
 #else
+#define WV_DBG_MODE(m) false
 #define WV_DBG(slot, it) do { } while (0)
 #endif
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int ACC_STAGES = 2;
@@ -65,7 +67,7 @@ constexpr int BAR_TAPS = 1;                // named barrier ids: 1 = down-conv t
 constexpr int BAR_ST_FULL = 2;             // 2,3 = staging tile written (drain arrive, math sync),
 constexpr int BAR_ST_EMPTY = 4;            // 4,5 = staging tile consumed (math arrive, drain sync)
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
-constexpr int GEMM_BAR_BYTES = 256;
+constexpr int GEMM_BAR_BYTES = 512;
 constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [2r <= 16][block_n] fp16
 
 enum { EPI_STAGED = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3 };
@@ -77,6 +79,7 @@ struct GemmArgs {
   int N, K;
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
+  int resident_b;     // 1: this CTA's W tile (all k-blocks) stays in shared memory; the ring carries A only
   uint32_t idesc;
   // tile -> (m tile, n tile, clip) without integer division (host computed)
   int tiles_n, tiles_m_per_clip, num_tiles;
@@ -110,17 +113,30 @@ struct GemmArgs {
   const uint8_t* presence;
   int hop, T, n_out, head_F;
   long long* dbg;   // timeline probe (profiling builds of scripts/microbench only), nullptr otherwise
+  int dbg_mode;     // -DWV_TIMELINE builds only: 1 = math warps skip global stores, 2 = skip the units, 3 = skip drain conversion+stores
 };
 
 __host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n * 2 + 16; }
-__host__ inline int gemm_stage_count(int block_n, bool staged) {
-  const int fixed = 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0);
-  int s = (GEMM_SMEM_LIMIT - fixed) / (A_STAGE_BYTES + block_n * BK * 2);
+// Shared-memory plan.  With resident_b the CTA's whole W tile (num_kb k-blocks) is loaded once and the
+// ring stages hold A k-blocks only (16 KB each): the ring then covers 4-5 tiles of loads in flight
+// instead of 3, which is what bounds the small-K layers (TMA issue -> data is ~8 000 cycles under load).
+__host__ inline int gemm_fixed_smem(int block_n, bool staged) {
+  return 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0);
+}
+__host__ inline bool gemm_resident_b(int block_n, int num_kb, bool staged, bool nt_fixed) {
+  const int w_bytes = num_kb * block_n * BK * 2;
+  return nt_fixed && w_bytes <= 64 * 1024 &&
+         (GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged) - w_bytes) / A_STAGE_BYTES >= 4;
+}
+__host__ inline int gemm_stage_count(int block_n, bool staged, int num_kb = 0, bool resident = false) {
+  const int avail = GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged);
+  int s = resident ? (avail - num_kb * block_n * BK * 2) / A_STAGE_BYTES : avail / (A_STAGE_BYTES + block_n * BK * 2);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
-__host__ inline int gemm_smem_bytes(int block_n, bool staged) {
-  return 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0) +
-         gemm_stage_count(block_n, staged) * (A_STAGE_BYTES + block_n * BK * 2);
+__host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bool resident = false) {
+  const int s = gemm_stage_count(block_n, staged, num_kb, resident);
+  return gemm_fixed_smem(block_n, staged) +
+         (resident ? s * A_STAGE_BYTES + num_kb * block_n * BK * 2 : s * (A_STAGE_BYTES + block_n * BK * 2));
 }
 
 // ELU(alpha=1): x > 0 ? x : e^x - 1 with one MUFU.EX2 (abs error ~1e-7, far below bf16 output ulp)
@@ -243,11 +259,12 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
       oh[i][1] = __hadd2(oh[i][1], as_h2(rres[i].y));
     }
   }
+  if (WV_DBG_MODE(1)) nrow = -1;
   if constexpr (RAW) {
     char* op = reinterpret_cast<char*>(g.out_raw + off);
 #pragma unroll
     for (int i = 0; i < R; ++i)
-      if (FULL || i < nrow)
+      if ((FULL && !WV_DBG_MODE(1)) || i < nrow)
         *reinterpret_cast<uint2*>(op + i * row_bytes) = make_uint2(as_u32(oh[i][0]), as_u32(oh[i][1]));
   }
   if constexpr (ACT) {
@@ -257,7 +274,7 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
     for (int i = 0; i < R; ++i) {
       const __half2 a0 = elu_h2(SCALE ? __hmul2(oh[i][0], s2) : oh[i][0]);
       const __half2 a1 = elu_h2(SCALE ? __hmul2(oh[i][1], s2) : oh[i][1]);
-      if (FULL || i < nrow)
+      if ((FULL && !WV_DBG_MODE(1)) || i < nrow)
         *reinterpret_cast<uint2*>(op + i * row_bytes) = make_uint2(as_u32(a0), as_u32(a1));
     }
   }
@@ -322,7 +339,9 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     }
     named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);                 // drain warps staged tile sb
     if (et == 0) WV_DBG(5, dbg_it);
+    if (lane == 0) WV_DBG(24 + (et >> 5), dbg_it);   // per math warp: start
     const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
+    if (WV_DBG_MODE(2)) have = false;
     while (have) {
       const int ro = grp * R;                                      // tile-relative output row
       const int gn = grp + gstride;
@@ -345,6 +364,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     }
     __syncwarp();
     if (et == 0) WV_DBG(6, dbg_it);
+    if (lane == 0) WV_DBG(12 + (et >> 5), dbg_it);   // per math warp: end
     ++dbg_it;
     if (--tiles_left >= STAGE_BUFS) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);   // tile sb may be refilled
     if (++sb == STAGE_BUFS) sb = 0;
@@ -477,13 +497,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int b_stage_bytes = g.block_n * BK * 2;
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + g.stages * A_STAGE_BYTES;
-  uint8_t* after = smemB + g.stages * b_stage_bytes;
+  const int num_kb = (g.K + BK - 1) / BK;
+  uint8_t* after = smemB + (g.resident_b ? num_kb : g.stages) * b_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   uint64_t* full = bars;                          // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
   uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [ACC_STAGES]
   uint64_t* acc_empty = acc_full + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  uint64_t* w_full = acc_empty + ACC_STAGES;      // resident W tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   uint8_t* down_w = after + GEMM_BAR_BYTES;       // [2r][block_n] fp32 (STAGED down-conv only)
   uint8_t* stage_tiles = down_w + DOWN_W_BYTES;   // [STAGE_BUFS][BM][pitch] fp16 (STAGED only)
 
@@ -493,8 +515,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // tile geometry (host computed): overlapping per-clip tiles carry the depthwise halo
   const int halo = g.tile_halo;
   const int rows_out = g.tile_stride;
-  const int num_kb = (g.K + BK - 1) / BK;
-  const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
+  const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + (g.resident_b ? 0 : b_stage_bytes));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -505,6 +526,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
+    mbar_init(w_full, 1);
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : EPI_WARPS);  // one arrive per draining warp
@@ -527,6 +549,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int dbg_it = 0;
+      if (g.resident_b) {   // the n tile of a CTA is fixed (grid is a multiple of tiles_n): load W once
+        const int n_fixed = tile_coord(g, blockIdx.x).nt * g.block_n;
+        mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(num_kb * b_stage_bytes));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smemB + kb * b_stage_bytes, &tmB, w_full, kb * BK, n_fixed);
+      }
       for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(), ++dbg_it) {
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
@@ -537,7 +564,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
           tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
-          tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
+          if (!g.resident_b) tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -551,6 +578,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int as = 0;
       uint32_t as_phase = 0;
       int dbg_it = 0;
+      if (g.resident_b) mbar_wait(w_full, 0);
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++dbg_it) {
         mbar_wait(&acc_empty[as], as_phase ^ 1);
         tc_fence_after();
@@ -560,7 +588,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == num_kb - 1) WV_DBG(1, dbg_it);
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * b_stage_bytes));
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + (g.resident_b ? kb : stage) * b_stage_bytes));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row -> +2 in the (addr>>4) field
@@ -589,11 +617,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (it >= STAGE_BUFS) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
         mbar_wait(&acc_full[as], as_phase);
         if (q == 0 && lane == 0) WV_DBG(3, it);
+        if (lane == 0) WV_DBG(36 + q, it);           // per drain warp: start
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
         const uint32_t rowp = stage_u32 + sb * (BM * pitch) + (q * 32 + lane) * pitch;
-        for (int c = 0; c < chunks; ++c) {
+        for (int c = 0; c < (WV_DBG_MODE(4) ? 0 : chunks); ++c) {
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
@@ -608,6 +637,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
         if (q == 0 && lane == 0) WV_DBG(4, it);
+        if (lane == 0) WV_DBG(8 + q, it);            // per drain warp: end
         named_bar_arrive(BAR_ST_FULL + sb, EPI_THREADS);   // release: this warp's 32 rows are staged
         if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
         if (++sb == STAGE_BUFS) sb = 0;

@@ -482,9 +482,14 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
   const bool staged = epi == EPI_STAGED;
   if (staged && g.taps != 1 && g.taps != 5) WV_THROW(WV_ERR_INVALID, "taps must be 1 or 5");
-  g.stages = gemm_stage_count(w.block_n, staged);
+  const int num_kb = ceil_div(K, BK);
+  const int tiles_n_ = w.N / w.block_n;
+  const bool nt_fixed = tiles_n_ <= g_num_sms;   // the grid is rounded down to a multiple of tiles_n below
+  const bool resident = gemm_resident_b(w.block_n, num_kb, staged, nt_fixed);
+  g.resident_b = resident ? 1 : 0;
+  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident);
   if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
-  op.i[7] = gemm_smem_bytes(w.block_n, staged);
+  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident);
   if (custom_tmA) {
     g.rows_per_clip = rows_per_clip;
     g.n_clips = n_clips;
@@ -525,6 +530,13 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.num_tiles = tiles;
   op.g = g;
   op.grid = std::min(tiles, g_num_sms);
+  if (g.resident_b && op.grid > g.tiles_n) op.grid -= op.grid % g.tiles_n;   // every CTA keeps one n tile
+  if (g.resident_b && op.grid < g.tiles_n) {   // fewer tiles than n tiles: stream W through the ring
+    g.resident_b = 0;
+    g.stages = gemm_stage_count(w.block_n, staged, num_kb, false);
+    op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false);
+    op.g = g;
+  }
   {
     const double Mt = static_cast<double>(g.rows_per_clip) * g.n_clips;
     op.flops = 2.0 * Mt * w.N * K;
@@ -1508,21 +1520,35 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
     c.B = B;
     add_gemm_dw(c, w, dw, static_cast<const h16*>(A), T, K, static_cast<const h16*>(residual),
                 static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale);
-    if (getenv("WV_TIMELINE")) {   // per-tile clock probes of CTA 0 (scripts/microbench_scale.py --timeline)
+    if (getenv("WV_TIMELINE") && atoi(getenv("WV_TIMELINE")) >= 10) {   // ablation timing: mode = value - 10, no probes
+      ops[0].g.dbg_mode = atoi(getenv("WV_TIMELINE")) - 10;
+      launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
+      CK(cudaGetLastError());
+      return;
+    }
+    if (getenv("WV_TIMELINE")) {   // per-tile clock probes of CTA 0 (scripts/timeline.py)
       long long* d = nullptr;
-      CK(cudaMalloc(&d, 48 * 8 * sizeof(long long)));
-      CK(cudaMemset(d, 0, 48 * 8 * sizeof(long long)));
+      CK(cudaMalloc(&d, 48 * 40 * sizeof(long long)));
+      CK(cudaMemset(d, 0, 48 * 40 * sizeof(long long)));
       ops[0].g.dbg = d;
       launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
       CK(cudaDeviceSynchronize());
-      std::vector<long long> h(48 * 8);
+      std::vector<long long> h(48 * 40);
       CK(cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       CK(cudaFree(d));
       const long long t0 = h[0];
       printf("tile: tma_issue  data_in  mma_commit  drain_start drain_end  math_start math_end   (cycles from first TMA)\n");
       for (int i = 0; i < 40; ++i) {
         printf("%3d:", i);
-        for (int k = 0; k < 7; ++k) printf(" %9lld", h[i * 8 + k] ? h[i * 8 + k] - t0 : -1);
+        for (int k = 0; k < 7; ++k) printf(" %9lld", h[i * 40 + k] ? h[i * 40 + k] - t0 : -1);
+        printf(" | drain start");
+        for (int k = 36; k < 40; ++k) printf(" %6lld", h[i * 40 + k] - t0);
+        printf(" end");
+        for (int k = 8; k < 12; ++k) printf(" %6lld", h[i * 40 + k] - t0);
+        printf(" | math start");
+        for (int k = 24; k < 36; ++k) printf(" %6lld", h[i * 40 + k] - t0);
+        printf(" end");
+        for (int k = 12; k < 24; ++k) printf(" %6lld", h[i * 40 + k] - t0);
         printf("\n");
       }
       return;
