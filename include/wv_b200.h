@@ -128,15 +128,21 @@ int wv_debug_tap(wv_net* net, const float* x, const float* msg, int B, int T, co
                  int which, void* dst, size_t dst_bytes, size_t* written);
 
 /* ---- single-kernel entry points (unit tests / micro-benchmarks; device pointers) -------- */
-/* out = epilogue(A[M,K] * W[N,K]^T): bf16 in, fp32 accumulate on tcgen05; see DESIGN.md. */
+/* out = epilogue(A[M,K] * W[N,K]^T): fp16 in, fp32 accumulate on tcgen05; see DESIGN.md. */
 int wv_op_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
                const float* bias, const void* residual, void* out_raw, void* out_act,
                float act_scale, int a_is_fp16, void* stream);
-/* A [B,T,K] bf16 -> 1x1 conv (W [N,K]) -> causal depthwise k=5 (dw_w5n [5][N], bias) fused in the
- * GEMM epilogue (+ residual [B,T,N]) -> out_raw / out_act = ELU(v*act_scale), each [B,T,N] bf16. */
+/* A [B,T,K] fp16 -> 1x1 conv (W [N,K]) -> causal depthwise k=5 (dw_w5n [5][N], bias) fused in the
+ * GEMM epilogue (+ residual [B,T,N]) -> out_raw / out_act = ELU(v*act_scale), each [B,T,N] fp16. */
 int wv_op_gemm_dw5(const void* A, const void* W, int B, int T, int N, int K, const float* dw_w5n,
                    const float* bias, const void* residual, void* out_raw, void* out_act,
                    float act_scale, void* stream);
+/* One fused SEANet residual block (modules/seanet.py:245-281), C <= 128, C % 32 == 0:
+ * x' = dw5(W2 ELU(dw5(W1 ELU(X*pre_scale)) + b1)) + b2 + X ; out_raw = x', out_act = ELU(x'*act_scale).
+ * X, out_* are [B,T,C] fp16; W1, W2 [C,C] fp16; taps [5][C], biases [C] fp32 (RS folded into dw2). */
+int wv_op_resblock(const void* X, const void* W1, const float* dw1_w5c, const float* dw1_b,
+                   const void* W2, const float* dw2_w5c, const float* dw2_b, int B, int T, int C,
+                   float pre_scale, void* out_raw, void* out_act, float act_scale, void* stream);
 int wv_op_dw5(const void* in, const float* w5c, const float* bias, const void* residual,
               void* out_raw, void* out_act, float act_scale, int B, int T, int C, void* stream);
 int wv_op_down(const void* in, const float* wkc, const float* bias, const float* film,

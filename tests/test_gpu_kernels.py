@@ -209,3 +209,45 @@ def test_gemm_with_fused_depthwise_epilogue(B, T, N, K, mode):
         ref = ref + R.float().cpu()
         bf16_close(out_raw.cpu(), ref, abs_=4e-3, mid=mid)
     bf16_close(out_act.cpu(), F.elu(ref * 0.75), abs_=4e-3, mid=mid)
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 1000, 64), (1, 120, 96), (3, 401, 96), (1, 7, 32), (2, 16000, 96), (5, 241, 64),
+                                   (1, 121, 128), (64, 2000, 32)])
+@pytest.mark.parametrize("mode", ["raw", "act", "both"])
+def test_fused_resblock(B, T, C, mode):
+    """One SEANet residual block (modules/seanet.py:245-281) as ONE kernel: the activation of x and
+    the intermediate h never leave shared memory; tiles of 128 rows with an 8-row causal halo (120
+    outputs), two tiles in flight per CTA."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(B * 131 + T * 7 + C)
+    X = torch.randn(B, T, C, generator=g).to(torch.float16)
+    W1 = (torch.randn(C, C, generator=g) / C ** 0.5).to(torch.float16)
+    W2 = (torch.randn(C, C, generator=g) / C ** 0.5).to(torch.float16)
+    dw1 = torch.randn(C, 1, 5, generator=g) * 0.4
+    dw2 = torch.randn(C, 1, 5, generator=g) * 0.3
+    b1 = torch.randn(C, generator=g) * 0.5
+    b2 = torch.randn(C, generator=g) * 0.5
+    pre, s_act = 0.866, 0.7071
+    out_raw = torch.full((B, T, C), float("nan"), dtype=torch.float16, device=dev) if mode != "act" else None
+    out_act = torch.full((B, T, C), float("nan"), dtype=torch.float16, device=dev) if mode != "raw" else None
+    k1 = dw1[:, 0, :].t().contiguous().to(dev); k2 = dw2[:, 0, :].t().contiguous().to(dev)
+    Xd, W1d, W2d, b1d, b2d = X.to(dev), W1.to(dev), W2.to(dev), b1.to(dev), b2.to(dev)   # keep every buffer alive
+    rc = _lib().wv_op_resblock(P(Xd), P(W1d), P(k1), P(b1d), P(W2d), P(k2), P(b2d), B, T, C, pre,
+                               P(out_raw), P(out_act), s_act, S())
+    assert rc == 0, _lib().wv_last_error()
+    torch.cuda.synchronize()
+
+    def dw5(u, w, b):
+        return F.conv1d(F.pad(u.transpose(1, 2), (4, 0)), w, b, groups=C).transpose(1, 2)
+
+    x = X.double()
+    a = F.elu(x * pre)
+    h = F.elu(dw5(a @ W1.double().t(), dw1.double(), b1.double()))
+    ref = (dw5(h @ W2.double().t(), dw2.double(), b2.double()) + x).float()
+    # error budget: fp16 rounding of a, of both staged GEMM tiles and of h, the half2 tap sums, and the
+    # <= 1e-3 absolute error of the half2 ELU on its exponential branch, pushed through |W2| and the taps
+    mag = (dw5((h.abs() @ W2.double().abs().t()), dw2.double().abs(), None)).float()
+    if out_raw is not None:
+        bf16_close(out_raw.cpu(), ref, rel=2 ** -9, abs_=6e-3, mid=mag * 0.5)
+    if out_act is not None:
+        bf16_close(out_act.cpu(), F.elu(ref * s_act), rel=2 ** -9, abs_=6e-3, mid=mag * 0.5)

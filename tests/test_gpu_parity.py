@@ -11,8 +11,9 @@ half2 epilogues; cf. BASELINE.md section 4 - PyTorch's own bf16 autocast of the 
   detector logits                        : SNR >= 52 dB, max-abs <= 0.08 ; avg prob max-abs <= 2e-4
   locator logits                         : SNR >= 52 dB, max-abs <= 0.08
   decoded bits                           : exact wherever |avg_ref - 0.5| > 3e-4 (guard band)
-  locator mask                           : exact wherever |logit_ref - 0.5| > 0.01; inside the
-                                           band at most 30 % of the in-band samples may differ
+  locator mask                           : exact wherever |logit_ref - 0.5| > 0.04 (half the logit
+                                           max-abs bound; observed mismatches sit within 0.004);
+                                           inside the band at most 30 % of the samples may differ
 """
 import os
 
@@ -55,7 +56,7 @@ def check_bits(avg_ref, bits_ref, avg, bits):
 
 
 def check_mask(logit_ref, mask_ref, mask):
-    safe = np.abs(logit_ref - 0.5) > 0.01
+    safe = np.abs(logit_ref - 0.5) > 0.04
     assert (mask == mask_ref)[safe].all(), "mask differs outside the guard band"
     band = ~safe
     if band.sum() > 50:

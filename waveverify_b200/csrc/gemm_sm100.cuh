@@ -79,6 +79,7 @@ struct GemmArgs {
   int N, K;
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
+  int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
   int resident_b;     // 1: this CTA's W tile (all k-blocks) stays in shared memory; the ring carries A only
   uint32_t idesc;
   // tile -> (m tile, n tile, clip) without integer division (host computed)
@@ -182,28 +183,22 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
   return t;
 }
 
-// Walks tile = blockIdx.x, blockIdx.x + gridDim.x, ... keeping (clip, mi, nt) up to date with adds
-// and compares only (the per-step deltas are decomposed once).
+// Walks the CTA's tiles l = blockIdx.x, blockIdx.x + gridDim.x, ...; with g.reverse the l-th tile is
+// num_tiles-1-l, so that a kernel starts on the rows the previous kernel of the plan wrote last
+// (they are still in L2) - consecutive launches of a plan alternate the direction.
+__device__ __forceinline__ int phys_tile(const GemmArgs& g, int l) { return g.reverse ? g.num_tiles - 1 - l : l; }
 struct TileWalker {
-  int tile, clip, mi, nt;
-  int d_nt, d_mi, d_clip;      // gridDim.x decomposed in the (clip, mi, nt) mixed radix
-  int tiles_n, tiles_m;
-  __device__ __forceinline__ TileWalker(const GemmArgs& g) {
-    tiles_n = g.tiles_n; tiles_m = g.tiles_m_per_clip;
-    tile = blockIdx.x;
-    const TileCoord t0 = tile_coord(g, tile);
-    clip = t0.clip; mi = t0.mi; nt = t0.nt;
-    const int step = gridDim.x;
-    int dm = step / tiles_n;
-    d_nt = step - dm * tiles_n;
-    if (g.n_clips == 1) { d_clip = 0; d_mi = dm; tiles_m = 0x7fffffff; }
-    else { d_clip = dm / tiles_m; d_mi = dm - d_clip * tiles_m; }
+  int tile, clip, mi, nt;      // tile = logical index l
+  __device__ __forceinline__ TileWalker(const GemmArgs& g) : tile(blockIdx.x), clip(0), mi(0), nt(0) { set(g); }
+  __device__ __forceinline__ void set(const GemmArgs& g) {
+    if (tile < g.num_tiles) {
+      const TileCoord t = tile_coord(g, phys_tile(g, tile));
+      clip = t.clip; mi = t.mi; nt = t.nt;
+    }
   }
-  __device__ __forceinline__ void next() {
+  __device__ __forceinline__ void next(const GemmArgs& g) {
     tile += gridDim.x;
-    nt += d_nt; mi += d_mi; clip += d_clip;
-    if (nt >= tiles_n) { nt -= tiles_n; ++mi; }
-    if (mi >= tiles_m) { mi -= tiles_m; ++clip; }
+    set(g);
   }
 };
 
@@ -301,7 +296,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   int sb = 0;
   int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   int dbg_it = 0;
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
     const int c = tc.nt * g.block_n + cg * 4;
     if (active && tc.nt != cached_nt) {                            // per-CTA constant when N fits one tile
@@ -397,7 +392,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   const __half2 s2 = h2_from(s_act, s_act);
   int sb = 0;
   int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next()) {
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int c = tc.nt * g.block_n + cg * 4;
     if (tc.nt != cached_nt) {                                      // (re)stage taps for this N tile
       cached_nt = tc.nt;
@@ -550,11 +545,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int dbg_it = 0;
       if (g.resident_b) {   // the n tile of a CTA is fixed (grid is a multiple of tiles_n): load W once
-        const int n_fixed = tile_coord(g, blockIdx.x).nt * g.block_n;
+        const int n_fixed = tile_coord(g, phys_tile(g, blockIdx.x)).nt * g.block_n;
         mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(num_kb * b_stage_bytes));
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smemB + kb * b_stage_bytes, &tmB, w_full, kb * BK, n_fixed);
       }
-      for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(), ++dbg_it) {
+      for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++dbg_it) {
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
         // (An L2 prefetch of the tile's residual rows from here - cp.async.bulk.prefetch.tensor through
@@ -663,7 +658,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int as = 0;
     uint32_t as_phase = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(g, tile);
+      const TileCoord tc = tile_coord(g, phys_tile(g, tile));
       const int nt = tc.nt, clip = tc.clip;
       const int r_base = tc.mi * rows_out;   // first OUTPUT row of the tile
       const int n0 = nt * g.block_n;

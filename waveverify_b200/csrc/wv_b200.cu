@@ -19,6 +19,7 @@
 #include "../../include/wv_b200.h"
 #include "gemm_sm100.cuh"
 #include "glue_kernels.cuh"
+#include "resblock_sm100.cuh"
 
 namespace {
 
@@ -98,6 +99,9 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
+bool g_serpentine = true;   // consecutive GEMM launches walk their tiles in opposite directions (WV_SERPENTINE=0 disables)
+int g_rb_maxc = 0;     // widest resblock that runs as ONE fused kernel (resblock_sm100.cuh, WV_RB_MAXC=96 enables it);
+                       // measured r01: correct, but bound by its three ELU passes (MUFU) - 280 vs 265 us at C=96
 bool g_pdl = false;  // programmatic dependent launch for every plan kernel (WV_PDL=1 enables; measured
                      // 1-2 % slower on the 64-clip batch, where launch gaps are already hidden)
 void init_device_once() {
@@ -116,6 +120,9 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  if (const char* e = getenv("WV_SERPENTINE")) g_serpentine = atoi(e) != 0;
+  if (const char* e = getenv("WV_RB_MAXC")) g_rb_maxc = atoi(e);   // 0 disables the fused resblock kernel
   CK(cudaFuncSetAttribute(conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   done = true;
 }
@@ -396,7 +403,7 @@ struct IoPtrs {
   float* probs = nullptr;
 };
 
-enum OpType { OP_GEMM, OP_DW5, OP_DOWN, OP_UP, OP_CONV_PRE, OP_CONV_LAST, OP_WAV_STAGE, OP_FRAMES,
+enum OpType { OP_RESBLOCK = 20, OP_GEMM = 0, OP_DW5, OP_DOWN, OP_UP, OP_CONV_PRE, OP_CONV_LAST, OP_WAV_STAGE, OP_FRAMES,
               OP_FILM, OP_BITS, OP_CONF, OP_LATENT_IN };
 
 struct Op {
@@ -405,6 +412,7 @@ struct Op {
   int epi = 0;
   CUtensorMap tmA, tmB, tmR;   // tmR: residual tile view for the L2 prefetch (else a copy of tmB)
   GemmArgs g;
+  ResblockArgs rb;   // OP_RESBLOCK (tmA = x tiles, tmB = W1, tmR = W2)
   int grid = 0;
   // generic
   const void* in = nullptr;
@@ -439,6 +447,7 @@ struct PlanCtx {
   int B = 0, T = 0;
   std::string next_tag;
   void push(Op& op) {
+    if (op.type == OP_GEMM && g_serpentine) op.g.reverse = static_cast<int>(ops->size() & 1);   // alternate directions
     op.tag = next_tag;
     next_tag.clear();
     ops->push_back(op);
@@ -616,12 +625,62 @@ void add_gemm_down(PlanCtx& c, const GemmW& pw, const DwW& dw, int r, const h16*
   op.bytes = n_in * K * 2.0 + n_out * pw.N * 2.0 * ((out_raw ? 1 : 0) + (out_act ? 1 : 0)) + static_cast<double>(pw.N) * K * 2.0;
 }
 
+bool resblock_fusable(const ResW& r, int C) {
+  return g_rb_maxc > 0 && C <= g_rb_maxc && C <= 128 && C % 32 == 0 && r.pw1.N == C && r.pw1.K == C && r.pw2.N == C &&
+         r.pw2.K == C && r.pw1.block_n == C && r.pw2.block_n == C && r.dw1.bias && r.dw2.bias &&
+         rb_pick_nx(C, ceil_div(C, BK)) >= 2;
+}
+
+// One residual block as ONE launch (resblock_sm100.cuh): reads the raw stream X only.
+void add_resblock_fused(PlanCtx& c, const ResW& r, const h16* X, int T, int C, h16* out_raw, h16* out_act,
+                        float act_scale, const std::string& name) {
+  Op op;
+  op.type = OP_RESBLOCK;
+  ResblockArgs& g = op.rb;
+  memset(&g, 0, sizeof(g));
+  g.C = C; g.num_kb = ceil_div(C, BK);
+  g.T = T; g.n_clips = c.B;
+  g.tiles_m_per_clip = ceil_div(T, RB_ROWS_OUT);
+  const long long tiles = static_cast<long long>(g.tiles_m_per_clip) * c.B;
+  if (tiles >= (1ll << 31)) WV_THROW(WV_ERR_UNSUPPORTED, "too many tiles (%lld)", tiles);
+  g.num_tiles = static_cast<int>(tiles);
+  g.magic_m = g.tiles_m_per_clip == 1 ? 0xFFFFFFFFu : static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(g.tiles_m_per_clip));
+  g.nx = rb_pick_nx(C, g.num_kb);
+  g.idesc = make_idesc_f16(BM, C, true);
+  g.pre_scale = r.pre_scale;
+  g.dw1_w = r.dw1.w; g.dw1_b = r.dw1.bias; g.dw2_w = r.dw2.w; g.dw2_b = r.dw2.bias;
+  g.x = X; g.out_raw = out_raw; g.out_act = out_act; g.act_scale = act_scale;
+  if (!c.dry()) op.tmA = make_tmap(X, 3, C, T, c.B, C, static_cast<uint64_t>(C) * T, BK, BM, true);
+  op.tmB = r.pw1.tm;
+  op.tmR = r.pw2.tm;
+  op.grid = std::min(g.num_tiles, g_num_sms);
+  op.i[7] = rb_smem_bytes(C, g.num_kb, g.nx);
+  op.out0 = out_raw; op.out1 = out_act;
+  const double n = static_cast<double>(c.B) * T;
+  op.flops = n * C * (4.0 * C + 20.0);
+  op.bytes = n * C * 2.0 * (1 + (out_raw ? 1 : 0) + (out_act ? 1 : 0)) + 4.0 * C * C;
+  op.out_bytes[0] = out_raw ? static_cast<size_t>(n) * C * 2 : 0;
+  op.out_bytes[1] = out_act ? static_cast<size_t>(n) * C * 2 : 0;
+  c.tag(name + ".fused");
+  c.push(op);
+}
+
 // One residual block (modules/seanet.py:245-281).  X raw (residual), A = ELU(X*pre_scale).
 // Produces Xn (raw, if need_raw) and An = ELU(Xn*next_act_scale) (if need_act); frees X and A.
 void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool need_raw, bool need_act,
                    float next_act_scale, Buf& Xn, Buf& An, const std::string& name) {
   const long long M = static_cast<long long>(c.B) * T;
   const size_t bytes = static_cast<size_t>(M) * C * 2;
+  if (resblock_fusable(r, C)) {   // the fused kernel activates X itself: A (if the producer made one) is not read
+    if (A.valid) c.release(A);
+    Xn = Buf(); An = Buf();
+    if (need_raw) Xn = c.alloc(bytes);
+    if (need_act) An = c.alloc(bytes);
+    add_resblock_fused(c, r, c.ptr<h16>(X), T, C, need_raw ? c.ptr<h16>(Xn) : nullptr, need_act ? c.ptr<h16>(An) : nullptr,
+                       next_act_scale, name);
+    c.release(X);
+    return;
+  }
   // half 1: A2 = ELU(dw5(W1 * A) + b1)
   Buf A2 = c.alloc(bytes);
   c.tag(name + ".h1");
@@ -1170,6 +1229,9 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         launch_gemm(op, g, st);
         break;
       }
+      case OP_RESBLOCK:
+        launch_k(resblock_sm100_kernel, op.grid, GEMM_THREADS, static_cast<size_t>(op.i[7]), st, op.tmA, op.tmB, op.tmR, op.rb);
+        break;
       case OP_DW5:
         launch_k(dw5_kernel, op.grid, 256, 0, st, static_cast<const h16*>(op.in), op.w, op.bias, static_cast<const h16*>(op.res),
                  static_cast<h16*>(op.out0), static_cast<h16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
@@ -1444,7 +1506,7 @@ int wv_net_profile_read(wv_net* net, int max_ops, float* ms, double* flops, doub
       ms[i] = t;
       flops[i] = p.ops[i].flops;
       bytes[i] = p.ops[i].bytes;
-      cls[i] = p.ops[i].type == OP_GEMM ? 100 + p.ops[i].epi : static_cast<int>(p.ops[i].type);
+      cls[i] = p.ops[i].type == OP_GEMM ? 100 + p.ops[i].epi : static_cast<int>(p.ops[i].type);   // OP_RESBLOCK = 20
     }
   });
   return rc == WV_OK ? count : rc;
@@ -1554,6 +1616,35 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
       return;
     }
     launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_op_resblock(const void* X, const void* W1, const float* dw1_w5c, const float* dw1_b, const void* W2,
+                   const float* dw2_w5c, const float* dw2_b, int B, int T, int C, float pre_scale, void* out_raw,
+                   void* out_act, float act_scale, void* stream) {
+  return guarded([&] {
+    init_device_once();
+    ResW r;
+    for (GemmW* w : {&r.pw1, &r.pw2}) {
+      w->N = C; w->K = C; w->ldw = C; w->fp16 = true; w->block_n = C;
+    }
+    r.pw1.w = const_cast<void*>(W1); r.pw2.w = const_cast<void*>(W2);
+    r.pw1.tm = make_tmap(W1, 2, C, C, 1, C, 0, BK, C, true);
+    r.pw2.tm = make_tmap(W2, 2, C, C, 1, C, 0, BK, C, true);
+    r.dw1.w = const_cast<float*>(dw1_w5c); r.dw1.bias = const_cast<float*>(dw1_b); r.dw1.k = 5; r.dw1.C = C;
+    r.dw2.w = const_cast<float*>(dw2_w5c); r.dw2.bias = const_cast<float*>(dw2_b); r.dw2.k = 5; r.dw2.C = C;
+    r.pre_scale = pre_scale;
+    if (C > 128 || C % 32 != 0 || rb_pick_nx(C, ceil_div(C, BK)) < 2)
+      WV_THROW(WV_ERR_UNSUPPORTED, "fused resblock needs C %% 32 == 0 and C <= 128 (got %d)", C);
+    std::vector<Op> ops;
+    PlanCtx c;
+    c.base = reinterpret_cast<uint8_t*>(16);
+    c.ops = &ops;
+    c.B = B;
+    add_resblock_fused(c, r, static_cast<const h16*>(X), T, C, static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale, "op");
+    launch_k(resblock_sm100_kernel, ops[0].grid, GEMM_THREADS, static_cast<size_t>(ops[0].i[7]), static_cast<cudaStream_t>(stream),
+             ops[0].tmA, ops[0].tmB, ops[0].tmR, ops[0].rb);
     CK(cudaGetLastError());
   });
 }
