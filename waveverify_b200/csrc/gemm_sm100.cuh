@@ -79,6 +79,7 @@ struct GemmArgs {
   int N, K;
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
+  int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
   int resident_b;     // 1: this CTA's W tile (all k-blocks) stays in shared memory; the ring carries A only
   uint32_t idesc;
@@ -544,6 +545,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int dbg_it = 0;
+      const uint64_t pol = l2_policy_evict_first();
       if (g.resident_b) {   // the n tile of a CTA is fixed (grid is a multiple of tiles_n): load W once
         const int n_fixed = tile_coord(g, phys_tile(g, blockIdx.x)).nt * g.block_n;
         mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(num_kb * b_stage_bytes));
@@ -558,7 +560,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
-          tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
+          if (g.a_evict_first) tma_load_3d_hint(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip, pol);
+          else tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
           if (!g.resident_b) tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }

@@ -99,6 +99,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
+bool g_evict_first = true;  // A operand TMA loads carry an L2 evict_first hint (WV_EVICT_FIRST=0 disables)
 bool g_serpentine = true;   // consecutive GEMM launches walk their tiles in opposite directions (WV_SERPENTINE=0 disables)
 int g_rb_maxc = 0;     // widest resblock that runs as ONE fused kernel (resblock_sm100.cuh, WV_RB_MAXC=96 enables it);
                        // measured r01: correct, but bound by its three ELU passes (MUFU) - 280 vs 265 us at C=96
@@ -121,6 +122,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  if (const char* e = getenv("WV_EVICT_FIRST")) g_evict_first = atoi(e) != 0;
   if (const char* e = getenv("WV_SERPENTINE")) g_serpentine = atoi(e) != 0;
   if (const char* e = getenv("WV_RB_MAXC")) g_rb_maxc = atoi(e);   // 0 disables the fused resblock kernel
   CK(cudaFuncSetAttribute(conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -448,6 +450,7 @@ struct PlanCtx {
   std::string next_tag;
   void push(Op& op) {
     if (op.type == OP_GEMM && g_serpentine) op.g.reverse = static_cast<int>(ops->size() & 1);   // alternate directions
+    if (op.type == OP_GEMM) op.g.a_evict_first = g_evict_first ? 1 : 0;
     op.tag = next_tag;
     next_tag.clear();
     ops->push_back(op);
