@@ -27,6 +27,12 @@
 
 namespace wv {
 
+#ifdef WV_TIMELINE
+#define RB_DBG(slot, pair) do { if (g.dbg != nullptr && blockIdx.x == 0 && (pair) < 24) g.dbg[(pair) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define RB_DBG(slot, pair) do { } while (0)
+#endif
+
 constexpr int RB_HALO = 8;
 constexpr int RB_ROWS_OUT = BM - RB_HALO;   // 120
 constexpr int RB_MAX_NX = 4;
@@ -34,6 +40,14 @@ constexpr int RB_BAR_BYTES = 512;
 constexpr int RB_SLOT_COLS = 256;
 constexpr int BAR_RB_FULL = 6;              // named barriers 6,7: staging tile of slot s written
 constexpr int BAR_RB_EMPTY = 8;             // 8,9: staging tile of slot s free for the next pair
+// Measured at C = 96 (64 x 16 000 rows): 12 math warps / 640 threads 280 us, 24 math warps / 1024
+// threads at 64 registers 313 us (spills), the two-launch form 265 us.  The kernel executes ~2x the
+// instructions of the two launches it replaces (three ELU passes, the in-place activation of the
+// padded tile, halo rows twice) and ends up issue-bound; see DESIGN.md.
+constexpr int RB_MATH_WARPS = 12;
+constexpr int RB_MATH_THREADS = RB_MATH_WARPS * 32;
+constexpr int RB_EPI_THREADS = (P1_WARPS + RB_MATH_WARPS) * 32;
+constexpr int RB_THREADS = 128 + RB_EPI_THREADS;
 
 struct ResblockArgs {
   int C, num_kb;
@@ -51,13 +65,15 @@ struct ResblockArgs {
   act_t* out_raw;
   act_t* out_act;
   float act_scale;
+  long long* dbg;               // -DWV_TIMELINE builds: per-pair clock probes of CTA 0 (scripts/timeline_rb.py)
 };
 
 __host__ __device__ inline int rb_xtile_bytes(int num_kb) { return num_kb * A_STAGE_BYTES; }
 __host__ __device__ inline int rb_w_bytes(int C, int num_kb) { return num_kb * C * BK * 2; }
+__host__ __device__ inline int rb_taps_bytes(int C) { return 2 * 6 * C * 2; }   // [conv][5 taps + bias][C] fp16
 __host__ inline int rb_smem_bytes(int C, int num_kb, int nx) {
   return 1024 + nx * rb_xtile_bytes(num_kb) + 2 * rb_w_bytes(C, num_kb) + RB_BAR_BYTES +
-         2 * BM * staged_pitch_bytes(C);
+         2 * BM * staged_pitch_bytes(C) + rb_taps_bytes(C);
 }
 __host__ inline int rb_pick_nx(int C, int num_kb) {
   for (int nx = RB_MAX_NX; nx >= 2; --nx)
@@ -114,18 +130,16 @@ __device__ __forceinline__ void rb_m2_tile(const ResblockArgs& g, const GemmArgs
                                            const __half2 (&wt)[5][2], const __half2 (&bs)[2], uint2 (&rres)[4]) {
   const size_t row_bytes = static_cast<size_t>(g.C) * 2;
   if (!active) return;
-  bool first = true;
   for (int grp = grp0; grp < RB_ROWS_OUT / 4; grp += gstride) {
     const int oo = grp * 4;                       // output row relative to the tile's first output row
     if (oo >= rows_left) break;
     const size_t off = base + static_cast<size_t>(oo) * g.C;
-    if (!first) {
+    {   // the residual rows were read by this tile's TMA load a moment ago: L2 hits
       const char* rp = reinterpret_cast<const char*>(g.x + off);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         rres[i] = oo + i < rows_left ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
     }
-    first = false;
     const uint32_t srow = tile_u32 + static_cast<uint32_t>(oo + 4) * pitch;   // staged rows oo+4 .. oo+11
     if (oo + 4 <= rows_left)
       staged_unit<5, 4, true, RAW, ACT, true, true>(gf, srow, pitch, off, row_bytes, 4, wt, bs, g.act_scale, rres);
@@ -134,7 +148,7 @@ __device__ __forceinline__ void rb_m2_tile(const ResblockArgs& g, const GemmArgs
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(RB_THREADS, 1)
 resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                       const __grid_constant__ CUtensorMap tmW2, const ResblockArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -157,6 +171,7 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   uint8_t* stage_tiles = reinterpret_cast<uint8_t*>(bars) + RB_BAR_BYTES;   // [2][128][pitch]
   const int pitch = staged_pitch_bytes(g.C);
+  uint8_t* taps_tbl = stage_tiles + 2 * BM * pitch;    // [2][6][C] fp16: depthwise taps + bias of both convs
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -175,11 +190,17 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&tm_empty[i], P1_WARPS);
-      mbar_init(&t0_done[i], P2_WARPS);
-      mbar_init(&m1_done[i], P2_WARPS);
+      mbar_init(&t0_done[i], RB_MATH_WARPS);
+      mbar_init(&m1_done[i], RB_MATH_WARPS);
     }
     mbar_init(w_full, 1);
     fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 2 * 6 * g.C; i += blockDim.x) {   // the depthwise taps live in shared memory: a phase
+    const int conv = i / (6 * g.C), r = (i / g.C) % 6, ch = i % g.C;  // loads its 6 half2 pairs when it starts
+    const float* wsrc = conv ? g.dw2_w : g.dw1_w;
+    const float* bsrc = conv ? g.dw2_b : g.dw1_b;
+    reinterpret_cast<__half*>(taps_tbl)[i] = __float2half_rn(r < 5 ? __ldg(wsrc + r * g.C + ch) : __ldg(bsrc + ch));
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -233,12 +254,14 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           mbar_wait(&tm_empty[s], pph ^ 1);          // TMEM slot drained (second GEMM of the previous pair)
           mbar_wait(&t0_done[s], pph);               // x tile landed and activated in place
           tc_fence_after();
+          RB_DBG(0 + s, pair);
           issue(xa + ((it + s) % g.nx) * xt_bytes, w1, tmem_base + static_cast<uint32_t>(s * RB_SLOT_COLS));
           umma_commit(&acc_full[s]);
         }
         for (int s = 0; s < nb; ++s) {
           mbar_wait(&m1_done[s], pph);               // h written into the x buffer (operand layout)
           tc_fence_after();
+          RB_DBG(2 + s, pair);
           issue(xa + ((it + s) % g.nx) * xt_bytes, w2, tmem_base + static_cast<uint32_t>(s * RB_SLOT_COLS));
           umma_commit(&acc_full[s]);
           umma_commit(&x_empty[(it + s) % g.nx]);    // the x buffer may be refilled once GEMM2 has read it
@@ -275,40 +298,40 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     for (int it = 0, pair = 0; it < my_tiles; it += 2, ++pair) {
       const int nb = my_tiles - it < 2 ? my_tiles - it : 2;
       for (int s = 0; s < nb; ++s) {                 // GEMM1 tiles
-        if (pair > 0) named_bar_sync(BAR_RB_EMPTY + s, EPI_THREADS);   // M2 of the previous pair left staging[s]
+        if (pair > 0) named_bar_sync(BAR_RB_EMPTY + s, RB_EPI_THREADS);   // M2 of the previous pair left staging[s]
+        if (q == 0 && lane == 0) RB_DBG(4 + s, pair);
         drain(s);
-        named_bar_arrive(BAR_RB_FULL + s, EPI_THREADS);
+        if (q == 0 && lane == 0) RB_DBG(6 + s, pair);
+        named_bar_arrive(BAR_RB_FULL + s, RB_EPI_THREADS);
       }
       for (int s = 0; s < nb; ++s) {                 // GEMM2 tiles (staging[s] was released by M1: GEMM2 waited for it)
+        if (q == 0 && lane == 0) RB_DBG(8 + s, pair);
         drain(s);
+        if (q == 0 && lane == 0) RB_DBG(10 + s, pair);
         if (lane == 0) mbar_arrive(&tm_empty[s]);
-        named_bar_arrive(BAR_RB_FULL + s, EPI_THREADS);
+        named_bar_arrive(BAR_RB_FULL + s, RB_EPI_THREADS);
       }
     }
   } else if (warp >= 4 + P1_WARPS) {
     // ------------------------------------------------------------ math warps
     const int et = threadIdx.x - (128 + P1_WARPS * 32);
     const int cgs = g.C >> 2;
-    const int gstride = P2_THREADS / cgs;
+    const int gstride = RB_MATH_THREADS / cgs;
     const int cg = et % cgs, grp0 = et / cgs;
     const bool active = grp0 < gstride;
     const int c = cg * 4;
     const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
     const uint32_t xa_u32 = smem_u32(xa);
-    __half2 wt1[5][2], wt2[5][2], bs1[2], bs2[2];
-    if (active) {
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.dw1_b + c));
-      const float4 b2 = __ldg(reinterpret_cast<const float4*>(g.dw2_b + c));
-      bs1[0] = h2_from(b1.x, b1.y); bs1[1] = h2_from(b1.z, b1.w);
-      bs2[0] = h2_from(b2.x, b2.y); bs2[1] = h2_from(b2.z, b2.w);
+    const uint32_t taps_u32 = smem_u32(taps_tbl) + c * 2;
+    auto load_taps = [&](int conv, __half2 (&wt)[5][2], __half2 (&bs)[2]) {
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(g.dw1_w + j * g.C + c));
-        const float4 w = __ldg(reinterpret_cast<const float4*>(g.dw2_w + j * g.C + c));
-        wt1[j][0] = h2_from(u.x, u.y); wt1[j][1] = h2_from(u.z, u.w);
-        wt2[j][0] = h2_from(w.x, w.y); wt2[j][1] = h2_from(w.z, w.w);
+        const uint2 u = lds_u2(taps_u32 + (conv * 6 + j) * g.C * 2);
+        wt[j][0] = as_h2(u.x); wt[j][1] = as_h2(u.y);
       }
-    }
+      const uint2 u = lds_u2(taps_u32 + (conv * 6 + 5) * g.C * 2);
+      bs[0] = as_h2(u.x); bs[1] = as_h2(u.y);
+    };
     GemmArgs gf = {};                                // the output pointers staged_unit reads
     gf.residual = g.x; gf.out_raw = g.out_raw; gf.out_act = g.out_act;
     const __half2 ps2 = h2_from(g.pre_scale, g.pre_scale);
@@ -318,9 +341,11 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       // ---- T0: a = ELU(x * pre_scale) in place (elementwise: independent of the swizzle)
       for (int s = 0; s < nb; ++s) {
         const int buf = (it + s) % g.nx;
+        if (et == 0) RB_DBG(12 + s, pair);
         mbar_wait(&x_full[buf], static_cast<uint32_t>((it + s) / g.nx) & 1u);
+        if (et == 0) RB_DBG(14 + s, pair);
         const uint32_t tile = xa_u32 + buf * xt_bytes;
-        for (int i = et; i < n_chunks; i += P2_THREADS) {
+        for (int i = et; i < n_chunks; i += RB_MATH_THREADS) {
           const uint4 u = lds_u4(tile + i * 16);
           sts_u4(tile + i * 16, as_u32(elu_h2(__hmul2(as_h2(u.x), ps2))), as_u32(elu_h2(__hmul2(as_h2(u.y), ps2))),
                  as_u32(elu_h2(__hmul2(as_h2(u.z), ps2))), as_u32(elu_h2(__hmul2(as_h2(u.w), ps2))));
@@ -328,14 +353,18 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t0_done[s]);
+        if (et == 0) RB_DBG(16 + s, pair);
       }
       // ---- M1: h = ELU(dw5(S1) + b1) -> operand layout in the x buffer
       for (int s = 0; s < nb; ++s) {
         int clip, mi;
         tile_rc(it + s, clip, mi);
         const int zero_rows = RB_HALO - mi * RB_ROWS_OUT;   // tile rows before the clip start (8 for mi = 0, else <= 0)
-        named_bar_sync(BAR_RB_FULL + s, EPI_THREADS);
+        named_bar_sync(BAR_RB_FULL + s, RB_EPI_THREADS);
+        if (et == 0) RB_DBG(18 + s, pair);
         if (active) {
+          __half2 wt1[5][2], bs1[2];
+          load_taps(0, wt1, bs1);
           const uint32_t tile_u32 = stage_u32 + s * (BM * pitch);
           const uint32_t xbuf = xa_u32 + ((it + s) % g.nx) * xt_bytes;
           for (int grp = grp0; grp < (BM - 4) / 4; grp += gstride)
@@ -344,6 +373,7 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&m1_done[s]);
+        if (et == 0) RB_DBG(20 + s, pair);
       }
       // ---- M2: x' = dw5(S2) + b2 + x -> global
       for (int s = 0; s < nb; ++s) {
@@ -352,16 +382,12 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const int r_base = mi * RB_ROWS_OUT;
         const int rows_left = min(g.T - r_base, RB_ROWS_OUT);
         const size_t base = (static_cast<size_t>(clip) * g.T + r_base) * g.C + c;
-        uint2 rres[4];
-        if (active) {                                // residual rows of the first unit, before the drain hand-off
-          const int oo = grp0 * 4;
-          const char* rp = reinterpret_cast<const char*>(g.x + base + static_cast<size_t>(oo) * g.C);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            rres[i] = (oo + i < rows_left && oo < RB_ROWS_OUT) ? __ldcg(reinterpret_cast<const uint2*>(rp + static_cast<size_t>(i) * g.C * 2)) : make_uint2(0u, 0u);
-        }
-        named_bar_sync(BAR_RB_FULL + s, EPI_THREADS);
+        named_bar_sync(BAR_RB_FULL + s, RB_EPI_THREADS);
+        if (et == 0) RB_DBG(22 + s, pair);
         const uint32_t tile_u32 = stage_u32 + s * (BM * pitch);
+        __half2 wt2[5][2], bs2[2];
+        uint2 rres[4];
+        if (active) load_taps(1, wt2, bs2);
         if (g.out_raw != nullptr && g.out_act != nullptr)
           rb_m2_tile<true, true>(g, gf, tile_u32, pitch, cg, grp0, gstride, active, base, rows_left, wt2, bs2, rres);
         else if (g.out_raw != nullptr)
@@ -369,7 +395,8 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         else
           rb_m2_tile<false, true>(g, gf, tile_u32, pitch, cg, grp0, gstride, active, base, rows_left, wt2, bs2, rres);
         __syncwarp();
-        if (it + 2 + s < my_tiles) named_bar_arrive(BAR_RB_EMPTY + s, EPI_THREADS);   // staging[s] free for the next pair
+        if (et == 0) RB_DBG(24 + s, pair);
+        if (it + 2 + s < my_tiles) named_bar_arrive(BAR_RB_EMPTY + s, RB_EPI_THREADS);   // staging[s] free for the next pair
       }
     }
   }

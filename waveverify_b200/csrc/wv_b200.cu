@@ -1233,7 +1233,7 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         break;
       }
       case OP_RESBLOCK:
-        launch_k(resblock_sm100_kernel, op.grid, GEMM_THREADS, static_cast<size_t>(op.i[7]), st, op.tmA, op.tmB, op.tmR, op.rb);
+        launch_k(resblock_sm100_kernel, op.grid, RB_THREADS, static_cast<size_t>(op.i[7]), st, op.tmA, op.tmB, op.tmR, op.rb);
         break;
       case OP_DW5:
         launch_k(dw5_kernel, op.grid, 256, 0, st, static_cast<const h16*>(op.in), op.w, op.bias, static_cast<const h16*>(op.res),
@@ -1646,9 +1646,28 @@ int wv_op_resblock(const void* X, const void* W1, const float* dw1_w5c, const fl
     c.ops = &ops;
     c.B = B;
     add_resblock_fused(c, r, static_cast<const h16*>(X), T, C, static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale, "op");
-    launch_k(resblock_sm100_kernel, ops[0].grid, GEMM_THREADS, static_cast<size_t>(ops[0].i[7]), static_cast<cudaStream_t>(stream),
+    long long* dbg = nullptr;
+    if (getenv("WV_TIMELINE_RB")) {
+      CK(cudaMalloc(&dbg, 24 * 32 * sizeof(long long)));
+      CK(cudaMemset(dbg, 0, 24 * 32 * sizeof(long long)));
+      ops[0].rb.dbg = dbg;
+    }
+    launch_k(resblock_sm100_kernel, ops[0].grid, RB_THREADS, static_cast<size_t>(ops[0].i[7]), static_cast<cudaStream_t>(stream),
              ops[0].tmA, ops[0].tmB, ops[0].tmR, ops[0].rb);
     CK(cudaGetLastError());
+    if (dbg) {
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> h(24 * 32);
+      CK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      CK(cudaFree(dbg));
+      long long t0 = h[12];
+      printf("pair: mma1a mma1b mma2a mma2b | dr1 start a b end a b | dr2 start a b end a b | T0 wait a b  got a b  done a b | M1 start a b done a b | M2 start a b done a b\n");
+      for (int p = 0; p < 14; ++p) {
+        printf("%2d:", p);
+        for (int k = 0; k < 26; ++k) printf(" %6lld", h[p * 32 + k] ? h[p * 32 + k] - t0 : -1);
+        printf("\n");
+      }
+    }
   });
 }
 
