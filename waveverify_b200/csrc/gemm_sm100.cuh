@@ -107,6 +107,8 @@ struct GemmArgs {
   // STFT
   float log_offset, inv_sigma, clamp_sq;
   int n_half;
+  int phases;          // > 1: frames with hop < 8 samples read as `phases` interleaved 16-byte-strided views of
+  int frames_per_clip; //      shifted waveform copies (4-D tensor map); "clip" = clip * phases + phase, row q = frame q*phases + phase
   // HEAD
   float* logits;
   uint8_t* mask_out;
@@ -560,7 +562,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
-          if (g.a_evict_first) tma_load_3d_hint(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip, pol);
+          if (g.phases > 1) tma_load_4d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip % g.phases, tc.clip / g.phases);
+          else if (g.a_evict_first) tma_load_3d_hint(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip, pol);
           else tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
           if (!g.resident_b) tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -674,8 +677,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       {
         const int r = r_base + q * 32 + lane;
-        const bool row_ok = r < g.rows_per_clip;
-        const long long m = static_cast<long long>(clip) * g.rows_per_clip + r;
+        bool row_ok = r < g.rows_per_clip;
+        long long m = static_cast<long long>(clip) * g.rows_per_clip + r;
+        if (EPI == EPI_STFT && g.phases > 1) {      // row q of (clip, phase) is frame q*phases + phase of the clip
+          const int f = r * g.phases + clip % g.phases;
+          row_ok = row_ok && f < g.frames_per_clip;
+          m = static_cast<long long>(clip / g.phases) * g.frames_per_clip + f;
+        }
         if constexpr (EPI == EPI_L2NORM) {
           if (h == 0) {
             float ss = 0.f;

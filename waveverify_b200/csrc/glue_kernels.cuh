@@ -314,20 +314,25 @@ conv_last_kernel(const act_t* __restrict__ in, const float* __restrict__ w, floa
 }
 
 // ---------------------------------------------------------------------------------------
-// Waveform staging for the conv-as-DFT STFTs (modules/conv.py:1036-1068): fp16 copy of x*scale
-// per clip with `lead` leading zeros (the causal n_fft-1 padding of the largest scale) and zero
-// tail up to the row pitch.
+// Waveform staging for the conv-as-DFT STFTs (modules/conv.py:1036-1068): fp16 copies of x*scale
+// per clip with `lead` leading zeros (the causal n_fft-1 padding of the largest scale) and a zero
+// tail up to the row pitch.  Eight copies per clip, copy s shifted left by s samples: a frame
+// sequence with hop h < 8 is then `8/h` interleaved views with a 16-byte row stride (the TMA stride
+// unit), phase r reading copy r*h - no frame matrix is materialised.   out[b][s][p] = staged[p + s]
+constexpr int WAV_COPIES = 8;
 __global__ void __launch_bounds__(256)
 wav_stage_kernel(const float* __restrict__ x, __half* __restrict__ out, float scale, int B, int T,
                  int lead, int pitch) {
   pdl_wait();
   pdl_launch_dependents();
-  const long long total = static_cast<long long>(B) * pitch;
+  const long long total = static_cast<long long>(B) * WAV_COPIES * pitch;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int p = static_cast<int>(idx % pitch);
-    const int b = static_cast<int>(idx / pitch);
-    const int t = p - lead;
+    const long long bs = idx / pitch;
+    const int sft = static_cast<int>(bs % WAV_COPIES);
+    const int b = static_cast<int>(bs / WAV_COPIES);
+    const int t = p + sft - lead;
     const float v = (t >= 0 && t < T) ? __ldcg(x + static_cast<long long>(b) * T + t) * scale : 0.f;
     out[idx] = __float2half_rn(v);
   }

@@ -91,6 +91,23 @@ CUtensorMap make_tmap(const void* base, int rank, uint64_t dim_k, uint64_t dim_r
   return m;
 }
 
+// fp16 4-D map (k, row, phase, clip) for the phased STFT frame view; strides in ELEMENTS.
+CUtensorMap make_tmap4(const void* base, uint64_t dim_k, uint64_t dim_row, uint64_t dim_phase, uint64_t dim_clip,
+                       uint64_t row_stride, uint64_t phase_stride, uint64_t clip_stride, int box_k, int box_row) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {dim_k, dim_row, dim_phase, dim_clip};
+  cuuint64_t strides[3] = {row_stride * 2, phase_stride * 2, clip_stride * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_row), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    WV_THROW(WV_ERR_INVALID, "TMA alignment violated (4-D frame view)");
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) WV_THROW(WV_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed with %d", (int)r);
+  return m;
+}
+
 int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
   static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
   for (int c : cands)
@@ -99,6 +116,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
+bool g_phased_stft = true;  // hop < 8 STFTs read frames through phased strided TMA views (WV_PHASED_STFT=0: frame matrix)
 bool g_evict_first = true;  // A operand TMA loads carry an L2 evict_first hint (WV_EVICT_FIRST=0 disables)
 bool g_serpentine = true;   // consecutive GEMM launches walk their tiles in opposite directions (WV_SERPENTINE=0 disables)
 int g_rb_maxc = 0;     // widest resblock that runs as ONE fused kernel (resblock_sm100.cuh, WV_RB_MAXC=96 enables it);
@@ -122,6 +140,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  if (const char* e = getenv("WV_PHASED_STFT")) g_phased_stft = atoi(e) != 0;
   if (const char* e = getenv("WV_EVICT_FIRST")) g_evict_first = atoi(e) != 0;
   if (const char* e = getenv("WV_SERPENTINE")) g_serpentine = atoi(e) != 0;
   if (const char* e = getenv("WV_RB_MAXC")) g_rb_maxc = atoi(e);   // 0 disables the fused resblock kernel
@@ -891,18 +910,34 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
   g.clamp_sq = (1e-5f * WAV_FP16_SCALE) * (1e-5f * WAV_FP16_SCALE);
   g.n_half = s.n_fft / 2;
   const int base = lead - (s.n_fft - 1);       // first sample of frame 0 inside the staged clip
+  const uint64_t clip_stride = static_cast<uint64_t>(WAV_COPIES) * pitch;   // 8 shifted copies per clip
   if ((s.hop * 2) % 16 == 0) {
     CUtensorMap tm;
     if (!c.dry())
-      tm = make_tmap(c.ptr<__half>(wav16) + base, 3, s.n_fft, F, c.B, s.hop, pitch, BK, BM, true);
+      tm = make_tmap(c.ptr<__half>(wav16) + base, 3, s.n_fft, F, c.B, s.hop, clip_stride, BK, BM, true);
     c.tag(name + ".stft");
     add_gemm(c, EPI_STFT, s.dft, nullptr, 0, 0, s.n_fft, g, &tm, F, c.B);
+  } else if (WAV_COPIES % s.hop == 0 && g_phased_stft) {
+    // hop < 8 samples: frame f = P*q + r starts at sample 8q + r*hop -> phase r = rows of copy r*hop
+    // with a 16-byte stride.  One GEMM over B*P "virtual clips" of ceil(F/P) rows.
+    const int P = WAV_COPIES / s.hop;
+    const int Fq = ceil_div(F, P);
+    g.phases = P;
+    g.frames_per_clip = F;
+    CUtensorMap tm;
+    if (!c.dry())
+      tm = make_tmap4(c.ptr<__half>(wav16) + base, s.n_fft, Fq, P, c.B, 8, static_cast<uint64_t>(s.hop) * pitch, clip_stride, BK, BM);
+    c.tag(name + ".stft");
+    add_gemm(c, EPI_STFT, s.dft, nullptr, 0, 0, s.n_fft, g, &tm, Fq, c.B * P);
+    Op& op = c.ops->back();
+    op.flops = 2.0 * static_cast<double>(M) * s.dft.N * s.n_fft;
+    op.bytes = static_cast<double>(M) * (2.0 * 8 + (s.dft.N / 2 + 1) * 2.0) + static_cast<double>(s.dft.N) * s.n_fft * 2.0;
   } else {
     Buf FR = c.alloc(static_cast<size_t>(M) * s.n_fft * 2);
     Op op;
     op.type = OP_FRAMES;
     op.in = c.ptr<__half>(wav16); op.out0 = c.ptr<__half>(FR);
-    op.i[0] = c.B; op.i[1] = F; op.i[2] = s.hop; op.i[3] = s.n_fft; op.i[4] = base; op.i[5] = pitch;
+    op.i[0] = c.B; op.i[1] = F; op.i[2] = s.hop; op.i[3] = s.n_fft; op.i[4] = base; op.i[5] = static_cast<int>(clip_stride);
     op.grid = elem_grid(M * (s.n_fft / 8));
     op.bytes = static_cast<double>(M) * s.n_fft * 2.0 + static_cast<double>(c.B) * pitch * 2.0;
     op.out_bytes[0] = static_cast<size_t>(M) * s.n_fft * 2;
@@ -928,16 +963,16 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
   const int B = c.B, T = c.T;
   const int lead = e.nfft_max - 1;
   const int pitch = static_cast<int>(round_up(lead + T, 8));
-  Buf wav16 = c.alloc(static_cast<size_t>(B) * pitch * 2);
+  Buf wav16 = c.alloc(static_cast<size_t>(B) * WAV_COPIES * pitch * 2 + 256);   // + slack: the last frame view may run a few samples past the last copy
   {
     Op op;
     op.type = OP_WAV_STAGE;
     op.out0 = c.ptr<__half>(wav16);
     op.fa = WAV_FP16_SCALE;
     op.i[0] = B; op.i[1] = T; op.i[2] = lead; op.i[3] = pitch;
-    op.grid = elem_grid(static_cast<long long>(B) * pitch);
-    op.bytes = static_cast<double>(B) * (T * 4.0 + pitch * 2.0);
-    op.out_bytes[0] = static_cast<size_t>(B) * pitch * 2;
+    op.grid = elem_grid(static_cast<long long>(B) * WAV_COPIES * pitch);
+    op.bytes = static_cast<double>(B) * (T * 4.0 + WAV_COPIES * pitch * 2.0);
+    op.out_bytes[0] = static_cast<size_t>(B) * WAV_COPIES * pitch * 2;
     c.tag("enc.wav16");
     c.push(op);
   }
