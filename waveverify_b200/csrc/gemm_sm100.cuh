@@ -79,6 +79,8 @@ struct GemmArgs {
   int N, K;
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
+  int kb_split;       // > 0: k-blocks >= kb_split re-read the A rows shifted by one (row r-1) at k - kb_split*64:
+                      //      [a[i] | a[i-1]] contraction of the fused transposed-conv + 1x1 (decoder upsample)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
   int resident_b;     // 1: this CTA's W tile (all k-blocks) stays in shared memory; the ring carries A only
@@ -563,6 +565,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
           if (g.phases > 1) tma_load_4d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip % g.phases, tc.clip / g.phases);
+          else if (g.kb_split > 0 && kb >= g.kb_split) tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], (kb - g.kb_split) * BK, r0 - 1, tc.clip);
           else if (g.a_evict_first) tma_load_3d_hint(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip, pol);
           else tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
           if (!g.resident_b) tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);

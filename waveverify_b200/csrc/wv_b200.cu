@@ -116,6 +116,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
+int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
 bool g_phased_stft = true;  // hop < 8 STFTs read frames through phased strided TMA views (WV_PHASED_STFT=0: frame matrix)
 bool g_evict_first = true;  // A operand TMA loads carry an L2 evict_first hint (WV_EVICT_FIRST=0 disables)
 bool g_serpentine = true;   // consecutive GEMM launches walk their tiles in opposite directions (WV_SERPENTINE=0 disables)
@@ -140,6 +141,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_PHASED_STFT")) g_phased_stft = atoi(e) != 0;
   if (const char* e = getenv("WV_EVICT_FIRST")) g_evict_first = atoi(e) != 0;
   if (const char* e = getenv("WV_SERPENTINE")) g_serpentine = atoi(e) != 0;
@@ -223,6 +225,7 @@ struct EncoderW {
 struct DecStageW {
   DwW up;                // [2r][C]
   GemmW halve;           // [C/2, C] + bias
+  GemmW up_halve;        // fused: [r*C/2, 2C] = halve o transposed depthwise conv (valid when .w != nullptr)
   std::vector<ResW> res;
   int r, C;
 };
@@ -841,7 +844,29 @@ void build_decoder_w(wv_net& n) {
     i += 2;
     st.up = depthwise(W, p + "." + std::to_string(i++) + ".convtr.convtr", 1.f, false);
     if (st.up.k != 2 * st.r) WV_THROW(WV_ERR_INVALID, "upsample kernel != 2*stride");
+    const std::string up_name = p + "." + std::to_string(i - 1) + ".convtr.convtr";
+    const std::string hv_name = p + "." + std::to_string(i) + ".conv.conv";
     st.halve = pointwise(W, p + "." + std::to_string(i++) + ".conv.conv", 1.f, true);
+    if (g_up_fuse_maxc > 0 && C <= g_up_fuse_maxc && C % BK == 0) {
+      // out[r*i + j, n] = b[n] + sum_c Wh[n,c] (a[i,c] w[c,j] + a[i-1,c] w[c,j+r])   (modules/conv.py:838-874 followed by
+      // the 1x1): one GEMM over the LOW-rate rows with K = [a[i] | a[i-1]] and N = (j, n); its [Ts, r*C/2]
+      // output IS the [Ts*r, C/2] high-rate tensor.  The upsampled tensor never exists.
+      const HostTensor& uw = W.get(up_name + ".weight");      // [C, 1, 2r]
+      const HostTensor& hw = W.get(hv_name + ".weight");      // [C/2, C, 1]
+      const HostTensor* hb = W.find(hv_name + ".bias");
+      const int r = st.r, Ch = C / 2;
+      std::vector<float> rows(static_cast<size_t>(r) * Ch * 2 * C), bias(static_cast<size_t>(r) * Ch, 0.f);
+      for (int j = 0; j < r; ++j)
+        for (int n = 0; n < Ch; ++n) {
+          float* dst = rows.data() + (static_cast<size_t>(j) * Ch + n) * 2 * C;
+          for (int cc = 0; cc < C; ++cc) {
+            dst[cc] = hw.data[static_cast<size_t>(n) * C + cc] * uw.data[static_cast<size_t>(cc) * 2 * r + j];
+            dst[C + cc] = hw.data[static_cast<size_t>(n) * C + cc] * uw.data[static_cast<size_t>(cc) * 2 * r + j + r];
+          }
+          if (hb) bias[static_cast<size_t>(j) * Ch + n] = hb->data[n];
+        }
+      st.up_halve = make_gemm_w(W, rows, r * Ch, 2 * C, true, pick_block_n(r * Ch, 0, STAGED_MAX_BN), bias.data(), r * Ch);
+    }
     for (int j = 0; j < cf.n_residual_dec; ++j)
       st.res.push_back(resblock_w(W, p + "." + std::to_string(i++), j, rs));     // idx=j, seanet.py:1159
     d.stages.push_back(st);
@@ -1060,6 +1085,35 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
   for (size_t s = 0; s < d.stages.size(); ++s) {
     const DecStageW& st = d.stages[s];
     const int To = Ts * st.r;
+    if (st.up_halve.w != nullptr) {   // fused transposed conv + 1x1: one GEMM over the low-rate rows
+      const int Ch = C / 2, Nf = st.r * Ch;
+      Buf X = c.alloc(static_cast<size_t>(B) * To * Ch * 2);
+      Buf An = c.alloc(static_cast<size_t>(B) * To * Ch * 2);
+      GemmArgs g = std_args(st.up_halve.bias, nullptr, c.ptr<h16>(X), c.ptr<h16>(An),
+                            st.res.empty() ? d.stage_scale : st.res[0].pre_scale, Nf);
+      g.kb_split = C / BK;
+      CUtensorMap tm;
+      if (!c.dry()) tm = make_tmap(c.ptr<h16>(A), 3, C, Ts, B, C, static_cast<uint64_t>(C) * Ts, BK, BM, true);
+      c.tag("dec.u" + std::to_string(s) + ".uphalve");
+      add_gemm(c, EPI_STAGED, st.up_halve, nullptr, 0, 0, 2 * C, g, &tm, Ts, B);
+      Op& op = c.ops->back();
+      op.bytes = static_cast<double>(B) * Ts * C * 2.0 + 2.0 * B * To * Ch * 2.0 + static_cast<double>(Nf) * 2 * C * 2.0;
+      c.release(A);
+      A = An;
+      Ts = To;
+      M = static_cast<long long>(B) * Ts;
+      C = Ch;
+      const int nres = static_cast<int>(st.res.size());
+      for (int j = 0; j < nres; ++j) {
+        const bool last = j == nres - 1;
+        Buf Xn, An2;
+        plan_resblock(c, st.res[j], X, A, Ts, C, !last, true, last ? d.stage_scale : st.res[j + 1].pre_scale, Xn, An2,
+                      "dec.u" + std::to_string(s) + ".r" + std::to_string(j));
+        X = Xn; A = An2;
+      }
+      if (nres == 0) c.release(X);
+      continue;
+    }
     Buf U = c.alloc(static_cast<size_t>(B) * To * C * 2);
     {
       Op op;
