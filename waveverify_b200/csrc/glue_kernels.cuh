@@ -325,16 +325,21 @@ wav_stage_kernel(const float* __restrict__ x, __half* __restrict__ out, float sc
                  int lead, int pitch) {
   pdl_wait();
   pdl_launch_dependents();
-  const long long total = static_cast<long long>(B) * WAV_COPIES * pitch;
+  const int p8n = pitch >> 3;                                  // pitch is a multiple of 8: one 16-byte store per thread
+  const long long total = static_cast<long long>(B) * WAV_COPIES * p8n;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int p = static_cast<int>(idx % pitch);
-    const long long bs = idx / pitch;
+    const int p = static_cast<int>(idx % p8n) * 8;
+    const long long bs = idx / p8n;
     const int sft = static_cast<int>(bs % WAV_COPIES);
     const int b = static_cast<int>(bs / WAV_COPIES);
-    const int t = p + sft - lead;
-    const float v = (t >= 0 && t < T) ? __ldcg(x + static_cast<long long>(b) * T + t) * scale : 0.f;
-    out[idx] = __float2half_rn(v);
+    const int t0 = p + sft - lead;
+    const float* xp = x + static_cast<long long>(b) * T;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (t0 + k >= 0 && t0 + k < T) ? __ldcg(xp + t0 + k) * scale : 0.f;
+    *reinterpret_cast<uint4*>(out + bs * pitch + p) =
+        make_uint4(pack_act2(v[0], v[1]), pack_act2(v[2], v[3]), pack_act2(v[4], v[5]), pack_act2(v[6], v[7]));
   }
 }
 

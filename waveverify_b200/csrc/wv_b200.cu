@@ -995,7 +995,7 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     op.out0 = c.ptr<__half>(wav16);
     op.fa = WAV_FP16_SCALE;
     op.i[0] = B; op.i[1] = T; op.i[2] = lead; op.i[3] = pitch;
-    op.grid = elem_grid(static_cast<long long>(B) * WAV_COPIES * pitch);
+    op.grid = elem_grid(static_cast<long long>(B) * WAV_COPIES * (pitch / 8));
     op.bytes = static_cast<double>(B) * (T * 4.0 + WAV_COPIES * pitch * 2.0);
     op.out_bytes[0] = static_cast<size_t>(B) * WAV_COPIES * pitch * 2;
     c.tag("enc.wav16");
