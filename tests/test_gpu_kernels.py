@@ -22,12 +22,11 @@ def S():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def bf16_close(out, ref, rel=2 ** -9, abs_=2e-3, mid=None):
+def half_close(out, ref, rel=2 ** -9, abs_=2e-3, mid=None):
     """Tolerance of the 16-bit path.  Activations are fp16 (11 significant bits, half-ulp 2^-12
     relative); the staged epilogue rounds the GEMM tile to fp16, then taps / bias / residual / scale
     each round once more (packed half2 arithmetic), and the half2 ELU carries <= 1e-3 absolute error
-    on its (-1, 0] branch: rel = 2^-9 and abs >= 2e-3 cover that chain with margin (and are still 2x
-    tighter than the bf16 tolerance this helper was first written for, hence the name)."""
+    on its (-1, 0] branch: rel = 2^-9 and abs >= 2e-3 cover that chain with margin."""
     err = (out.float() - ref).abs()
     tol = rel * ref.abs() + abs_
     if mid is not None:          # fp16 rounding of the staged accumulator, before bias / residual
@@ -75,9 +74,9 @@ def test_gemm_tcgen05(M, N, K, bias, res, act):
     if res:
         ref = ref + R.double()
     ref = ref.float()
-    bf16_close(out, ref, mid=acc.float())
+    half_close(out, ref, mid=acc.float())
     if act:
-        bf16_close(outa, F.elu(ref * 0.8), abs_=3e-3, mid=acc.float())
+        half_close(outa, F.elu(ref * 0.8), abs_=3e-3, mid=acc.float())
 
 
 def test_gemm_fp16_operands():
@@ -90,7 +89,7 @@ def test_gemm_fp16_operands():
     rc = _lib().wv_op_gemm(P(A), K, P(W), K, M, N, K, None, None, P(out), None, 1.0, 1, S())
     assert rc == 0, _lib().wv_last_error()
     torch.cuda.synchronize()
-    bf16_close(out, (A.double() @ W.double().t()).float())
+    half_close(out, (A.double() @ W.double().t()).float())
 
 
 def _cl(x):  # [B,C,T] fp32 -> channels-last fp16 [B,T,C]
@@ -121,9 +120,9 @@ def test_dw5(B, T, C, mode):
         ref = ref + rin.float().cpu().transpose(1, 2)
     ref = ref.transpose(1, 2)
     if out_raw is not None:
-        bf16_close(out_raw.cpu(), ref)
+        half_close(out_raw.cpu(), ref)
     if out_act is not None:
-        bf16_close(out_act.cpu(), F.elu(ref * 0.7), abs_=2e-3)
+        half_close(out_act.cpu(), F.elu(ref * 0.7), abs_=2e-3)
 
 
 @pytest.mark.parametrize("B,Tin,C,r", [(2, 1000, 128, 2), (1, 16001, 64, 4), (3, 401, 256, 5), (2, 77, 1024, 8), (1, 3, 64, 8)])
@@ -155,8 +154,8 @@ def test_down_conv_film(B, Tin, C, r, film):
         bet = ft[:, 1, :, 1].repeat_interleave(C // 4, dim=1).unsqueeze(-1)
         ref = ref * gam + bet
     ref = ref.transpose(1, 2)
-    bf16_close(out_raw.cpu(), ref, abs_=2e-3)
-    bf16_close(out_act.cpu(), F.elu(ref * 0.9), abs_=3e-3)
+    half_close(out_raw.cpu(), ref, abs_=2e-3)
+    half_close(out_act.cpu(), F.elu(ref * 0.9), abs_=3e-3)
 
 
 def C_void(t):
@@ -178,7 +177,7 @@ def test_up_conv_transposed(B, Tin, C, r):
     torch.cuda.synchronize()
     xq = xin.float().cpu().transpose(1, 2)
     ref = F.conv_transpose1d(xq, w, None, stride=r, groups=C)[..., : Tin * r]   # modules/conv.py:838-874
-    bf16_close(out.cpu(), ref.transpose(1, 2), abs_=2e-3)
+    half_close(out.cpu(), ref.transpose(1, 2), abs_=2e-3)
 
 
 @pytest.mark.parametrize("B,T,N,K", [(2, 1000, 64, 64), (1, 50, 1536, 128), (3, 401, 96, 96), (2, 124, 256, 256),
@@ -207,8 +206,8 @@ def test_gemm_with_fused_depthwise_epilogue(B, T, N, K, mode):
     mid = F.conv1d(F.pad(G.abs().transpose(1, 2), (4, 0)), dw.abs(), None, groups=N).transpose(1, 2)
     if R is not None:
         ref = ref + R.float().cpu()
-        bf16_close(out_raw.cpu(), ref, abs_=4e-3, mid=mid)
-    bf16_close(out_act.cpu(), F.elu(ref * 0.75), abs_=4e-3, mid=mid)
+        half_close(out_raw.cpu(), ref, abs_=4e-3, mid=mid)
+    half_close(out_act.cpu(), F.elu(ref * 0.75), abs_=4e-3, mid=mid)
 
 
 @pytest.mark.parametrize("B,T,C", [(2, 1000, 64), (1, 120, 96), (3, 401, 96), (1, 7, 32), (2, 16000, 96), (5, 241, 64),
@@ -248,6 +247,6 @@ def test_fused_resblock(B, T, C, mode):
     # <= 1e-3 absolute error of the half2 ELU on its exponential branch, pushed through |W2| and the taps
     mag = (dw5((h.abs() @ W2.double().abs().t()), dw2.double().abs(), None)).float()
     if out_raw is not None:
-        bf16_close(out_raw.cpu(), ref, rel=2 ** -9, abs_=6e-3, mid=mag * 0.5)
+        half_close(out_raw.cpu(), ref, rel=2 ** -9, abs_=6e-3, mid=mag * 0.5)
     if out_act is not None:
-        bf16_close(out_act.cpu(), F.elu(ref * s_act), rel=2 ** -9, abs_=6e-3, mid=mag * 0.5)
+        half_close(out_act.cpu(), F.elu(ref * s_act), rel=2 ** -9, abs_=6e-3, mid=mag * 0.5)
