@@ -116,6 +116,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
+long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
 int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
 bool g_phased_stft = true;  // hop < 8 STFTs read frames through phased strided TMA views (WV_PHASED_STFT=0: frame matrix)
 bool g_evict_first = true;  // A operand TMA loads carry an L2 evict_first hint (WV_EVICT_FIRST=0 disables)
@@ -141,6 +142,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_PHASED_STFT")) g_phased_stft = atoi(e) != 0;
   if (const char* e = getenv("WV_EVICT_FIRST")) g_evict_first = atoi(e) != 0;
@@ -455,6 +457,16 @@ struct Op {
   size_t out_bytes[2] = {0, 0};
 };
 
+// A small (launch-bound) plan is captured once per I/O signature into a CUDA graph whose kernels
+// read and write library-owned I/O buffers; a call then is: copy inputs in, one graph launch, copy
+// outputs out (single-clip latency 2.0 ms -> see DESIGN.md).
+struct PlanGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint8_t* mem = nullptr;
+  IoPtrs io;                         // the library-owned buffers inside `mem`
+  size_t bytes[14] = {0};
+};
 struct Plan {
   int B = 0, T = 0;
   std::vector<Op> ops;
@@ -462,6 +474,14 @@ struct Plan {
   size_t ws_bytes = 0;
   Buf latent;          // h16 [B*F, dim]
   int F = 0;
+  std::map<uint32_t, PlanGraph> graphs;   // keyed by the set of non-null I/O pointers
+  ~Plan() {
+    for (auto& kv : graphs) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+      if (kv.second.mem) cudaFree(kv.second.mem);
+    }
+  }
 };
 
 struct PlanCtx {
@@ -743,7 +763,9 @@ struct wv_net {
   long long chunk_samples = 0;
   bool profile = false;
   const Plan* last_plan = nullptr;   // plan whose events hold the last profiled run
+  cudaStream_t cap_stream = nullptr; // capture stream for the small-batch CUDA graphs
   ~wv_net() {
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (auto& kv : plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
     for (auto& kv : dec_plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
     if (ws) cudaFree(ws);
@@ -1483,6 +1505,51 @@ int wv_net_set_chunk(wv_net* net, int max_clip_samples) {
   return WV_OK;
 }
 
+// Run `plan` through a CUDA graph (captured on first use for this set of requested outputs).
+static void run_plan_graph(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st) {
+  const int B = plan.B, T = plan.T, nb = n.cfg.nbits;
+  const size_t BT = static_cast<size_t>(B) * T;
+  // field order: x msg presence | wm y latent logits bits avg conf valid mask probs
+  const void* user[13] = {io.x, io.msg, io.presence, io.wm, io.y, io.latent, io.logits, io.bits, io.avg, io.conf, io.valid, io.mask, io.probs};
+  const size_t sizes[13] = {BT * 4, static_cast<size_t>(B) * n.cfg.msg_dimension * 4, BT, BT * 4, BT * 4,
+                            static_cast<size_t>(B) * n.enc.dim * plan.F * 4, BT * nb * 4, static_cast<size_t>(B) * nb,
+                            static_cast<size_t>(B) * nb * 4, static_cast<size_t>(B) * 4, static_cast<size_t>(B) * nb, BT, BT * 4};
+  uint32_t key = 0;
+  for (int i = 0; i < 13; ++i) if (user[i]) key |= 1u << i;
+  PlanGraph& pg = plan.graphs[key];
+  if (pg.exec == nullptr) {
+    size_t total = 0, off[13];
+    for (int i = 0; i < 13; ++i) { off[i] = total; if (user[i]) total += round_up(sizes[i], 256); }
+    CK(cudaMalloc(reinterpret_cast<void**>(&pg.mem), std::max<size_t>(total, 256)));
+    auto at = [&](int i) -> uint8_t* { return user[i] ? pg.mem + off[i] : nullptr; };
+    pg.io.x = reinterpret_cast<const float*>(at(0)); pg.io.msg = reinterpret_cast<const float*>(at(1));
+    pg.io.presence = at(2); pg.io.wm = reinterpret_cast<float*>(at(3)); pg.io.y = reinterpret_cast<float*>(at(4));
+    pg.io.latent = reinterpret_cast<float*>(at(5)); pg.io.logits = reinterpret_cast<float*>(at(6)); pg.io.bits = at(7);
+    pg.io.avg = reinterpret_cast<float*>(at(8)); pg.io.conf = reinterpret_cast<float*>(at(9)); pg.io.valid = at(10);
+    pg.io.mask = at(11); pg.io.probs = reinterpret_cast<float*>(at(12));
+    for (int i = 0; i < 13; ++i) pg.bytes[i] = user[i] ? sizes[i] : 0;
+    if (!n.cap_stream) CK(cudaStreamCreateWithFlags(&n.cap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamBeginCapture(n.cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      run_plan(n, plan, pg.io, n.cap_stream);
+    } catch (...) {
+      cudaGraph_t dead = nullptr;
+      cudaStreamEndCapture(n.cap_stream, &dead);
+      if (dead) cudaGraphDestroy(dead);
+      throw;
+    }
+    CK(cudaStreamEndCapture(n.cap_stream, &pg.graph));
+    CK(cudaGraphInstantiate(&pg.exec, pg.graph, 0));
+  }
+  const void* internal[13] = {pg.io.x, pg.io.msg, pg.io.presence, pg.io.wm, pg.io.y, pg.io.latent, pg.io.logits, pg.io.bits,
+                              pg.io.avg, pg.io.conf, pg.io.valid, pg.io.mask, pg.io.probs};
+  for (int i = 0; i < 3; ++i)
+    if (user[i]) CK(cudaMemcpyAsync(const_cast<void*>(internal[i]), user[i], pg.bytes[i], cudaMemcpyDeviceToDevice, st));
+  CK(cudaGraphLaunch(pg.exec, st));
+  for (int i = 3; i < 13; ++i)
+    if (user[i]) CK(cudaMemcpyAsync(const_cast<void*>(user[i]), internal[i], pg.bytes[i], cudaMemcpyDeviceToDevice, st));
+}
+
 static int forward_common(wv_net* net, int B, int T, const IoPtrs& io0, cudaStream_t st) {
   return guarded([&] {
     DeviceGuard dg(net->device);
@@ -1510,7 +1577,10 @@ static int forward_common(wv_net* net, int B, int T, const IoPtrs& io0, cudaStre
       if (io.presence) io.presence += so;
       if (io.mask) io.mask += so;
       if (io.probs) io.probs += so;
-      run_plan(*net, plan, io, st);
+      if (bn == B && !net->profile && g_graph_max_samples > 0 && static_cast<long long>(B) * T <= g_graph_max_samples)
+        run_plan_graph(*net, plan, io, st);
+      else
+        run_plan(*net, plan, io, st);
     }
   });
 }
