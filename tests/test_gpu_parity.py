@@ -49,9 +49,11 @@ def check_wave(ref, got, what):
     assert np.abs(ref - got).max() <= 4e-4, f"{what}: max-abs {np.abs(ref - got).max()}"
 
 
-def check_bits(avg_ref, bits_ref, avg, bits):
-    assert np.abs(avg - avg_ref).max() <= 2e-4
-    safe = np.abs(avg_ref - 0.5) > 3e-4
+def check_bits(avg_ref, bits_ref, avg, bits, tol=2e-4):
+    """tol: bound on |avg - avg_ref|.  2e-4 holds for clips of >= 0.25 s (the time-mean averages the
+    per-sample logit error); very short clips are bounded by the logit error itself (0.25 * 0.008)."""
+    assert np.abs(avg - avg_ref).max() <= tol
+    safe = np.abs(avg_ref - 0.5) > 1.5 * tol
     assert (bits == bits_ref)[safe].all()
 
 
@@ -258,3 +260,33 @@ def test_large_batch_config2_shapes_and_sanity():
     safe = (avg - 0.5).abs() > 1e-5
     assert bool(((avg >= 0.5).to(torch.uint8) == d["bits"])[safe].all())
     np.testing.assert_allclose(d["conf"].cpu().numpy(), avg.mean(dim=1).cpu().numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (1, 319), (3, 321), (2, 640), (1, 1919), (2, 7777), (5, 960),
+                                 (1, 33333), (40, 480)])
+def test_cuda_path_matches_oracle_ragged_shapes(B, T):
+    """Tile / hop / chunk boundaries: clips shorter than one hop, one frame, T = k*hop +- 1, batches that
+    take the CUDA-graph path and ones that do not; every output against the oracle."""
+    m = models(False, 0)
+    dev = torch.device("cuda:0")
+    rng = np.random.RandomState(B * 1000 + T)
+    x = torch.from_numpy((0.1 * rng.standard_normal((B, 1, T))).astype(np.float32))
+    msg = torch.from_numpy(rng.randint(0, 2, (B, 16)).astype(np.int64))
+    with torch.no_grad():
+        wm_o = O.generator_forward(x, msg, m["generator"][1], m["generator"][2])
+    for rep in range(2):                       # second pass: cached plan / instantiated graph
+        wm, y, _ = m["generator"][0].embed_batch(x.to(dev), msg.to(dev))
+        assert snr_db(wm_o.numpy(), wm.cpu().numpy()) >= 46.0
+        assert torch.equal(y.cpu(), x + wm.cpu())
+    yc = y.cpu()
+    with torch.no_grad():
+        lg_o = O.detector_forward(yc, m["detector"][1], m["detector"][2])
+        ll_o = O.locator_forward(yc, m["locator"][1], m["locator"][2])
+    bits_o, avg_o, _, _ = O.decode_bits(lg_o)
+    for rep in range(2):
+        d = m["detector"][0].detect_batch(y, want_logits=True)
+        l = m["locator"][0].locate_batch(y, want_logits=True)
+        assert snr_db(lg_o.numpy(), d["logits"].cpu().numpy()) >= 50.0
+        assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 50.0
+        check_bits(avg_o.numpy(), bits_o.numpy(), d["avg"].cpu().numpy(), d["bits"].cpu().numpy(), tol=2e-4 if T >= 4000 else 2e-3)
+        check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy())
