@@ -79,6 +79,7 @@ struct GemmArgs {
   int N, K;
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
+  int stage_bufs;     // STAGED: staging tiles (2; 1 for long-K layers, whose ring gets the space instead)
   int kb_split;       // > 0: k-blocks >= kb_split re-read the A rows shifted by one (row r-1) at k - kb_split*64:
                       //      [a[i] | a[i-1]] contraction of the fused transposed-conv + 1x1 (decoder upsample)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
@@ -126,22 +127,22 @@ __host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n 
 // Shared-memory plan.  With resident_b the CTA's whole W tile (num_kb k-blocks) is loaded once and the
 // ring stages hold A k-blocks only (16 KB each): the ring then covers 4-5 tiles of loads in flight
 // instead of 3, which is what bounds the small-K layers (TMA issue -> data is ~8 000 cycles under load).
-__host__ inline int gemm_fixed_smem(int block_n, bool staged) {
-  return 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + STAGE_BUFS * BM * staged_pitch_bytes(block_n) : 0);
+__host__ inline int gemm_fixed_smem(int block_n, bool staged, int stage_bufs = STAGE_BUFS) {
+  return 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + stage_bufs * BM * staged_pitch_bytes(block_n) : 0);
 }
 __host__ inline bool gemm_resident_b(int block_n, int num_kb, bool staged, bool nt_fixed) {
   const int w_bytes = num_kb * block_n * BK * 2;
   return nt_fixed && w_bytes <= 64 * 1024 &&
          (GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged) - w_bytes) / A_STAGE_BYTES >= 4;
 }
-__host__ inline int gemm_stage_count(int block_n, bool staged, int num_kb = 0, bool resident = false) {
-  const int avail = GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged);
+__host__ inline int gemm_stage_count(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS) {
+  const int avail = GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged, stage_bufs);
   int s = resident ? (avail - num_kb * block_n * BK * 2) / A_STAGE_BYTES : avail / (A_STAGE_BYTES + block_n * BK * 2);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
-__host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bool resident = false) {
-  const int s = gemm_stage_count(block_n, staged, num_kb, resident);
-  return gemm_fixed_smem(block_n, staged) +
+__host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS) {
+  const int s = gemm_stage_count(block_n, staged, num_kb, resident, stage_bufs);
+  return gemm_fixed_smem(block_n, staged, stage_bufs) +
          (resident ? s * A_STAGE_BYTES + num_kb * block_n * BK * 2 : s * (A_STAGE_BYTES + block_n * BK * 2));
 }
 
@@ -366,8 +367,8 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     if (et == 0) WV_DBG(6, dbg_it);
     if (lane == 0) WV_DBG(12 + (et >> 5), dbg_it);   // per math warp: end
     ++dbg_it;
-    if (--tiles_left >= STAGE_BUFS) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);   // tile sb may be refilled
-    if (++sb == STAGE_BUFS) sb = 0;
+    if (--tiles_left >= g.stage_bufs) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);   // tile sb may be refilled
+    if (++sb == g.stage_bufs) sb = 0;
   }
 }
 
@@ -460,8 +461,8 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
       }
     }
     __syncwarp();
-    if (--tiles_left >= STAGE_BUFS) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);
-    if (++sb == STAGE_BUFS) sb = 0;
+    if (--tiles_left >= g.stage_bufs) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);
+    if (++sb == g.stage_bufs) sb = 0;
   }
 }
 
@@ -618,7 +619,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t as_phase = 0;
       uint32_t v[32];
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        if (it >= STAGE_BUFS) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
+        if (it >= g.stage_bufs) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
         mbar_wait(&acc_full[as], as_phase);
         if (q == 0 && lane == 0) WV_DBG(3, it);
         if (lane == 0) WV_DBG(36 + q, it);           // per drain warp: start
@@ -644,7 +645,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) WV_DBG(8 + q, it);            // per drain warp: end
         named_bar_arrive(BAR_ST_FULL + sb, EPI_THREADS);   // release: this warp's 32 rows are staged
         if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
-        if (++sb == STAGE_BUFS) sb = 0;
+        if (++sb == g.stage_bufs) sb = 0;
       }
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global

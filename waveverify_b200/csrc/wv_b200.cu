@@ -117,6 +117,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
+int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
 int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
 bool g_phased_stft = true;  // hop < 8 STFTs read frames through phased strided TMA views (WV_PHASED_STFT=0: frame matrix)
 bool g_evict_first = true;  // A operand TMA loads carry an L2 evict_first hint (WV_EVICT_FIRST=0 disables)
@@ -143,6 +144,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
+  if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
   if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_PHASED_STFT")) g_phased_stft = atoi(e) != 0;
   if (const char* e = getenv("WV_EVICT_FIRST")) g_evict_first = atoi(e) != 0;
@@ -541,9 +543,12 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   const bool nt_fixed = tiles_n_ <= g_num_sms;   // the grid is rounded down to a multiple of tiles_n below
   const bool resident = gemm_resident_b(w.block_n, num_kb, staged, nt_fixed);
   g.resident_b = resident ? 1 : 0;
-  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident);
+  // long-K layers (>= g_one_buf_kb k-blocks per tile, W streamed) could run with one staging tile and a deeper
+  // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
+  g.stage_bufs = (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb) ? 1 : STAGE_BUFS;
+  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs);
   if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
-  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident);
+  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs);
   if (custom_tmA) {
     g.rows_per_clip = rows_per_clip;
     g.n_clips = n_clips;
@@ -587,8 +592,8 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   if (g.resident_b && op.grid > g.tiles_n) op.grid -= op.grid % g.tiles_n;   // every CTA keeps one n tile
   if (g.resident_b && op.grid < g.tiles_n) {   // fewer tiles than n tiles: stream W through the ring
     g.resident_b = 0;
-    g.stages = gemm_stage_count(w.block_n, staged, num_kb, false);
-    op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false);
+    g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs);
+    op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs);
     op.g = g;
   }
   {
