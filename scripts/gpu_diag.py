@@ -22,17 +22,17 @@ S = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 def gemm_case(M, N, K, bias, res, act, fp16=False):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
-    dt = torch.float16 if fp16 else torch.bfloat16
+    dt = torch.float16 if fp16 else torch.float16
     lda = (K + 7) // 8 * 8
     A = torch.zeros(M, lda, dtype=dt); A[:, :K] = torch.randn(M, K, generator=g).to(dt)
     W = torch.zeros(N, lda, dtype=dt); W[:, :K] = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt)
     b = torch.randn(N, generator=g) if bias else None
-    R = torch.randn(M, N, generator=g).to(torch.bfloat16) if res else None
+    R = torch.randn(M, N, generator=g).to(torch.float16) if res else None
     A, W = A.to(dev), W.to(dev)
     b = b.to(dev) if bias else None
     R = R.to(dev) if res else None
-    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
-    outa = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if act else None
+    out = torch.empty(M, N, dtype=torch.float16, device=dev)
+    outa = torch.empty(M, N, dtype=torch.float16, device=dev) if act else None
     rc = L.wv_op_gemm(P(A), lda, P(W), lda, M, N, K, P(b), P(R), P(out), P(outa), 0.8, int(fp16), S())
     torch.cuda.synchronize()
     if rc != 0:

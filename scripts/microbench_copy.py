@@ -12,7 +12,7 @@ def timeit(fn, reps=10):
     return min(ts) * 1e3
 for mb in (32, 65, 131, 262, 524, 1048, 2097):
     n = mb * 1000 * 1000 // 2
-    a = torch.randn(n, device=dev).to(torch.bfloat16); b = torch.empty_like(a)
+    a = torch.randn(n, device=dev).to(torch.float16); b = torch.empty_like(a)
     t = timeit(lambda: b.copy_(a))
     t2 = timeit(lambda: b.zero_())
     t3 = timeit(lambda: a.sum())

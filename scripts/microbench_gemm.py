@@ -28,13 +28,13 @@ def timeit(fn, reps=10):
 
 
 for (B, T, Cc) in [(64, 16000, 64), (64, 16000, 96), (64, 8000, 128), (64, 8000, 192), (64, 2000, 256), (64, 2000, 384), (64, 400, 768)]:
-    A = torch.randn(B, T, Cc, device=dev).to(torch.bfloat16)
-    W = (torch.randn(Cc, Cc, device=dev) / Cc ** 0.5).to(torch.bfloat16)
+    A = torch.randn(B, T, Cc, device=dev).to(torch.float16)
+    W = (torch.randn(Cc, Cc, device=dev) / Cc ** 0.5).to(torch.float16)
     dw = torch.randn(5, Cc, device=dev) * 0.3
     bias = torch.randn(Cc, device=dev)
-    R = torch.randn(B, T, Cc, device=dev).to(torch.bfloat16)
-    o1 = torch.empty(B, T, Cc, device=dev, dtype=torch.bfloat16)
-    o2 = torch.empty(B, T, Cc, device=dev, dtype=torch.bfloat16)
+    R = torch.randn(B, T, Cc, device=dev).to(torch.float16)
+    o1 = torch.empty(B, T, Cc, device=dev, dtype=torch.float16)
+    o2 = torch.empty(B, T, Cc, device=dev, dtype=torch.float16)
     M = B * T
     mb = M * Cc * 2 / 1e6
     t_plain_raw = timeit(lambda: L.wv_op_gemm(P(A), Cc, P(W), Cc, M, Cc, Cc, None, None, P(o1), None, 1.0, 0, S()))

@@ -202,7 +202,7 @@ def test_gemm_with_fused_depthwise_epilogue(B, T, N, K, mode):
     G = (A.double() @ W.double().t()).to(torch.float16).float().cpu()      # the kernel stages the GEMM tile in fp16
     ref = F.conv1d(F.pad(G.transpose(1, 2), (4, 0)), dw, b, groups=N).transpose(1, 2)
     # a staged element may round the other way than the emulation (fp32 summation order): bound by
-    # one fp16 ulp of |G| pushed through |w| (bound kept at the bf16 size)
+    # one fp16 ulp of |G| pushed through |w| (bound kept generous)
     mid = F.conv1d(F.pad(G.abs().transpose(1, 2), (4, 0)), dw.abs(), None, groups=N).transpose(1, 2)
     if R is not None:
         ref = ref + R.float().cpu()

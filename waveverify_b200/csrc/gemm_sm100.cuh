@@ -146,12 +146,6 @@ __host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bo
          (resident ? s * A_STAGE_BYTES + num_kb * block_n * BK * 2 : s * (A_STAGE_BYTES + block_n * BK * 2));
 }
 
-// ELU(alpha=1): x > 0 ? x : e^x - 1 with one MUFU.EX2 (abs error ~1e-7, far below bf16 output ulp)
-__device__ __forceinline__ float elu_fast(float x) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-  return x > 0.f ? x : e - 1.f;
-}
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
