@@ -48,7 +48,8 @@ constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int ACC_STAGES = 2;
+constexpr int ACC_STAGES = 2;               // accumulator stages of MAX_BN columns; pair mode: 4 stages of 128 columns
+constexpr int MAX_ACC_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 16;               // L2NORM / STFT / HEAD epilogues (640-thread CTA)
 constexpr int EPI_SPLIT = EPI_WARPS / 4;    // warps sharing one TMEM lane quarter split the columns
@@ -80,6 +81,9 @@ struct GemmArgs {
   int block_n;
   int stages;         // smem ring depth (host computed from block_n)
   int stage_bufs;     // STAGED: staging tiles (2; 1 for long-K layers, whose ring gets the space instead)
+  int pair;           // 1: two M tiles (same n tile) share every W k-block: one ring stage = 2 A tiles + 1 W tile,
+                      //    four 128-column accumulator stages (long-K layers are bound by L2 -> SM operand traffic)
+  int acc_stages, acc_cols;
   int kb_split;       // > 0: k-blocks >= kb_split re-read the A rows shifted by one (row r-1) at k - kb_split*64:
                       //      [a[i] | a[i-1]] contraction of the fused transposed-conv + 1x1 (decoder upsample)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
@@ -135,15 +139,19 @@ __host__ inline bool gemm_resident_b(int block_n, int num_kb, bool staged, bool 
   return nt_fixed && w_bytes <= 64 * 1024 &&
          (GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged) - w_bytes) / A_STAGE_BYTES >= 4;
 }
-__host__ inline int gemm_stage_count(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS) {
+__host__ inline int gemm_stage_count(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS,
+                                     bool pair = false) {
   const int avail = GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged, stage_bufs);
-  int s = resident ? (avail - num_kb * block_n * BK * 2) / A_STAGE_BYTES : avail / (A_STAGE_BYTES + block_n * BK * 2);
+  const int a_bytes = pair ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
+  int s = resident ? (avail - num_kb * block_n * BK * 2) / a_bytes : avail / (a_bytes + block_n * BK * 2);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
-__host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS) {
-  const int s = gemm_stage_count(block_n, staged, num_kb, resident, stage_bufs);
+__host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS,
+                                    bool pair = false) {
+  const int s = gemm_stage_count(block_n, staged, num_kb, resident, stage_bufs, pair);
+  const int a_bytes = pair ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
   return gemm_fixed_smem(block_n, staged, stage_bufs) +
-         (resident ? s * A_STAGE_BYTES + num_kb * block_n * BK * 2 : s * (A_STAGE_BYTES + block_n * BK * 2));
+         (resident ? s * a_bytes + num_kb * block_n * BK * 2 : s * (a_bytes + block_n * BK * 2));
 }
 
 template <int N>
@@ -183,22 +191,54 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
   return t;
 }
 
-// Walks the CTA's tiles l = blockIdx.x, blockIdx.x + gridDim.x, ...; with g.reverse the l-th tile is
-// num_tiles-1-l, so that a kernel starts on the rows the previous kernel of the plan wrote last
-// (they are still in L2) - consecutive launches of a plan alternate the direction.
-__device__ __forceinline__ int phys_tile(const GemmArgs& g, int l) { return g.reverse ? g.num_tiles - 1 - l : l; }
-struct TileWalker {
-  int tile, clip, mi, nt;      // tile = logical index l
-  __device__ __forceinline__ TileWalker(const GemmArgs& g) : tile(blockIdx.x), clip(0), mi(0), nt(0) { set(g); }
-  __device__ __forceinline__ void set(const GemmArgs& g) {
-    if (tile < g.num_tiles) {
-      const TileCoord t = tile_coord(g, phys_tile(g, tile));
-      clip = t.clip; mi = t.mi; nt = t.nt;
-    }
+// The k-th tile of this CTA (physical tile index, -1 if that slot is empty, done when the CTA has no more).
+// Unpaired: l = blockIdx.x + k*gridDim.x.  Pair mode: the CTA walks UNITS u = blockIdx.x + (k>>1)*gridDim.x of
+// two M tiles with the same n tile, u -> (mp, nt), tile = (2*mp + (k&1))*tiles_n + nt; with an odd number of
+// M tiles the second half of the last units does not exist.  With g.reverse the order is walked from the end,
+// so that a kernel starts on the rows the previous kernel of the plan wrote last (still in L2).
+__device__ __forceinline__ int seq_tile(const GemmArgs& g, int k, bool& done) {
+  if (!g.pair) {
+    const int l = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+    done = l >= g.num_tiles;
+    return done ? -1 : (g.reverse ? g.num_tiles - 1 - l : l);
   }
+  const int tiles_m = g.tiles_m_per_clip * g.n_clips;
+  const int num_units = ((tiles_m + 1) >> 1) * g.tiles_n;
+  int u = static_cast<int>(blockIdx.x) + (k >> 1) * static_cast<int>(gridDim.x);
+  done = u >= num_units;
+  if (done) return -1;
+  if (g.reverse) u = num_units - 1 - u;
+  int mp, nt;
+  if (g.tiles_n == 1) { mp = u; nt = 0; }
+  else fast_divmod(static_cast<uint32_t>(u), static_cast<uint32_t>(g.tiles_n), g.magic_n, mp, nt);
+  const int mt = 2 * mp + (k & 1);
+  return mt < tiles_m ? mt * g.tiles_n + nt : -1;
+}
+__device__ __forceinline__ int cta_tile_count(const GemmArgs& g) {
+  int n = 0;
+  for (int k = 0;; ++k) {
+    bool done;
+    const int l = seq_tile(g, k, done);
+    if (done) break;
+    n += l >= 0;
+  }
+  return n;
+}
+struct TileWalker {
+  int k, tile, clip, mi, nt;   // tile = physical index, num_tiles when the CTA is done
+  __device__ __forceinline__ TileWalker(const GemmArgs& g) : k(-1), tile(0), clip(0), mi(0), nt(0) { next(g); }
   __device__ __forceinline__ void next(const GemmArgs& g) {
-    tile += gridDim.x;
-    set(g);
+    for (;;) {
+      ++k;
+      bool done;
+      const int l = seq_tile(g, k, done);
+      if (done) { tile = g.num_tiles; return; }
+      if (l < 0) continue;
+      tile = l;
+      const TileCoord t = tile_coord(g, l);
+      clip = t.clip; mi = t.mi; nt = t.nt;
+      return;
+    }
   }
 };
 
@@ -294,7 +334,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   int cached_nt = -1;
   __half2 wt[TAPS][2], bs[2];
   int sb = 0;
-  int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  int tiles_left = cta_tile_count(g);
   int dbg_it = 0;
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
@@ -391,7 +431,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   __half2 bs2[2];
   const __half2 s2 = h2_from(s_act, s_act);
   int sb = 0;
-  int tiles_left = (g.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  int tiles_left = cta_tile_count(g);
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int c = tc.nt * g.block_n + cg * 4;
     if (tc.nt != cached_nt) {                                      // (re)stage taps for this N tile
@@ -490,16 +530,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int b_stage_bytes = g.block_n * BK * 2;
+  const int a_stage_bytes = g.pair ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
   uint8_t* smemA = smem;
-  uint8_t* smemB = smem + g.stages * A_STAGE_BYTES;
+  uint8_t* smemB = smem + g.stages * a_stage_bytes;
   const int num_kb = (g.K + BK - 1) / BK;
   uint8_t* after = smemB + (g.resident_b ? num_kb : g.stages) * b_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
   uint64_t* full = bars;                          // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;            // [MAX_STAGES]
-  uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [ACC_STAGES]
-  uint64_t* acc_empty = acc_full + ACC_STAGES;
-  uint64_t* w_full = acc_empty + ACC_STAGES;      // resident W tile landed
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;     // [MAX_ACC_STAGES]
+  uint64_t* acc_empty = acc_full + MAX_ACC_STAGES;
+  uint64_t* w_full = acc_empty + MAX_ACC_STAGES;  // resident W tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   uint8_t* down_w = after + GEMM_BAR_BYTES;       // [2r][block_n] fp32 (STAGED down-conv only)
   uint8_t* stage_tiles = down_w + DOWN_W_BYTES;   // [STAGE_BUFS][BM][pitch] fp16 (STAGED only)
@@ -511,6 +552,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int halo = g.tile_halo;
   const int rows_out = g.tile_stride;
   const uint32_t stage_bytes = static_cast<uint32_t>(A_STAGE_BYTES + (g.resident_b ? 0 : b_stage_bytes));
+  const int acc_stages = g.acc_stages, acc_cols = g.acc_cols;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -522,7 +564,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&empty[i], 1);
     }
     mbar_init(w_full, 1);
-    for (int i = 0; i < ACC_STAGES; ++i) {
+    for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : EPI_WARPS);  // one arrive per draining warp
     }
@@ -546,10 +588,36 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int dbg_it = 0;
       const uint64_t pol = l2_policy_evict_first();
       if (g.resident_b) {   // the n tile of a CTA is fixed (grid is a multiple of tiles_n): load W once
-        const int n_fixed = tile_coord(g, phys_tile(g, blockIdx.x)).nt * g.block_n;
+        bool d0;
+        const int n_fixed = tile_coord(g, seq_tile(g, 0, d0)).nt * g.block_n;
         mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(num_kb * b_stage_bytes));
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smemB + kb * b_stage_bytes, &tmB, w_full, kb * BK, n_fixed);
       }
+      if (g.pair) {
+        // one ring stage = the k-block of TWO M tiles (same n tile) + the W k-block they share
+        for (int ku = 0;; ++ku) {
+          bool done, d1;
+          const int l0 = seq_tile(g, 2 * ku, done);
+          if (done) break;
+          const int l1 = seq_tile(g, 2 * ku + 1, d1);
+          const TileCoord t0 = tile_coord(g, l0);
+          const TileCoord t1 = l1 >= 0 ? tile_coord(g, l1) : t0;
+          const int ra = t0.mi * rows_out - halo, rb = t1.mi * rows_out - halo;
+          const int n0 = t0.nt * g.block_n;
+          const uint32_t bytes = static_cast<uint32_t>((l1 >= 0 ? 2 : 1) * A_STAGE_BYTES + b_stage_bytes);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            uint8_t* a0 = smemA + stage * a_stage_bytes;
+            const bool sh = g.kb_split > 0 && kb >= g.kb_split;      // [a[i] | a[i-1]] contraction (see kb_split)
+            const int kc = (sh ? kb - g.kb_split : kb) * BK;
+            tma_load_3d(a0, &tmA, &full[stage], kc, ra - (sh ? 1 : 0), t0.clip);
+            if (l1 >= 0) tma_load_3d(a0 + A_STAGE_BYTES, &tmA, &full[stage], kc, rb - (sh ? 1 : 0), t1.clip);
+            tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else
       for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++dbg_it) {
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
@@ -578,10 +646,48 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t as_phase = 0;
       int dbg_it = 0;
       if (g.resident_b) mbar_wait(w_full, 0);
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++dbg_it) {
+      if (g.pair) {
+        int c = 0;                                   // tiles issued so far: accumulator stage c % acc_stages
+        for (int ku = 0;; ++ku) {
+          bool done, d1;
+          seq_tile(g, 2 * ku, done);
+          if (done) break;
+          const int nv = seq_tile(g, 2 * ku + 1, d1) >= 0 ? 2 : 1;
+          const int s0 = c % acc_stages, s1 = (c + 1) % acc_stages;
+          mbar_wait(&acc_empty[s0], ((c / acc_stages) & 1) ^ 1);
+          if (nv == 2) mbar_wait(&acc_empty[s1], (((c + 1) / acc_stages) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + static_cast<uint32_t>(s0 * acc_cols), d1t = tmem_base + static_cast<uint32_t>(s1 * acc_cols);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(smemA + stage * a_stage_bytes));
+            const uint64_t adesc1 = make_sw128_kmajor_desc(smem_u32(smemA + stage * a_stage_bytes + A_STAGE_BYTES));
+            const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * b_stage_bytes));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_f16(d0, adesc0 + 2 * k, bdesc + 2 * k, g.idesc, (kb | k) ? 1u : 0u);
+            if (nv == 2) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16(d1t, adesc1 + 2 * k, bdesc + 2 * k, g.idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);
+            if (kb == num_kb - 1) {
+              umma_commit(&acc_full[s0]);
+              if (nv == 2) umma_commit(&acc_full[s1]);
+            }
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          }
+          c += nv;
+        }
+      } else
+      for (int k_ = 0;; ++k_, ++dbg_it) {
+        bool done;
+        const int l_ = seq_tile(g, k_, done);
+        if (done) break;
+        if (l_ < 0) continue;
         mbar_wait(&acc_empty[as], as_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * MAX_BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * acc_cols);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           if (kb == num_kb - 1) WV_DBG(1, dbg_it);
@@ -597,7 +703,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == num_kb - 1) { umma_commit(&acc_full[as]); WV_DBG(2, dbg_it); }
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
-        if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
+        if (++as == acc_stages) { as = 0; as_phase ^= 1; }
       }
     }
   } else if (EPI == EPI_STAGED && warp < 4) {
@@ -612,14 +718,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int as = 0, sb = 0, it = 0;
       uint32_t as_phase = 0;
       uint32_t v[32];
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      for (int k_ = 0;; ++k_) {
+        bool done;
+        const int l_ = seq_tile(g, k_, done);
+        if (done) break;
+        if (l_ < 0) continue;
         if (it >= g.stage_bufs) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
         mbar_wait(&acc_full[as], as_phase);
         if (q == 0 && lane == 0) WV_DBG(3, it);
         if (lane == 0) WV_DBG(36 + q, it);           // per drain warp: start
         tc_fence_after();
         const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * acc_cols);
         const uint32_t rowp = stage_u32 + sb * (BM * pitch) + (q * 32 + lane) * pitch;
         for (int c = 0; c < (WV_DBG_MODE(4) ? 0 : chunks); ++c) {
           tmem_ld32(taddr + c * 32, v);
@@ -638,8 +748,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (q == 0 && lane == 0) WV_DBG(4, it);
         if (lane == 0) WV_DBG(8 + q, it);            // per drain warp: end
         named_bar_arrive(BAR_ST_FULL + sb, EPI_THREADS);   // release: this warp's 32 rows are staged
-        if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
+        if (++as == acc_stages) { as = 0; as_phase ^= 1; }
         if (++sb == g.stage_bufs) sb = 0;
+        ++it;
       }
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global
@@ -661,8 +772,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int h = e >> 2;   // column split: this warp takes chunks c with c % EPI_SPLIT == h
     int as = 0;
     uint32_t as_phase = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(g, phys_tile(g, tile));
+    for (int k_ = 0;; ++k_) {
+      bool done;
+      const int l_ = seq_tile(g, k_, done);
+      if (done) break;
+      if (l_ < 0) continue;
+      const TileCoord tc = tile_coord(g, l_);
       const int nt = tc.nt, clip = tc.clip;
       const int r_base = tc.mi * rows_out;   // first OUTPUT row of the tile
       const int n0 = nt * g.block_n;
@@ -670,7 +785,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[as], as_phase);
       tc_fence_after();
       const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * MAX_BN);
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * acc_cols);
       uint32_t v[32];
 
       {
@@ -783,7 +898,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
-      if (++as == ACC_STAGES) { as = 0; as_phase ^= 1; }
+      if (++as == acc_stages) { as = 0; as_phase ^= 1; }
     }
   }
 

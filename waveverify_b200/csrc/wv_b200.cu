@@ -117,6 +117,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
+int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
 int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
 int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
 bool g_phased_stft = true;  // hop < 8 STFTs read frames through phased strided TMA views (WV_PHASED_STFT=0: frame matrix)
@@ -144,6 +145,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
+  if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
   if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
   if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_PHASED_STFT")) g_phased_stft = atoi(e) != 0;
@@ -546,9 +548,14 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   // long-K layers (>= g_one_buf_kb k-blocks per tile, W streamed) could run with one staging tile and a deeper
   // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
   g.stage_bufs = (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb) ? 1 : STAGE_BUFS;
-  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs);
+  // pair mode (two M tiles per W k-block) for the long-K layers whose W tile does not stay resident
+  const bool pair = staged && !resident && g.down_r == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
+  g.pair = pair ? 1 : 0;
+  g.acc_stages = pair ? MAX_ACC_STAGES : ACC_STAGES;
+  g.acc_cols = pair ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
+  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs, pair);
   if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
-  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs);
+  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs, pair);
   if (custom_tmA) {
     g.rows_per_clip = rows_per_clip;
     g.n_clips = n_clips;
@@ -589,6 +596,18 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.num_tiles = tiles;
   op.g = g;
   op.grid = std::min(tiles, g_num_sms);
+  if (g.pair) {
+    const long long units = (static_cast<long long>(g.tiles_m_per_clip) * g.n_clips + 1) / 2 * g.tiles_n;
+    if (units < 4LL * g_num_sms) {   // too few units: wave quantisation costs more than the shared W loads save
+      g.pair = 0;
+      g.acc_stages = ACC_STAGES; g.acc_cols = MAX_BN;
+      g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs, false);
+      op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs, false);
+      op.g = g;
+    } else {
+      op.grid = static_cast<int>(std::min<long long>(units, g_num_sms));
+    }
+  }
   if (g.resident_b && op.grid > g.tiles_n) op.grid -= op.grid % g.tiles_n;   // every CTA keeps one n tile
   if (g.resident_b && op.grid < g.tiles_n) {   // fewer tiles than n tiles: stream W through the ring
     g.resident_b = 0;
