@@ -341,6 +341,9 @@ def run_ours(a):
             roofline["peak_src"] = peaks["src"] + (" (sustained)" if roofline["bound"] == "tensor" else "")
             roofline["launches"] = c["launches"]
             roofline["avg_launch_us"] = round(1e3 * c["ms"] / max(1, c["launches"]), 2)
+            tp = os.path.join(ROOT, "profiles", "ncu_tensor_pipe.json")
+            if os.path.exists(tp):   # tensor-pipe utilisation of the largest launches, from the committed ncu capture
+                roofline["tensor_pipe_pct_ncu"] = {k: v for k, v in json.load(open(tp)).items() if not k.startswith("_")}
             roofline["alg_bytes_per_launch"] = round(1e6 * c["mb"] / max(1, c["launches"]))
             roofline["alg_gflop_per_launch"] = round(c["gflop"] / max(1, c["launches"]), 3)
             roofline["note"] = ("aggregate over all launches of this kernel in one step (profiled sub-batch x%d); "
