@@ -114,6 +114,8 @@ struct GemmArgs {
   // STFT
   float log_offset, inv_sigma, clamp_sq;
   int n_half;
+  int epi_groups;      // 2: narrow tiles (<= 64 columns): the 16 epilogue warps form two groups of 8, one per accumulator
+                       //    stage, so that two tiles are in the epilogue at once (it is latency-bound per tile)
   int phases;          // > 1: frames with hop < 8 samples read as `phases` interleaved 16-byte-strided views of
   int frames_per_clip; //      shifted waveform copies (4-D tensor map); "clip" = clip * phases + phase, row q = frame q*phases + phase
   // HEAD
@@ -566,7 +568,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(w_full, 1);
     for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : EPI_WARPS);  // one arrive per draining warp
+      mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : (EPI == EPI_STFT && g.epi_groups == 2 ? EPI_WARPS / 2 : EPI_WARPS));  // one arrive per draining warp
     }
     fence_mbar_init();
   }
@@ -769,7 +771,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ epilogue (16 warps)
     const int e = warp - 4;
     const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
-    const int h = e >> 2;   // column split: this warp takes chunks c with c % EPI_SPLIT == h
+    const bool two_groups = EPI == EPI_STFT && g.epi_groups == 2;
+    const int h = two_groups ? (e >> 2) & 1 : e >> 2;   // column split: this warp takes chunks c with c % split == h
+    const int split = two_groups ? 2 : EPI_SPLIT;
+    const int grp = e >> 3;                              // two_groups: group g owns accumulator stage g = every other tile
     int as = 0;
     uint32_t as_phase = 0;
     for (int k_ = 0;; ++k_) {
@@ -777,6 +782,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int l_ = seq_tile(g, k_, done);
       if (done) break;
       if (l_ < 0) continue;
+      if (two_groups && as != grp) {                     // the other group's tile (acc_stages == 2: stage = tile parity)
+        if (++as == acc_stages) { as = 0; as_phase ^= 1; }
+        continue;
+      }
       const TileCoord tc = tile_coord(g, l_);
       const int nt = tc.nt, clip = tc.clip;
       const int r_base = tc.mi * rows_out;   // first OUTPUT row of the tile
@@ -836,7 +845,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         } else if constexpr (EPI == EPI_STFT) {
-          for (int c = h; c < chunks; c += EPI_SPLIT) {
+          for (int c = h; c < chunks; c += split) {
             const int p0 = (n0 + c * 32) >> 1;
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();

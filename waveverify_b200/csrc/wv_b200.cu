@@ -117,6 +117,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
+bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
 int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
 int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
 int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
@@ -145,6 +146,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
+  if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e) != 0;
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
   if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
   if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
@@ -539,6 +541,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.block_n = w.block_n;
   g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
   const bool staged = epi == EPI_STAGED;
+  g.epi_groups = (epi == EPI_STFT && w.block_n <= 64 && g_epi_groups) ? 2 : 1;
   if (staged && g.taps != 1 && g.taps != 5) WV_THROW(WV_ERR_INVALID, "taps must be 1 or 5");
   const int num_kb = ceil_div(K, BK);
   const int tiles_n_ = w.N / w.block_n;
