@@ -861,8 +861,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
                 y[0] = (0.5f * __logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
                 const float yn = (0.5f * __logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
-                // bin N/2 plus the 7 zero pad columns (ldo = n_half + 8): one 16-byte store
+                // bin N/2 plus the zero pad columns up to the row pitch (ldo = n_half + 8 or + 16)
                 *reinterpret_cast<uint4*>(yp + g.n_half) = make_uint4(pack_act2(yn, 0.f), 0u, 0u, 0u);
+                if (g.ldo - g.n_half > 8) *reinterpret_cast<uint4*>(yp + g.n_half + 8) = make_uint4(0u, 0u, 0u, 0u);
               }
               uint4* op = reinterpret_cast<uint4*>(yp + p0);
 #pragma unroll

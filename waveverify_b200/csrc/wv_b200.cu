@@ -117,6 +117,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
+int g_ldy_align = 8;        // log-spectrogram row pitch in elements (WV_LDY_ALIGN: 8 = 16 B, 16 = 32 B = one DRAM sector per chunk)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
 int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
 int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
@@ -146,6 +147,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
+  if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e) != 0;
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
   if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
@@ -973,7 +975,7 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
   // row pitch of the log-spectrogram: next multiple of 8 elements (16 B, the TMA stride unit); pad
   // columns are written as zeros.  (A 64-byte-aligned pitch was measured: the 1x1 gains 10 % but the
   // STFT epilogue loses more to the extra pad stores.)
-  const int ldy = static_cast<int>(round_up(K2, 8));
+  const int ldy = static_cast<int>(round_up(K2, g_ldy_align));
   Buf Y = c.alloc(static_cast<size_t>(M) * ldy * 2);
   GemmArgs g;
   memset(&g, 0, sizeof(g));
