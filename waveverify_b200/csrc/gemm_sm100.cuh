@@ -107,6 +107,13 @@ struct GemmArgs {
   act_t* out_act;
   float act_scale;
   int ldo;
+  // STAGED, last_mode: the decoder's output conv C -> 1, k = 5 (modules/seanet.py:1177-1202) as a GEMM with one
+  // column per tap (P[t, j] = w_j . a[t]) and out[t] = tanh(b + sum_j P[t-4+j, j]); fp32 staging; fused trim + watermark add
+  int last_mode, last_T;
+  float last_bias;
+  const float* last_x;
+  float* last_wm;
+  float* last_y;
   // L2NORM
   float l2_scale;
   float* out_f32_t;  // [clips, N, F] fp32 (latent for the API), nullable
@@ -502,6 +509,37 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   }
 }
 
+// last_mode math: one thread per output sample of the tile (124 of the 384 math threads).
+__device__ __forceinline__ void staged_last_loop(const GemmArgs& g, const uint8_t* stage_tiles) {
+  constexpr int ROWS_OUT = BM - 4;
+  const int pitch = staged_pitch_bytes(g.block_n);
+  const int et = threadIdx.x - (128 + P1_WARPS * 32);
+  const uint32_t stage_u32 = smem_u32(stage_tiles);
+  int sb = 0;
+  int tiles_left = cta_tile_count(g);
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+    named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);
+    const int t = tc.mi * ROWS_OUT + et;
+    if (et < ROWS_OUT && t < g.last_T) {
+      const uint32_t row = stage_u32 + sb * (BM * pitch) + et * pitch;
+      float acc = g.last_bias;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(row + j * pitch + j * 4));
+        acc += v;
+      }
+      const float wm = tanhf(acc);
+      const long long o = static_cast<long long>(tc.clip) * g.last_T + t;
+      if (g.last_wm != nullptr) g.last_wm[o] = wm;
+      if (g.last_y != nullptr) g.last_y[o] = __ldcg(g.last_x + o) + wm;
+    }
+    __syncwarp();
+    if (--tiles_left >= g.stage_bufs) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);
+    if (++sb == g.stage_bufs) sb = 0;
+  }
+}
+
 template <int TAPS, int R>
 __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   const bool res = g.residual != nullptr, raw = g.out_raw != nullptr, act = g.out_act != nullptr;
@@ -736,6 +774,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = 0; c < (WV_DBG_MODE(4) ? 0 : chunks); ++c) {
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
+          if (g.last_mode) {   // output conv: the five tap columns stay fp32 (32 bytes per row)
+            sts_u4(rowp, v[0], v[1], v[2], v[3]);
+            sts_u4(rowp + 16, v[4], v[5], v[6], v[7]);
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             sts_u4(rowp + c * 64 + i * 16,
@@ -757,7 +800,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global
       reg_alloc<REGS_MATH>();
-      if (g.down_r > 0) {
+      if (g.last_mode) {
+        staged_last_loop(g, stage_tiles);
+      } else if (g.down_r > 0) {
         switch (g.down_r) {
           case 2: staged_down_loop<2>(g, stage_tiles, down_w, lane); break;
           case 4: staged_down_loop<4>(g, stage_tiles, down_w, lane); break;

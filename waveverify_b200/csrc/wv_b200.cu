@@ -118,6 +118,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
 int g_ldy_align = 8;        // log-spectrogram row pitch in elements (WV_LDY_ALIGN: 8 = 16 B, 16 = 32 B = one DRAM sector per chunk)
+bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
 int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
 int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
@@ -148,6 +149,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
+  if (const char* e = getenv("WV_LAST_GEMM")) g_last_gemm = atoi(e) != 0;
   if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e) != 0;
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
   if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
@@ -245,6 +247,7 @@ struct DecoderW {
   std::vector<DecStageW> stages;
   float* last_w = nullptr;   // [5][C]
   float last_b = 0.f;
+  GemmW last_gemm;           // the same conv as a GEMM: [32, C] fp16, row j < 5 = tap j (wav_std folded), rest zero
   int C_last;
   float stage_scale;
 };
@@ -931,6 +934,12 @@ void build_decoder_w(wv_net& n) {
   for (int c = 0; c < C; ++c)
     for (int j = 0; j < 5; ++j) h[j * C + c] = lw.data[c * 5 + j] * WAV_STD;        // seanet.py:1193
   d.last_w = W.dev.upload(h);
+  {
+    std::vector<float> rows(static_cast<size_t>(32) * C, 0.f);
+    for (int j = 0; j < 5; ++j)
+      for (int c = 0; c < C; ++c) rows[static_cast<size_t>(j) * C + c] = h[j * C + c];
+    d.last_gemm = make_gemm_w(W, rows, 32, C, true, 32, nullptr, 0);
+  }
   const HostTensor* lb = W.find(p + "." + std::to_string(i) + ".conv.conv.bias");
   d.last_b = lb ? lb->data[0] * WAV_STD : 0.f;
   d.C_last = C;
@@ -1199,7 +1208,22 @@ void plan_decoder(PlanCtx& c, wv_net& n, const Buf& Z, int F, int T_out) {
     }
     if (nres == 0) c.release(X);
   }
-  {
+  if (g_last_gemm) {
+    // output conv C -> 1, k = 5 as a tcgen05 GEMM with one column per tap; the epilogue sums the five
+    // shifted columns, applies tanh, trims to T_out and adds the watermark to x (io pointers at run time)
+    GemmArgs g = std_args(nullptr, nullptr, nullptr, nullptr, 1.f, 32);
+    g.taps = 5;                // tile geometry: 4-row causal halo, 124 outputs per tile
+    g.last_mode = 1;
+    g.last_T = T_out;
+    g.last_bias = d.last_b;
+    CUtensorMap tm;
+    if (!c.dry()) tm = make_tmap(c.ptr<h16>(A), 3, C, Ts, B, C, static_cast<uint64_t>(C) * Ts, BK, BM, true);
+    c.tag("dec.last");
+    add_gemm(c, EPI_STAGED, d.last_gemm, nullptr, 0, 0, C, g, &tm, Ts, B);
+    Op& op = c.ops->back();
+    op.flops = 2.0 * 5 * C * B * T_out;
+    op.bytes = static_cast<double>(B) * T_out * (2.0 * C + 12.0);
+  } else {
     Op op;
     op.type = OP_CONV_LAST;
     op.in = c.ptr<h16>(A); op.w = d.last_w; op.fa = d.last_b;
@@ -1365,6 +1389,7 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
       case OP_GEMM: {
         GemmArgs g = op.g;
         if (op.epi == EPI_L2NORM) g.out_f32_t = io.latent;
+        if (g.last_mode) { g.last_x = io.x; g.last_wm = io.wm; g.last_y = io.y; }
         if (op.epi == EPI_HEAD) {
           g.logits = io.logits; g.mask_out = io.mask; g.probs = io.probs; g.presence = io.presence;
           if (!(io.bits || io.avg || io.conf || io.valid)) g.partial = nullptr;
