@@ -116,6 +116,29 @@ int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8
                           int B, int nbits, const uint8_t* pred_mask, const uint8_t* gt_mask,
                           long long n_mask, long long* counters, void* stream);
 
+/* ---- validation path: device pointers, fp32 [B, T] ------------------
+ * wv_augment_gather replaces LocalizationAugmentation.forward (utils/localization_augmentation.py:
+ * 212-325) and SequenceAugmentation.forward (utils/seq_augmentation.py:100-277) with one gather pass.
+ *   seg_op [B, n_seg] u8 (NULL = no localization step): 0 keep, 1 revert to original, 2 zeros,
+ *   3 original of clip seg_src[b, s]; segment s covers samples [s*seg_len, (s+1)*seg_len).
+ *   seq_kind: 0 identity, 1 reverse, 2 circular shift by seq_a, 3 shuffle of n_perm segments of
+ *   seq_c samples (seq_perm device int[n_perm]; T_out = n_perm*seq_c), 4 swap chunks [seq_a,+seq_c)
+ *   and [seq_b,+seq_c).  T_out = T except for kind 3.
+ *   gt_in (nullable): presence of the input (all ones when NULL).  Each out_* is nullable. */
+int wv_augment_gather(const float* original, const float* watermarked, const float* gt_in, int B, int T,
+                      const uint8_t* seg_op, const int* seg_src, int seg_len, int n_seg, int seq_kind,
+                      int seq_a, int seq_b, int seq_c, const int* seq_perm, int n_perm, int T_out,
+                      float* out_wm, float* out_orig, float* out_gt, void* stream);
+/* utils/effect_augmentation.py pointwise effects over n samples: 0 identity (:1364), 1 amplitude_scaling
+ * (p0 = scale, :2000), 2 quantization (p0 = 2^(bit_depth-1) - 1, :1090-1111), 3 additive noise
+ * x + noise*p0 with the caller's N(0,1) draw (:2105, :2338), 4 the same with an in-kernel Philox draw. */
+int wv_effect_pointwise(int effect, const float* in, long long n, float p0, const float* noise,
+                        unsigned long long seed, float* out, void* stream);
+/* sample_suppression (:2061-2103): audio[b, idx[b, j]] = 0 and mask[b, idx[b, j]] = 0 (mask nullable), in place. */
+int wv_effect_suppress(float* audio, float* mask, const long long* idx, int B, int T, int k, void* stream);
+/* median_filter (:1246-1312, scipy.signal.medfilt: zero-padded ends), odd k <= 31. */
+int wv_effect_median(const float* in, int B, int T, int k, float* out, void* stream);
+
 /* ---- profiling / debugging (used by bench.py and the tests) ------------------------------- */
 /* When enabled, every launch of a forward is bracketed by CUDA events on the caller's stream. */
 int wv_net_set_profile(wv_net* net, int enable);

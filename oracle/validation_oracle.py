@@ -1,0 +1,126 @@
+"""CPU oracle for the validation-path augmentations and effects.
+
+TEST INFRASTRUCTURE ONLY (see oracle/wv_oracle.py): numpy restatement, sequential slice operations
+in the reference's own order; only `tests/` may import it.
+
+Parity pinning: pinned against OUTPUTS OF THE REFERENCE ITSELF (utils/localization_augmentation.py,
+utils/seq_augmentation.py, utils/effect_augmentation.py imported unmodified in the build container
+by oracle/make_golden_validation.py, with stand-ins for the absent matplotlib / julius /
+audiotools imports that these functions never call) -> tests/golden/validation/validation.npz, re-checked
+by tests/test_validation_oracle.py.  Random draws follow the reference's call order on the
+global numpy / torch generators, so seeding those reproduces the reference's selections.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def localization_augment(original: np.ndarray, watermarked: np.ndarray, segment_length: int):
+    """utils/localization_augmentation.py:212-325.  [B, C, T] float32 in; returns
+    (watermarked', ground_truth, updated_original, stats%)."""
+    original = original.astype(np.float32).copy()
+    upd = original.copy()
+    wm = watermarked.astype(np.float32).copy()
+    B, _, T = wm.shape
+    gt = np.ones_like(wm)
+    stats = dict(original_revert=0, zero_replace=0, cross_substitute=0, unchanged=0)
+    total_segments = int(np.ceil(T / segment_length))                      # :259
+    k = int(total_segments * 0.20)                                         # :260
+    for b in range(B):
+        starts = np.arange(0, T, segment_length)                           # :269
+        for start in np.random.choice(starts, k, replace=False):           # :272-276
+            end = min(start + segment_length, T)
+            p = np.random.rand()                                           # :281
+            if p < 0.33:                                                   # :126-149
+                wm[b, :, start:end] = original[b, :, start:end]
+                gt[b, :, start:end] = 0
+                stats["original_revert"] += end - start
+            elif p < 0.66:                                                 # :151-175
+                wm[b, :, start:end] = 0
+                upd[b, :, start:end] = 0
+                gt[b, :, start:end] = 0
+                stats["zero_replace"] += end - start
+            elif B >= 2:                                                   # :177-210
+                other = np.random.choice([j for j in range(B) if j != b])
+                wm[b, :, start:end] = original[other, :, start:end]
+                upd[b, :, start:end] = original[other, :, start:end]
+                gt[b, :, start:end] = 0
+                stats["cross_substitute"] += end - start
+    total = B * T
+    stats["unchanged"] = total - stats["original_revert"] - stats["zero_replace"] - stats["cross_substitute"]
+    return wm, gt, upd, {k_: float(v / total * 100) for k_, v in stats.items()}
+
+
+def sequence_augment(updated_original: np.ndarray, watermarked: np.ndarray, gt: np.ndarray, sample_rate: int):
+    """utils/seq_augmentation.py:100-277.  Returns (watermarked', updated_original', gt', method)."""
+    B, C, T = watermarked.shape
+    r = np.random.rand()                                                   # :154
+    tensors = [watermarked, updated_original, gt]
+    if r < 0.3:                                                            # :165-170
+        return (*[np.ascontiguousarray(t[:, :, ::-1]) for t in tensors], "reverse")
+    if r < 0.7:                                                            # :172-178
+        shift = np.random.randint(1, T)
+        return (*[np.roll(t, shift, axis=2) for t in tensors], "circular_shift")
+    if r < 1.0:                                                            # :181-207
+        seg = int(0.5 * sample_rate)
+        if T >= 2 * seg:
+            n = T // seg
+            perm = torch.randperm(n).numpy()
+            outs = [t[:, :, :n * seg].reshape(B, C, n, seg)[:, :, perm].reshape(B, C, n * seg) for t in tensors]
+            return (*outs, "shuffle")
+        return (*tensors, "unchanged")
+    return (*tensors, "unchanged")
+
+
+def chunk_swap(x: np.ndarray, c1: int, c2: int, size: int) -> np.ndarray:
+    """utils/seq_augmentation.py:236-240 (the swap itself; the reference never selects this method)."""
+    y = x.copy()
+    tmp = y[:, :, c1:c1 + size].copy()
+    y[:, :, c1:c1 + size] = y[:, :, c2:c2 + size]
+    y[:, :, c2:c2 + size] = tmp
+    return y
+
+
+def amplitude_scaling(x: np.ndarray, scale: float) -> np.ndarray:
+    """utils/effect_augmentation.py:2022."""
+    return (x.astype(np.float32) * np.float32(scale)).astype(np.float32)
+
+
+def quantization(x: np.ndarray, bit_depth: int) -> np.ndarray:
+    """utils/effect_augmentation.py:1103-1109: round-half-even(x * m) / m in fp32."""
+    m = np.float32(2 ** (bit_depth - 1) - 1)
+    return (np.rint(x.astype(np.float32) * m) / m).astype(np.float32)
+
+
+def add_noise(x: np.ndarray, noise: np.ndarray, std: float) -> np.ndarray:
+    """utils/effect_augmentation.py:2127-2128 / 2362-2363 with the N(0,1) draw given."""
+    return (x.astype(np.float32) + noise.astype(np.float32) * np.float32(std)).astype(np.float32)
+
+
+def sample_suppression(x: np.ndarray, mask, idx: np.ndarray):
+    """utils/effect_augmentation.py:2084-2098; idx [B*C, k] = the randperm heads."""
+    y = x.copy()
+    B, C, T = x.shape
+    m = None if mask is None else mask.copy()
+    for b in range(B):
+        for c in range(C):
+            y[b, c, idx[b * C + c]] = 0
+            if m is not None:
+                m[b, c, idx[b * C + c]] = 0
+    return y, m
+
+
+def median_filter(x: np.ndarray, kernel_size: int) -> np.ndarray:
+    """utils/effect_augmentation.py:1278-1307 -> scipy.signal.medfilt (zero-padded ends)."""
+    if kernel_size % 2 == 0:
+        kernel_size += 1
+    h = kernel_size // 2
+    B, C, T = x.shape
+    out = np.empty_like(x)
+    for b in range(B):
+        for c in range(C):
+            p = np.concatenate([np.zeros(h, x.dtype), x[b, c], np.zeros(h, x.dtype)])
+            w = np.lib.stride_tricks.sliding_window_view(p, kernel_size)
+            out[b, c] = np.sort(w, axis=1)[:, h]
+    return out

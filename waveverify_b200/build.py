@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "wv_b200.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("wv_b200.cu", "gemm_sm100.cuh", "glue_kernels.cuh", "ptx_sm100.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("wv_b200.cu", "gemm_sm100.cuh", "glue_kernels.cuh", "ptx_sm100.cuh", "validation_kernels.cuh", "resblock_sm100.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "wv_b200.h"))
 LIB = os.path.join(HERE, "libwv_b200.so")
 

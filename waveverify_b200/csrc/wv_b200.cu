@@ -19,6 +19,7 @@
 #include "../../include/wv_b200.h"
 #include "gemm_sm100.cuh"
 #include "glue_kernels.cuh"
+#include "validation_kernels.cuh"
 #include "resblock_sm100.cuh"
 
 namespace {
@@ -30,6 +31,12 @@ thread_local std::string g_err;
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
+}
+template <typename... Args>
+int failf(int code, const char* fmt, Args... args) {
+  char b[512];
+  snprintf(b, sizeof(b), fmt, args...);
+  return fail(code, std::string(b));
 }
 struct WvError {
   int code;
@@ -1696,6 +1703,87 @@ int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8
     if (work <= 0) return;
     metrics_kernel<<<elem_grid(work), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         bits, valid, msg_bits, nb, pred_mask, gt_mask, n_mask, reinterpret_cast<unsigned long long*>(counters));
+    CK(cudaGetLastError());
+  });
+}
+
+// ---- validation path: temporal augmentations + cheap effects (validation_kernels.cuh) ---------
+int wv_augment_gather(const float* original, const float* watermarked, const float* gt_in, int B, int T,
+                      const uint8_t* seg_op, const int* seg_src, int seg_len, int n_seg, int seq_kind, int seq_a,
+                      int seq_b, int seq_c, const int* seq_perm, int n_perm, int T_out, float* out_wm,
+                      float* out_orig, float* out_gt, void* stream) {
+  if (!watermarked) return fail(WV_ERR_INVALID, "watermarked is required");
+  if (B < 0 || T <= 0) return failf(WV_ERR_INVALID, "bad shape B=%d T=%d", B, T);
+  if ((seg_op != nullptr || out_orig != nullptr) && !original) return fail(WV_ERR_INVALID, "original is required");
+  if (seg_op != nullptr && (seg_len <= 0 || static_cast<long long>(n_seg) * seg_len < T))
+    return failf(WV_ERR_INVALID, "segment table [%d x %d] does not cover T=%d", n_seg, seg_len, T);
+  if (seg_op != nullptr && !seg_src) return fail(WV_ERR_INVALID, "seg_src is required with seg_op");
+  if (seq_kind < 0 || seq_kind > 4) return failf(WV_ERR_INVALID, "unknown sequence map %d", seq_kind);
+  int want_T = T;
+  if (seq_kind == 2 && (seq_a < 0 || seq_a >= T)) return failf(WV_ERR_INVALID, "shift %d outside [0, %d)", seq_a, T);
+  if (seq_kind == 3) {
+    if (!seq_perm || seq_c <= 0 || n_perm <= 0 || static_cast<long long>(n_perm) * seq_c > T)
+      return failf(WV_ERR_INVALID, "bad shuffle: %d segments of %d samples for T=%d", n_perm, seq_c, T);
+    want_T = n_perm * seq_c;
+  }
+  if (seq_kind == 4) {
+    const int lo = std::min(seq_a, seq_b), hi = std::max(seq_a, seq_b);
+    if (seq_c <= 0 || lo < 0 || hi + seq_c > T || hi - lo < seq_c)
+      return failf(WV_ERR_INVALID, "bad chunk swap [%d,+%d) <-> [%d,+%d) for T=%d", seq_a, seq_c, seq_b, seq_c, T);
+  }
+  if (T_out != want_T) return failf(WV_ERR_INVALID, "T_out=%d, expected %d", T_out, want_T);
+  return guarded([&] {
+    init_device_once();
+    if (B == 0) return;
+    SeqMap m{seq_kind, seq_a, seq_b, seq_c, seq_perm, n_perm};
+    const long long aug_blocks = static_cast<long long>(B) * ceil_div(T_out, AUG_TILE);
+    augment_gather_kernel<<<static_cast<int>(std::min<long long>(aug_blocks, static_cast<long long>(g_num_sms) * 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        original, watermarked, gt_in, B, T, seg_op, seg_src, seg_len, n_seg, m, T_out, out_wm, out_orig, out_gt);
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_effect_pointwise(int effect, const float* in, long long n, float p0, const float* noise,
+                        unsigned long long seed, float* out, void* stream) {
+  if (effect < 0 || effect > 4) return failf(WV_ERR_INVALID, "unknown pointwise effect %d", effect);
+  if (!in || !out || n < 0) return fail(WV_ERR_INVALID, "in / out are required");
+  if (effect == 3 && !noise) return fail(WV_ERR_INVALID, "effect 3 needs the noise draw");
+  if (effect == 2 && !(p0 >= 1.f)) return failf(WV_ERR_INVALID, "quantization scale %g < 1", p0);
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(noise)) & 15)
+    return fail(WV_ERR_INVALID, "buffers must be 16-byte aligned");
+  return guarded([&] {
+    init_device_once();
+    if (n == 0) return;
+    effect_pointwise_kernel<<<elem_grid((n + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(effect, in, n, p0, noise, seed, out);
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_effect_suppress(float* audio, float* mask, const long long* idx, int B, int T, int k, void* stream) {
+  if (!audio || (k > 0 && !idx) || B < 0 || T <= 0 || k < 0) return fail(WV_ERR_INVALID, "bad suppress arguments");
+  return guarded([&] {
+    init_device_once();
+    if (B == 0 || k == 0) return;
+    effect_suppress_kernel<<<elem_grid(static_cast<long long>(B) * k), 256, 0, static_cast<cudaStream_t>(stream)>>>(audio, mask, idx, B, T, k);
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_effect_median(const float* in, int B, int T, int k, float* out, void* stream) {
+  if (!in || !out || B < 0 || T <= 0) return fail(WV_ERR_INVALID, "bad median arguments");
+  if (k < 1 || k > MEDIAN_MAX_K || k % 2 == 0) return failf(WV_ERR_INVALID, "median window %d: odd, 1..%d", k, MEDIAN_MAX_K);
+  return guarded([&] {
+    init_device_once();
+    if (B == 0) return;
+    const long long tiles = static_cast<long long>(B) * ceil_div(T, MEDIAN_TILE);
+    const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(g_num_sms) * 16));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (k) {
+#define WV_MED(K) case K: effect_median_kernel<K><<<grid, MEDIAN_THREADS, 0, st>>>(in, B, T, out); break;
+      WV_MED(1) WV_MED(3) WV_MED(5) WV_MED(7) WV_MED(9) WV_MED(11) WV_MED(13) WV_MED(15) WV_MED(17) WV_MED(19)
+      WV_MED(21) WV_MED(23) WV_MED(25) WV_MED(27) WV_MED(29) WV_MED(31)
+#undef WV_MED
+    }
     CK(cudaGetLastError());
   });
 }
