@@ -86,6 +86,10 @@ struct GemmArgs {
   int acc_stages, acc_cols;
   int kb_split;       // > 0: k-blocks >= kb_split re-read the A rows shifted by one (row r-1) at k - kb_split*64:
                       //      [a[i] | a[i-1]] contraction of the fused transposed-conv + 1x1 (decoder upsample)
+  int a2_split;       // > 0: k-blocks >= a2_split are read from a SECOND A tensor (tmR) at k - a2_split*64, same rows
+  int dual;           // 1 (with a2_split): the tile's columns are [acc1 | acc2], block_n/2 channels each: acc1 = the 1x1 conv
+                      //    that feeds the depthwise taps, acc2 = a second 1x1 conv over the second A tensor that is added
+                      //    un-tapped (last encoder resblock + spectrogram branch in one launch, modules/seanet.py:936-943)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
   int resident_b;     // 1: this CTA's W tile (all k-blocks) stays in shared memory; the ring carries A only
@@ -264,11 +268,11 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, ui
 
 // One math unit: R output rows x 4 channels.  nrow < R only at the end of a tile / clip (FULL=false):
 // rows past nrow are neither read (they may lie beyond the staging tile) nor written.
-template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool FULL, bool SCALE>
+template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool FULL, bool SCALE, bool DUAL = false>
 __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*smem addr of tile row ro*/,
                                             int pitch, size_t off, size_t row_bytes, int nrow,
                                             const __half2 (&wt)[TAPS][2], const __half2 (&bs)[2], float s_act,
-                                            const uint2 (&rres)[R]) {
+                                            const uint2 (&rres)[R], uint32_t dual_off = 0) {
   constexpr int HALO = TAPS - 1;
   __half2 oh[R][2];
   if constexpr (TAPS > 1) {
@@ -294,6 +298,14 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
       const uint2 u = (FULL || i < nrow) ? lds_u2(srow + i * pitch) : make_uint2(0u, 0u);
       oh[i][0] = __hadd2(as_h2(u.x), bs[0]);
       oh[i][1] = __hadd2(as_h2(u.y), bs[1]);
+    }
+  }
+  if constexpr (DUAL) {   // second accumulator (un-tapped): same output rows = tile rows ro+HALO .. , columns + block_n/2
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const uint2 u = (FULL || i < nrow) ? lds_u2(srow + (TAPS - 1 + i) * pitch + dual_off) : make_uint2(0u, 0u);
+      oh[i][0] = __hadd2(oh[i][0], as_h2(u.x));
+      oh[i][1] = __hadd2(oh[i][1], as_h2(u.y));
     }
   }
   if constexpr (RES) {
@@ -326,14 +338,16 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
 
 // STAGED math warps.  thread = (4-channel group, R-row group): 8-byte smem reads / global accesses
 // keep a warp on contiguous row segments; a thread walks its row groups in passes of 384 threads.
-template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE>
+template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE, bool DUAL = false>
 __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   constexpr int HALO = TAPS - 1;
   constexpr int ROWS_OUT = BM - HALO;
   constexpr int N_GROUPS = (ROWS_OUT + R - 1) / R;
   const int pitch = staged_pitch_bytes(g.block_n);
   const int et = threadIdx.x - (128 + P1_WARPS * 32);
-  const int cgs = g.block_n >> 2;                                // 4-channel groups per row
+  const int bn = DUAL ? g.block_n >> 1 : g.block_n;              // output channels per tile
+  const int n_ch = DUAL ? g.N >> 1 : g.N;                        // output channels of the layer
+  const int cgs = bn >> 2;                                       // 4-channel groups per row
   const int gstride = P2_THREADS / cgs;                          // row groups per pass
   const int cg = et % cgs, grp0 = et / cgs;
   const bool active = grp0 < gstride;
@@ -347,7 +361,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   int dbg_it = 0;
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
-    const int c = tc.nt * g.block_n + cg * 4;
+    const int c = tc.nt * bn + cg * 4;
     if (active && tc.nt != cached_nt) {                            // per-CTA constant when N fits one tile
       cached_nt = tc.nt;
       if (g.bias != nullptr) {
@@ -359,7 +373,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       if constexpr (TAPS > 1) {
 #pragma unroll
         for (int j = 0; j < TAPS; ++j) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * n_ch + c));
           wt[j][0] = h2_from(w0.x, w0.y); wt[j][1] = h2_from(w0.z, w0.w);
         }
       }
@@ -396,9 +410,9 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       const size_t off = base + static_cast<size_t>(ro) * g.ldo;
       const uint32_t srow = tile_u32 + ro * pitch;
       if (ro + R <= rows_left)
-        staged_unit<TAPS, R, RES, RAW, ACT, true, SCALE>(g, srow, pitch, off, row_bytes, R, wt, bs, s_act, rres);
+        staged_unit<TAPS, R, RES, RAW, ACT, true, SCALE, DUAL>(g, srow, pitch, off, row_bytes, R, wt, bs, s_act, rres, bn * 2);
       else
-        staged_unit<TAPS, R, RES, RAW, ACT, false, SCALE>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act, rres);
+        staged_unit<TAPS, R, RES, RAW, ACT, false, SCALE, DUAL>(g, srow, pitch, off, row_bytes, rows_left - ro, wt, bs, s_act, rres, bn * 2);
       if constexpr (RES) {
 #pragma unroll
         for (int i = 0; i < R; ++i) rres[i] = rnext[i];
@@ -558,6 +572,13 @@ __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const ui
 }
 template <int TAPS>
 __device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
+  if constexpr (TAPS == 5) {
+    if (g.dual) {   // last encoder resblock + spectrogram 1x1: residual in, activated output only
+      if (g.act_scale != 1.f) staged_math_loop<5, 4, true, false, true, true, true>(g, stage_tiles, lane);
+      else staged_math_loop<5, 4, true, false, true, false, true>(g, stage_tiles, lane);
+      return;
+    }
+  }
   staged_math_dispatch<TAPS, 4>(g, stage_tiles, lane);   // 6- and 8-row units were measured: slower
 }
 
@@ -597,6 +618,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (g.a2_split > 0) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
@@ -668,6 +690,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
           if (g.phases > 1) tma_load_4d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip % g.phases, tc.clip / g.phases);
+          else if (g.a2_split > 0 && kb >= g.a2_split) tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmR, &full[stage], (kb - g.a2_split) * BK, r0, tc.clip);
           else if (g.kb_split > 0 && kb >= g.kb_split) tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], (kb - g.kb_split) * BK, r0 - 1, tc.clip);
           else if (g.a_evict_first) tma_load_3d_hint(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip, pol);
           else tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);

@@ -125,6 +125,7 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
 int g_ldy_align = 8;        // log-spectrogram row pitch in elements (WV_LDY_ALIGN: 8 = 16 B, 16 = 32 B = one DRAM sector per chunk)
+int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
 int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
@@ -156,6 +157,7 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
+  if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_LAST_GEMM")) g_last_gemm = atoi(e) != 0;
   if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e) != 0;
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
@@ -226,6 +228,9 @@ struct SpecW {
 struct EncStageW {
   std::vector<ResW> res;
   SpecW spec;
+  GemmW dual;            // [W2 | 0 ; 0 | Wspec] per n tile: last resblock's second 1x1 and the spectrogram 1x1 in one GEMM
+  int dual_split_kb = 0; // k-blocks of the first operand (h1); 0 = not built
+  int dual_ldy = 0;      // log-spectrogram row pitch the weights were laid out for
   GemmW down_pw;
   DwW down_dw;
   int r, C;
@@ -382,6 +387,35 @@ SpecW spec_w(Weights& W, const std::string& p, int n_fft, int hop, float mean, f
   const float sc = rs * W.scalar_or(p + ".scale_param", 1.f);            // seanet.py:499-505
   s.layer = pointwise(W, p + ".layer.conv.conv", sc, false);
   return s;
+}
+
+// Last resblock of an encoder stage + spectrogram branch as one GEMM (modules/seanet.py:936-943):
+//   x'' = RS*(dw5(W2 h1) + b2) + x + RS*scale*(Ws y)
+// Operand rows of n tile nt (bn = block_n/2 output channels): rows [0, bn) = [W2 | 0], rows [bn, 2bn) = [0 | Ws];
+// the contraction is [h1 (K1 padded to 64) | y (ldy padded to 64)], so accumulator columns [0, bn) hold
+// W2 h1 (input of the depthwise taps) and columns [bn, 2bn) hold Ws y (added un-tapped).
+void build_dual_w(Weights& W, EncStageW& st, const std::string& res_p, const std::string& spec_p, float rs, int C) {
+  const HostTensor& w2 = W.get(res_p + ".block.4.conv.conv.weight");
+  const HostTensor& ws = W.get(spec_p + ".layer.conv.conv.weight");
+  const int K2 = st.spec.n_fft / 2 + 1;
+  if (w2.shape.size() != 3 || w2.shape[0] != C || w2.shape[1] != C || ws.shape.size() != 3 || ws.shape[0] != C || ws.shape[1] != K2) return;
+  const float sc = rs * W.scalar_or(spec_p + ".scale_param", 1.f);
+  const int ldy = static_cast<int>(round_up(K2, g_ldy_align));
+  const int k1p = static_cast<int>(round_up(C, BK)), k2p = static_cast<int>(round_up(ldy, BK));
+  const int Kc = k1p + k2p;
+  const int block_n = std::min(2 * C, STAGED_MAX_BN), bn = block_n / 2;
+  if (block_n % 32 != 0 || C % bn != 0) return;
+  std::vector<float> rows(static_cast<size_t>(2) * C * Kc, 0.f);
+  for (int n = 0; n < C; ++n) {
+    const int nt = n / bn, j = n % bn;
+    float* r1 = rows.data() + (static_cast<size_t>(nt) * block_n + j) * Kc;
+    float* r2 = rows.data() + (static_cast<size_t>(nt) * block_n + bn + j) * Kc;
+    for (int k = 0; k < C; ++k) r1[k] = w2.data[static_cast<size_t>(n) * C + k];
+    for (int k = 0; k < K2; ++k) r2[k1p + k] = ws.data[static_cast<size_t>(n) * K2 + k] * sc;
+  }
+  st.dual = make_gemm_w(W, rows, 2 * C, Kc, true, block_n, nullptr, 0);
+  st.dual_split_kb = k1p / BK;
+  st.dual_ldy = ldy;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -564,7 +598,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
   g.stage_bufs = (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb) ? 1 : STAGE_BUFS;
   // pair mode (two M tiles per W k-block) for the long-K layers whose W tile does not stay resident
-  const bool pair = staged && !resident && g.down_r == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
+  const bool pair = staged && !resident && g.down_r == 0 && g.a2_split == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
   g.pair = pair ? 1 : 0;
   g.acc_stages = pair ? MAX_ACC_STAGES : ACC_STAGES;
   g.acc_cols = pair ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
@@ -582,7 +616,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   }
   op.tmB = w.tm;
   op.tmR = w.tm;
-  if (staged && g.residual != nullptr && !c.dry())   // residual shares the output's [clip, row, ldo] layout
+  if (staged && g.residual != nullptr && g.a2_split == 0 && !c.dry())   // residual shares the output's [clip, row, ldo] layout
     op.tmR = make_tmap(g.residual, 3, g.ldo, g.rows_per_clip, g.n_clips, g.ldo,
                        static_cast<uint64_t>(g.ldo) * g.rows_per_clip, w.block_n, BM, false, false);
   op.g = g;
@@ -835,6 +869,9 @@ void build_encoder_w(wv_net& n) {
     for (int j = 1; j <= cf.n_residual_enc; ++j)                                // idx=j, seanet.py:684
       st.res.push_back(resblock_w(W, p + ".blocks." + std::to_string(s) + "." + std::to_string(j - 1), j, rs));
     st.spec = spec_w(W, p + ".spec_blocks." + std::to_string(s), nfft, hop, SPEC_MEANS[s], SPEC_STDS[s], rs);
+    if (cf.n_residual_enc >= 1 && C <= g_spec_fuse_maxc)
+      build_dual_w(W, st, p + ".blocks." + std::to_string(s) + "." + std::to_string(cf.n_residual_enc - 1),
+                   p + ".spec_blocks." + std::to_string(s), rs, C);
     st.down_pw = pointwise(W, p + ".downsample." + std::to_string(s) + ".2.conv.conv", 1.f, false);
     st.down_dw = depthwise(W, p + ".downsample." + std::to_string(s) + ".3.conv.conv", 1.f, true);
     if (st.down_dw.k != 2 * st.r) WV_THROW(WV_ERR_INVALID, "downsample kernel != 2*stride");
@@ -984,8 +1021,8 @@ void build_head_w(wv_net& n) {
 }
 
 // STFT branch + 1x1 + residual add (modules/seanet.py:463-507): Aout = ELU((X + spec) * act_scale)
-void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, Buf& X,
-               int C, float act_scale, Buf& Aout, const std::string& name) {
+// STFT -> log-magnitude -> normalise (modules/conv.py:1036-1080, seanet.py:463-497): Y [B*F, ldy] fp16
+Buf plan_spec_stft(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, const std::string& name, int& ldy_out) {
   const long long M = static_cast<long long>(c.B) * F;
   const int K2 = s.n_fft / 2 + 1;
   // row pitch of the log-spectrogram: next multiple of 8 elements (16 B, the TMA stride unit); pad
@@ -1039,6 +1076,15 @@ void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead
     add_gemm(c, EPI_STFT, s.dft, c.ptr<__half>(FR), s.n_fft, M, s.n_fft, g);
     c.release(FR);
   }
+  ldy_out = ldy;
+  return Y;
+}
+
+void plan_spec(PlanCtx& c, const SpecW& s, const Buf& wav16, int pitch, int lead, int F, Buf& X,
+               int C, float act_scale, Buf& Aout, const std::string& name) {
+  const long long M = static_cast<long long>(c.B) * F;
+  int ldy = 0;
+  Buf Y = plan_spec_stft(c, s, wav16, pitch, lead, F, name, ldy);
   Aout = c.alloc(static_cast<size_t>(M) * C * 2);
   c.tag(name + ".out");
   // contraction over the padded width ldy (pad columns of Y and of the weights are zero): a TMA
@@ -1101,14 +1147,50 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
   for (int s = 0; s < S; ++s) {
     const EncStageW& st = e.stages[s];
     const int nres = static_cast<int>(st.res.size());
+    const bool fuse_spec = st.dual_split_kb > 0 && nres >= 1 && !resblock_fusable(st.res[nres - 1], C);
     for (int j = 0; j < nres; ++j) {
       const bool last = j == nres - 1;
+      const std::string rname = "enc.s" + std::to_string(s) + ".r" + std::to_string(j);
+      if (last && fuse_spec) {
+        // first half as usual; the second half also contracts the log-spectrogram with the spec 1x1
+        // (second accumulator) and writes only A = ELU((x' + spec) * scale): x' never reaches HBM
+        const ResW& r = st.res[j];
+        const size_t bytes = static_cast<size_t>(B) * Ts * C * 2;
+        Buf H = c.alloc(bytes);
+        c.tag(rname + ".h1");
+        add_gemm_dw(c, r.pw1, r.dw1, c.ptr<h16>(A), Ts, C, nullptr, nullptr, c.ptr<h16>(H), 1.f);
+        c.release(A);
+        int ldy = 0;
+        Buf Y = plan_spec_stft(c, st.spec, wav16, pitch, lead, Ts, "enc.s" + std::to_string(s) + ".spec", ldy);
+        if (ldy != st.dual_ldy) WV_THROW(WV_ERR_INVALID, "log-spectrogram pitch %d != %d", ldy, st.dual_ldy);
+        A = c.alloc(bytes);
+        GemmArgs g = std_args(r.dw2.bias, c.ptr<h16>(X), nullptr, c.ptr<h16>(A), down_scale, C);
+        g.taps = 5;
+        g.dw_w = r.dw2.w;
+        g.dual = 1;
+        g.a2_split = st.dual_split_kb;
+        CUtensorMap tm;
+        if (!c.dry()) tm = make_tmap(c.ptr<h16>(H), 3, C, Ts, B, C, static_cast<uint64_t>(C) * Ts, BK, BM, false);
+        c.tag(rname + ".out+spec");
+        add_gemm(c, EPI_STAGED, st.dual, nullptr, 0, 0, st.dual.K, g, &tm, Ts, B);
+        Op& op = c.ops->back();
+        if (!c.dry()) op.tmR = make_tmap(c.ptr<h16>(Y), 3, ldy, Ts, B, ldy, static_cast<uint64_t>(ldy) * Ts, BK, BM, false);
+        const double n = static_cast<double>(B) * Ts;
+        op.flops = 2.0 * n * C * (C + ldy) + 10.0 * n * C;
+        op.bytes = n * 2.0 * (C + ldy + C + C) + static_cast<double>(C) * (C + ldy) * 2.0;   // h1, y, x in; A out
+        op.out_bytes[0] = 0;
+        op.out_bytes[1] = bytes;
+        c.release(H);
+        c.release(Y);
+        c.release(X);
+        break;
+      }
       Buf Xn, An;
-      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An,
-                    "enc.s" + std::to_string(s) + ".r" + std::to_string(j));
+      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An, rname);
       X = Xn; A = An;
     }
-    plan_spec(c, st.spec, wav16, pitch, lead, Ts, X, C, down_scale, A, "enc.s" + std::to_string(s) + ".spec");   // A = ELU((x+spec)*scale)
+    if (!fuse_spec)
+      plan_spec(c, st.spec, wav16, pitch, lead, Ts, X, C, down_scale, A, "enc.s" + std::to_string(s) + ".spec");   // A = ELU((x+spec)*scale)
     const int To = ceil_div(Ts, st.r);
     const bool last_stage = s == S - 1;
     Buf Ain = A;
