@@ -64,4 +64,6 @@ print(out)
 if a.md:
     open(a.md, "w").write(out + "\n")
 if a.traffic_json:
-    json.dump({k: v["rd"] + v["wr"] for k, v in agg.items() if v["rd"] + v["wr"] > 0}, open(a.traffic_json, "w"), indent=1)
+    json.dump({k: {"dram_bytes_per_step": v["rd"] + v["wr"], "launches": v["launches"],
+                   "dram_bytes_per_launch": (v["rd"] + v["wr"]) / max(1, v["launches"])}
+               for k, v in agg.items() if v["rd"] + v["wr"] > 0}, open(a.traffic_json, "w"), indent=1)
