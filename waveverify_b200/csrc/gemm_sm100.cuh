@@ -90,6 +90,7 @@ struct GemmArgs {
   int dual;           // 1 (with a2_split): the tile's columns are [acc1 | acc2], block_n/2 channels each: acc1 = the 1x1 conv
                       //    that feeds the depthwise taps, acc2 = a second 1x1 conv over the second A tensor that is added
                       //    un-tapped (last encoder resblock + spectrogram branch in one launch, modules/seanet.py:936-943)
+  int unit_rows;      // STAGED math units: rows per unit (4, or 6 for tile widths whose 4-row groups leave the second pass mostly idle)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
   int resident_b;     // 1: this CTA's W tile (all k-blocks) stays in shared memory; the ring carries A only
@@ -574,12 +575,20 @@ template <int TAPS>
 __device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   if constexpr (TAPS == 5) {
     if (g.dual) {   // last encoder resblock + spectrogram 1x1: residual in, activated output only
-      if (g.act_scale != 1.f) staged_math_loop<5, 4, true, false, true, true, true>(g, stage_tiles, lane);
-      else staged_math_loop<5, 4, true, false, true, false, true>(g, stage_tiles, lane);
+      if (g.unit_rows == 6) {
+        if (g.act_scale != 1.f) staged_math_loop<5, 6, true, false, true, true, true>(g, stage_tiles, lane);
+        else staged_math_loop<5, 6, true, false, true, false, true>(g, stage_tiles, lane);
+      } else {
+        if (g.act_scale != 1.f) staged_math_loop<5, 4, true, false, true, true, true>(g, stage_tiles, lane);
+        else staged_math_loop<5, 4, true, false, true, false, true>(g, stage_tiles, lane);
+      }
       return;
     }
   }
-  staged_math_dispatch<TAPS, 4>(g, stage_tiles, lane);   // 6- and 8-row units were measured: slower
+  // 6- and 8-row units were measured slower at 96 columns (16 row groups per pass: 4-row units already fill two
+  // passes); at 64 columns (24 row groups per pass) 4-row units leave the second pass 7/24 occupied
+  if (g.unit_rows == 6) staged_math_dispatch<TAPS, 6>(g, stage_tiles, lane);
+  else staged_math_dispatch<TAPS, 4>(g, stage_tiles, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

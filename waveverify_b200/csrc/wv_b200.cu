@@ -125,6 +125,8 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 int g_num_sms = 0;
 long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
 int g_ldy_align = 8;        // log-spectrogram row pitch in elements (WV_LDY_ALIGN: 8 = 16 B, 16 = 32 B = one DRAM sector per chunk)
+unsigned g_rows6_mask = (1u << (64 / 32)) | (1u << (128 / 32));   // STAGED tiles of these widths (bit = channels / 32) use 6-row math units:
+                            // 4-row groups leave their last pass mostly idle there (WV_ROWS6_BN = comma list of widths, 0 = off)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
@@ -158,6 +160,15 @@ void init_device_once() {
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
+  if (const char* e = getenv("WV_ROWS6_BN")) {
+    g_rows6_mask = 0;
+    for (const char* q = e; *q;) {
+      const int v = atoi(q);
+      if (v >= 32 && v <= 256) g_rows6_mask |= 1u << (v / 32);
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+  }
   if (const char* e = getenv("WV_LAST_GEMM")) g_last_gemm = atoi(e) != 0;
   if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e) != 0;
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
@@ -587,6 +598,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.block_n = w.block_n;
   g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
   const bool staged = epi == EPI_STAGED;
+  g.unit_rows = (staged && ((g_rows6_mask >> ((g.dual ? w.block_n / 2 : w.block_n) / 32)) & 1u) && !g.last_mode && g.down_r == 0) ? 6 : 4;
   g.epi_groups = (epi == EPI_STFT && w.block_n <= 64 && g_epi_groups) ? 2 : 1;
   if (staged && g.taps != 1 && g.taps != 5) WV_THROW(WV_ERR_INVALID, "taps must be 1 or 5");
   const int num_kb = ceil_div(K, BK);
