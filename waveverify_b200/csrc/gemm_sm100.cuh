@@ -90,6 +90,8 @@ struct GemmArgs {
   int dual;           // 1 (with a2_split): the tile's columns are [acc1 | acc2], block_n/2 channels each: acc1 = the 1x1 conv
                       //    that feeds the depthwise taps, acc2 = a second 1x1 conv over the second A tensor that is added
                       //    un-tapped (last encoder resblock + spectrogram branch in one launch, modules/seanet.py:936-943)
+  int math_groups;    // STAGED: 2 = the twelve math warps form two groups of six, one per staging tile, so that the per-tile
+                      //   serial part of a group (tile coordinates, barrier hand-off, last partial pass) overlaps the other group's math
   int unit_rows;      // STAGED math units: rows per unit (4, or 6 for tile widths whose 4-row groups leave the second pass mostly idle)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
@@ -345,11 +347,15 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   constexpr int ROWS_OUT = BM - HALO;
   constexpr int N_GROUPS = (ROWS_OUT + R - 1) / R;
   const int pitch = staged_pitch_bytes(g.block_n);
-  const int et = threadIdx.x - (128 + P1_WARPS * 32);
+  const int et_all = threadIdx.x - (128 + P1_WARPS * 32);
+  const int gthreads = g.math_groups == 2 ? P2_THREADS / 2 : P2_THREADS;   // threads that share a tile
+  const int my_grp = et_all >= gthreads ? 1 : 0;                 // group g owns the CTA's tiles g, g+2, .. and staging tile g
+  const int et = et_all - my_grp * gthreads;
+  const int bar_threads = P1_WARPS * 32 + gthreads;              // drain warps + this group
   const int bn = DUAL ? g.block_n >> 1 : g.block_n;              // output channels per tile
   const int n_ch = DUAL ? g.N >> 1 : g.N;                        // output channels of the layer
   const int cgs = bn >> 2;                                       // 4-channel groups per row
-  const int gstride = P2_THREADS / cgs;                          // row groups per pass
+  const int gstride = gthreads / cgs;                            // row groups per pass
   const int cg = et % cgs, grp0 = et / cgs;
   const bool active = grp0 < gstride;
   const size_t row_bytes = static_cast<size_t>(g.ldo) * 2;
@@ -357,10 +363,14 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
   int cached_nt = -1;
   __half2 wt[TAPS][2], bs[2];
-  int sb = 0;
-  int tiles_left = cta_tile_count(g);
-  int dbg_it = 0;
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+  const bool two = g.math_groups == 2;
+  int sb = two ? my_grp : 0;
+  const int tiles_cta = cta_tile_count(g);
+  int tiles_left = two ? (tiles_cta - my_grp + 1) >> 1 : tiles_cta;   // tiles this group still has to process
+  const int keep = two ? 1 : g.stage_bufs;                         // no later drain waits for the last `keep` tiles
+  int dbg_it = 0, idx = 0;
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++idx) {
+    if (two && (idx & 1) != my_grp) continue;
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
     const int c = tc.nt * bn + cg * 4;
     if (active && tc.nt != cached_nt) {                            // per-CTA constant when N fits one tile
@@ -396,9 +406,10 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     if constexpr (RES) {
       if (have) load_res(grp * R, rres);
     }
-    named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);                 // drain warps staged tile sb
-    if (et == 0) WV_DBG(5, dbg_it);
-    if (lane == 0) WV_DBG(24 + (et >> 5), dbg_it);   // per math warp: start
+    if (et_all == 0) WV_DBG(7, dbg_it);                           // warp 0 reaches the hand-off barrier
+    named_bar_sync(BAR_ST_FULL + sb, bar_threads);                 // drain warps staged tile sb
+    if (et_all == 0) WV_DBG(5, dbg_it);
+    if (lane == 0) WV_DBG(24 + (et_all >> 5), dbg_it);   // per math warp: start
     const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
     if (WV_DBG_MODE(2)) have = false;
     while (have) {
@@ -422,11 +433,11 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       have = have_next;
     }
     __syncwarp();
-    if (et == 0) WV_DBG(6, dbg_it);
-    if (lane == 0) WV_DBG(12 + (et >> 5), dbg_it);   // per math warp: end
+    if (lane == 0) WV_DBG(12 + (et_all >> 5), dbg_it);   // per math warp: end
+    if (--tiles_left >= keep) named_bar_arrive(BAR_ST_EMPTY + sb, bar_threads);   // tile sb may be refilled
+    if (et_all == 0) WV_DBG(6, dbg_it);              // warp 0: after releasing the staging tile
     ++dbg_it;
-    if (--tiles_left >= g.stage_bufs) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);   // tile sb may be refilled
-    if (++sb == g.stage_bufs) sb = 0;
+    if (!two && ++sb == g.stage_bufs) sb = 0;
   }
 }
 
@@ -786,6 +797,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp < 4 + P1_WARPS) {
       // ---------------------------------------------------------- drain warps: TMEM -> fp16 -> smem
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
+      const int drain_bar_threads = P1_WARPS * 32 + (g.math_groups == 2 ? P2_THREADS / 2 : P2_THREADS);
       const uint32_t stage_u32 = smem_u32(stage_tiles);
       int as = 0, sb = 0, it = 0;
       uint32_t as_phase = 0;
@@ -795,7 +807,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int l_ = seq_tile(g, k_, done);
         if (done) break;
         if (l_ < 0) continue;
-        if (it >= g.stage_bufs) named_bar_sync(BAR_ST_EMPTY + sb, EPI_THREADS);   // math warps left tile sb
+        if (it >= g.stage_bufs) named_bar_sync(BAR_ST_EMPTY + sb, drain_bar_threads);   // math warps left tile sb
         mbar_wait(&acc_full[as], as_phase);
         if (q == 0 && lane == 0) WV_DBG(3, it);
         if (lane == 0) WV_DBG(36 + q, it);           // per drain warp: start
@@ -824,7 +836,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
         if (q == 0 && lane == 0) WV_DBG(4, it);
         if (lane == 0) WV_DBG(8 + q, it);            // per drain warp: end
-        named_bar_arrive(BAR_ST_FULL + sb, EPI_THREADS);   // release: this warp's 32 rows are staged
+        named_bar_arrive(BAR_ST_FULL + sb, drain_bar_threads);   // release: this warp's 32 rows are staged
         if (++as == acc_stages) { as = 0; as_phase ^= 1; }
         if (++sb == g.stage_bufs) sb = 0;
         ++it;

@@ -127,6 +127,8 @@ long long g_graph_max_samples = 32 * 16000;   // calls of up to this many sample
 int g_ldy_align = 8;        // log-spectrogram row pitch in elements (WV_LDY_ALIGN: 8 = 16 B, 16 = 32 B = one DRAM sector per chunk)
 unsigned g_rows6_mask = (1u << (64 / 32)) | (1u << (128 / 32));   // STAGED tiles of these widths (bit = channels / 32) use 6-row math units:
                             // 4-row groups leave their last pass mostly idle there (WV_ROWS6_BN = comma list of widths, 0 = off)
+int g_math_groups = 4;      // STAGED math warps as two groups of six, one per staging tile: 1 = never, 2 = always, 3 = launches without a
+                            // residual, 4 = per launch class as measured (WV_MATH_GROUPS)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
@@ -160,6 +162,7 @@ void init_device_once() {
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
+  if (const char* e = getenv("WV_MATH_GROUPS")) g_math_groups = atoi(e);
   if (const char* e = getenv("WV_ROWS6_BN")) {
     g_rows6_mask = 0;
     for (const char* q = e; *q;) {
@@ -609,6 +612,15 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   // long-K layers (>= g_one_buf_kb k-blocks per tile, W streamed) could run with one staging tile and a deeper
   // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
   g.stage_bufs = (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb) ? 1 : STAGE_BUFS;
+  {
+    // measured per launch class (profiles/r01h_math_groups.md): two groups win for the 1x1 + dw5 launches without a
+    // residual (resblock first halves, -5..-12 %) and for the 64-column tiles / the spec-fused launch with one;
+    // they lose 2-4 % on the residual launches with 96 / 128-column tiles and on the plain 1x1 launches
+    const int bn_eff = g.dual ? w.block_n / 2 : w.block_n;
+    const bool heur = g.residual == nullptr ? g.taps == 5 : (bn_eff == 64 || g.dual);
+    const bool want = g_math_groups == 2 || (g_math_groups == 3 && g.residual == nullptr) || (g_math_groups == 4 && heur);
+    g.math_groups = (staged && want && g.stage_bufs == 2 && g.down_r == 0 && !g.last_mode) ? 2 : 1;
+  }
   // pair mode (two M tiles per W k-block) for the long-K layers whose W tile does not stay resident
   const bool pair = staged && !resident && g.down_r == 0 && g.a2_split == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
   g.pair = pair ? 1 : 0;
@@ -1991,6 +2003,7 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
       CK(cudaMalloc(&d, 48 * 40 * sizeof(long long)));
       CK(cudaMemset(d, 0, 48 * 40 * sizeof(long long)));
       ops[0].g.dbg = d;
+      if (getenv("WV_TIMELINE_MODE")) ops[0].g.dbg_mode = atoi(getenv("WV_TIMELINE_MODE"));   // probes + ablation bits
       launch_gemm(ops[0], ops[0].g, static_cast<cudaStream_t>(stream));
       CK(cudaDeviceSynchronize());
       std::vector<long long> h(48 * 40);
@@ -2000,7 +2013,7 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
       printf("tile: tma_issue  data_in  mma_commit  drain_start drain_end  math_start math_end   (cycles from first TMA)\n");
       for (int i = 0; i < 40; ++i) {
         printf("%3d:", i);
-        for (int k = 0; k < 7; ++k) printf(" %9lld", h[i * 40 + k] ? h[i * 40 + k] - t0 : -1);
+        for (int k = 0; k < 8; ++k) printf(" %9lld", h[i * 40 + k] ? h[i * 40 + k] - t0 : -1);   // column 8 = warp 0 at the hand-off barrier
         printf(" | drain start");
         for (int k = 36; k < 40; ++k) printf(" %6lld", h[i * 40 + k] - t0);
         printf(" end");
