@@ -92,6 +92,8 @@ struct GemmArgs {
                       //    un-tapped (last encoder resblock + spectrogram branch in one launch, modules/seanet.py:936-943)
   int math_groups;    // STAGED: 2 = the twelve math warps form two groups of six, one per staging tile, so that the per-tile
                       //   serial part of a group (tile coordinates, barrier hand-off, last partial pass) overlaps the other group's math
+  int a_prefetch;     // > 0: the producer asks L2 for the A rows of the tile this many tiles ahead (cp.async.bulk.prefetch.tensor):
+                      //   DRAM -> L2 runs further ahead than the shared-memory ring can hold
   int unit_rows;      // STAGED math units: rows per unit (4, or 6 for tile widths whose 4-row groups leave the second pass mostly idle)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
@@ -700,7 +702,20 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       } else
+      {
+      TileWalker pf(g);
+      for (int i = 0; i < g.a_prefetch && pf.tile < g.num_tiles; ++i) pf.next(g);
       for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++dbg_it) {
+        if (g.a_prefetch > 0 && pf.tile < g.num_tiles) {
+          const int pr0 = pf.mi * rows_out - halo;
+          if (pf.nt == 0 && pr0 >= 0 && g.phases <= 1) {
+            const int kbs = g.a2_split > 0 ? g.a2_split : (g.kb_split > 0 ? g.kb_split : num_kb);
+            for (int kb = 0; kb < kbs; ++kb) tma_prefetch_l2_3d(&tmA, kb * BK, pr0, pf.clip);
+            if (g.a2_split > 0)
+              for (int kb = g.a2_split; kb < num_kb; ++kb) tma_prefetch_l2_3d(&tmR, (kb - g.a2_split) * BK, pr0, pf.clip);
+          }
+          pf.next(g);
+        }
         const int r0 = tc.mi * rows_out - halo;   // may be negative: zero fill
         const int n0 = tc.nt * g.block_n;
         // (An L2 prefetch of the tile's residual rows from here - cp.async.bulk.prefetch.tensor through
@@ -717,6 +732,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (!g.resident_b) tma_load_2d(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, n0);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
+      }
       }
     }
   } else if (warp == 1) {

@@ -129,6 +129,7 @@ unsigned g_rows6_mask = (1u << (64 / 32)) | (1u << (128 / 32));   // STAGED tile
                             // 4-row groups leave their last pass mostly idle there (WV_ROWS6_BN = comma list of widths, 0 = off)
 int g_math_groups = 4;      // STAGED math warps as two groups of six, one per staging tile: 1 = never, 2 = always, 3 = launches without a
                             // residual, 4 = per launch class as measured (WV_MATH_GROUPS)
+int g_a_prefetch = 0;       // STAGED / STFT producers prefetch the A rows of the tile this many tiles ahead into L2 (WV_A_PREFETCH, 0 = off)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
@@ -162,6 +163,7 @@ void init_device_once() {
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
+  if (const char* e = getenv("WV_A_PREFETCH")) g_a_prefetch = atoi(e);
   if (const char* e = getenv("WV_MATH_GROUPS")) g_math_groups = atoi(e);
   if (const char* e = getenv("WV_ROWS6_BN")) {
     g_rows6_mask = 0;
@@ -611,6 +613,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.resident_b = resident ? 1 : 0;
   // long-K layers (>= g_one_buf_kb k-blocks per tile, W streamed) could run with one staging tile and a deeper
   // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
+  g.a_prefetch = staged ? g_a_prefetch : 0;
   g.stage_bufs = (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb) ? 1 : STAGE_BUFS;
   {
     // measured per launch class (profiles/r01h_math_groups.md): two groups win for the 1x1 + dw5 launches without a
