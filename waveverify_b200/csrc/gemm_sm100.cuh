@@ -116,6 +116,13 @@ struct GemmArgs {
   act_t* out_act;
   float act_scale;
   int ldo;
+  // STAGED, pre mode (pre_w != nullptr, residual == nullptr): the residual stream of the encoder's first resblock is the
+  // output of conv_pre (1 -> C, k = 5 causal, modules/seanet.py:657-664); the math warps recompute it from five waveform
+  // samples (same fp32 FMA order and fp16 rounding as conv_pre_kernel: bit-identical) instead of reading C channels
+  const float* pre_w;   // [5][C] fp32, 1/wav_std folded
+  const float* pre_b;   // [C]
+  const float* pre_x;   // [clips, pre_T] fp32 waveform (set at run time)
+  int pre_T;
   // STAGED, last_mode: the decoder's output conv C -> 1, k = 5 (modules/seanet.py:1177-1202) as a GEMM with one
   // column per tap (P[t, j] = w_j . a[t]) and out[t] = tanh(b + sum_j P[t-4+j, j]); fp32 staging; fused trim + watermark add
   int last_mode, last_T;
@@ -343,7 +350,7 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
 
 // STAGED math warps.  thread = (4-channel group, R-row group): 8-byte smem reads / global accesses
 // keep a warp on contiguous row segments; a thread walks its row groups in passes of 384 threads.
-template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE, bool DUAL = false>
+template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE, bool DUAL = false, bool PRE = false>
 __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   constexpr int HALO = TAPS - 1;
   constexpr int ROWS_OUT = BM - HALO;
@@ -398,10 +405,40 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     // second unit before the first unit's math, so their latency overlaps the wait / the math.
     uint2 rres[R], rnext[R];
     auto load_res = [&](int ro, uint2 (&r)[R]) {
-      const char* rp = reinterpret_cast<const char*>(g.residual + base + static_cast<size_t>(ro) * g.ldo);
+      if constexpr (PRE) {   // v[t,c] = b[c] + sum_j w[j][c] * x[t-4+j], rounded to fp16 like conv_pre_kernel stores it
+        const float* xp = g.pre_x + static_cast<size_t>(tc.clip) * g.pre_T;
+        const int t0 = r_base + ro - 4;
+        float xs[R + 4];
 #pragma unroll
-      for (int i = 0; i < R; ++i)
-        r[i] = ro + i < rows_left ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
+        for (int k = 0; k < R + 4; ++k) {
+          const int tt = t0 + k;
+          xs[k] = (tt >= 0 && tt < g.pre_T) ? __ldg(xp + tt) : 0.f;
+        }
+        // taps and bias come from L1 every unit (24 registers would not fit next to the unit's working set)
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.pre_b + c));
+        float o[R][4];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { o[i][0] = b0.x; o[i][1] = b0.y; o[i][2] = b0.z; o[i][3] = b0.w; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {   // per output the FMA order is j = 0..4, as in conv_pre_kernel
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(g.pre_w + j * n_ch + c));
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            o[i][0] = fmaf(w0.x, xs[i + j], o[i][0]);
+            o[i][1] = fmaf(w0.y, xs[i + j], o[i][1]);
+            o[i][2] = fmaf(w0.z, xs[i + j], o[i][2]);
+            o[i][3] = fmaf(w0.w, xs[i + j], o[i][3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          r[i] = ro + i < rows_left ? make_uint2(pack_act2(o[i][0], o[i][1]), pack_act2(o[i][2], o[i][3])) : make_uint2(0u, 0u);
+      } else {
+        const char* rp = reinterpret_cast<const char*>(g.residual + base + static_cast<size_t>(ro) * g.ldo);
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          r[i] = ro + i < rows_left ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
+      }
     };
     int grp = grp0;
     bool have = active && grp < N_GROUPS && grp * R < rows_left;
@@ -587,6 +624,19 @@ __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const ui
 template <int TAPS>
 __device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   if constexpr (TAPS == 5) {
+    if (g.pre_w != nullptr) {   // first encoder resblock: residual recomputed from the waveform (conv_pre)
+      const bool sc = g.act_scale != 1.f;
+#define WV_PRE(RR, RAWO, SC, DU) staged_math_loop<5, RR, true, RAWO, true, SC, DU, true>(g, stage_tiles, lane)
+      if (g.dual) {             // single-resblock stages (Locator): the same launch also carries the spectrogram 1x1
+        if (g.unit_rows == 6) { if (sc) WV_PRE(6, false, true, true); else WV_PRE(6, false, false, true); }
+        else { if (sc) WV_PRE(4, false, true, true); else WV_PRE(4, false, false, true); }
+      } else {
+        if (g.unit_rows == 6) { if (sc) WV_PRE(6, true, true, false); else WV_PRE(6, true, false, false); }
+        else { if (sc) WV_PRE(4, true, true, false); else WV_PRE(4, true, false, false); }
+      }
+#undef WV_PRE
+      return;
+    }
     if (g.dual) {   // last encoder resblock + spectrogram 1x1: residual in, activated output only
       if (g.unit_rows == 6) {
         if (g.act_scale != 1.f) staged_math_loop<5, 6, true, false, true, true, true>(g, stage_tiles, lane);

@@ -130,6 +130,8 @@ unsigned g_rows6_mask = (1u << (64 / 32)) | (1u << (128 / 32));   // STAGED tile
 int g_math_groups = 4;      // STAGED math warps as two groups of six, one per staging tile: 1 = never, 2 = always, 3 = launches without a
                             // residual, 4 = per launch class as measured (WV_MATH_GROUPS)
 int g_a_prefetch = 0;       // STAGED / STFT producers prefetch the A rows of the tile this many tiles ahead into L2 (WV_A_PREFETCH, 0 = off)
+bool g_pre_fuse = false;    // the first encoder resblock recomputes its residual (= conv_pre output) from the waveform instead of reading it
+                            // (WV_PRE_FUSE=1; bit-identical; measured r01h: conv_pre 68 -> 61 us, r0.out 113 -> 121 us, +-0 overall: off)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
@@ -163,6 +165,7 @@ void init_device_once() {
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
+  if (const char* e = getenv("WV_PRE_FUSE")) g_pre_fuse = atoi(e) != 0;
   if (const char* e = getenv("WV_A_PREFETCH")) g_a_prefetch = atoi(e);
   if (const char* e = getenv("WV_MATH_GROUPS")) g_math_groups = atoi(e);
   if (const char* e = getenv("WV_ROWS6_BN")) {
@@ -737,18 +740,24 @@ void add_dw5(PlanCtx& c, const DwW& w, const h16* in, const h16* res, h16* out_r
 // 1x1 conv (tcgen05 GEMM) with the following causal depthwise k=5 conv fused into its epilogue:
 // per-clip overlapping tiles (128 rows in, 124 out).  A is [B, T, K] channels-last.
 void add_gemm_dw(PlanCtx& c, const GemmW& pw, const DwW& dw, const h16* A, int T, int K, const h16* res,
-                 h16* out_raw, h16* out_act, float act_scale) {
+                 h16* out_raw, h16* out_act, float act_scale, const DwW* pre = nullptr) {
   if (dw.k != 5 || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused depthwise conv must be k=5 over the GEMM's N");
   GemmArgs g = std_args(dw.bias, res, out_raw, out_act, act_scale, pw.N);
   g.taps = 5;
   g.dw_w = dw.w;
+  if (pre != nullptr) {   // residual = conv_pre(waveform), recomputed in the epilogue (io.x at run time)
+    if (res != nullptr || (!c.dry() && (!out_raw || !out_act)) || pre->k != 5 || pre->C != pw.N || !pre->bias)
+      WV_THROW(WV_ERR_INVALID, "pre-conv residual needs k=5 taps over N, both outputs and no stored residual");
+    g.pre_w = pre->w; g.pre_b = pre->bias; g.pre_T = T;
+  }
   CUtensorMap tm;
   if (!c.dry()) tm = make_tmap(A, 3, K, T, c.B, K, static_cast<uint64_t>(K) * T, BK, BM, false);
   add_gemm(c, EPI_STAGED, pw, nullptr, 0, 0, K, g, &tm, T, c.B);
   Op& op = c.ops->back();
   const double n = static_cast<double>(c.B) * T;
   op.flops += 10.0 * n * pw.N;
-  op.bytes = n * 2.0 * (K + pw.N * ((res ? 1 : 0) + (out_raw ? 1 : 0) + (out_act ? 1 : 0))) + static_cast<double>(pw.N) * K * 2.0;
+  op.bytes = n * 2.0 * (K + pw.N * ((res ? 1 : 0) + (out_raw ? 1 : 0) + (out_act ? 1 : 0))) + static_cast<double>(pw.N) * K * 2.0 +
+             (pre ? n * 4.0 : 0.0);
 }
 
 // Encoder downsample (modules/seanet.py:745-771): 1x1 conv C -> 2C (tcgen05 GEMM) with the strided
@@ -813,7 +822,7 @@ void add_resblock_fused(PlanCtx& c, const ResW& r, const h16* X, int T, int C, h
 // One residual block (modules/seanet.py:245-281).  X raw (residual), A = ELU(X*pre_scale).
 // Produces Xn (raw, if need_raw) and An = ELU(Xn*next_act_scale) (if need_act); frees X and A.
 void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool need_raw, bool need_act,
-                   float next_act_scale, Buf& Xn, Buf& An, const std::string& name) {
+                   float next_act_scale, Buf& Xn, Buf& An, const std::string& name, const DwW* pre = nullptr) {
   const long long M = static_cast<long long>(c.B) * T;
   const size_t bytes = static_cast<size_t>(M) * C * 2;
   if (resblock_fusable(r, C)) {   // the fused kernel activates X itself: A (if the producer made one) is not read
@@ -836,10 +845,10 @@ void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool
   if (need_raw) Xn = c.alloc(bytes);
   if (need_act) An = c.alloc(bytes);
   c.tag(name + ".out");
-  add_gemm_dw(c, r.pw2, r.dw2, c.ptr<h16>(A2), T, C, c.ptr<h16>(X), need_raw ? c.ptr<h16>(Xn) : nullptr,
-              need_act ? c.ptr<h16>(An) : nullptr, next_act_scale);
+  add_gemm_dw(c, r.pw2, r.dw2, c.ptr<h16>(A2), T, C, pre ? nullptr : c.ptr<h16>(X), need_raw ? c.ptr<h16>(Xn) : nullptr,
+              need_act ? c.ptr<h16>(An) : nullptr, next_act_scale, pre);
   c.release(A2);
-  c.release(X);
+  if (X.valid) c.release(X);
 }
 
 struct Net;
@@ -1154,18 +1163,22 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
     c.push(op);
   }
   int Ts = T, C = e.C0;
-  Buf X = c.alloc(static_cast<size_t>(B) * Ts * C * 2), A = c.alloc(static_cast<size_t>(B) * Ts * C * 2);
+  // the first resblock can recompute its residual (this conv's raw output) from the waveform: X is then never stored
+  const bool pre_mode = g_pre_fuse && !e.stages.empty() && !e.stages[0].res.empty() && !resblock_fusable(e.stages[0].res[0], C) &&
+                        (e.stages[0].res.size() >= 2 || e.stages[0].dual_split_kb > 0);
+  Buf X = pre_mode ? Buf() : c.alloc(static_cast<size_t>(B) * Ts * C * 2), A = c.alloc(static_cast<size_t>(B) * Ts * C * 2);
   {
     Op op;
     op.type = OP_CONV_PRE;
-    op.out0 = c.ptr<h16>(X); op.out1 = c.ptr<h16>(A);
+    op.out0 = pre_mode ? nullptr : c.ptr<h16>(X); op.out1 = c.ptr<h16>(A);
     op.w = e.conv_pre.w; op.bias = e.conv_pre.bias;
     op.fa = e.stages[0].res[0].pre_scale;
     op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
     op.grid = elem_grid(static_cast<long long>(B) * ceil_div(Ts, PRE_TT) * (C / 8));
     op.flops = 10.0 * B * Ts * C;
-    op.bytes = static_cast<double>(B) * Ts * (4.0 + 4.0 * C);
-    op.out_bytes[0] = op.out_bytes[1] = static_cast<size_t>(B) * Ts * C * 2;
+    op.bytes = static_cast<double>(B) * Ts * (4.0 + (pre_mode ? 2.0 : 4.0) * C);
+    op.out_bytes[0] = pre_mode ? 0 : static_cast<size_t>(B) * Ts * C * 2;
+    op.out_bytes[1] = static_cast<size_t>(B) * Ts * C * 2;
     c.tag("enc.pre");
     c.push(op);
   }
@@ -1191,11 +1204,13 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
         Buf Y = plan_spec_stft(c, st.spec, wav16, pitch, lead, Ts, "enc.s" + std::to_string(s) + ".spec", ldy);
         if (ldy != st.dual_ldy) WV_THROW(WV_ERR_INVALID, "log-spectrogram pitch %d != %d", ldy, st.dual_ldy);
         A = c.alloc(bytes);
-        GemmArgs g = std_args(r.dw2.bias, c.ptr<h16>(X), nullptr, c.ptr<h16>(A), down_scale, C);
+        const bool pre_here = pre_mode && s == 0 && j == 0;
+        GemmArgs g = std_args(r.dw2.bias, pre_here ? nullptr : c.ptr<h16>(X), nullptr, c.ptr<h16>(A), down_scale, C);
         g.taps = 5;
         g.dw_w = r.dw2.w;
         g.dual = 1;
         g.a2_split = st.dual_split_kb;
+        if (pre_here) { g.pre_w = e.conv_pre.w; g.pre_b = e.conv_pre.bias; g.pre_T = Ts; }
         CUtensorMap tm;
         if (!c.dry()) tm = make_tmap(c.ptr<h16>(H), 3, C, Ts, B, C, static_cast<uint64_t>(C) * Ts, BK, BM, false);
         c.tag(rname + ".out+spec");
@@ -1204,16 +1219,17 @@ void plan_encoder(PlanCtx& c, wv_net& n, Plan& plan) {
         if (!c.dry()) op.tmR = make_tmap(c.ptr<h16>(Y), 3, ldy, Ts, B, ldy, static_cast<uint64_t>(ldy) * Ts, BK, BM, false);
         const double n = static_cast<double>(B) * Ts;
         op.flops = 2.0 * n * C * (C + ldy) + 10.0 * n * C;
-        op.bytes = n * 2.0 * (C + ldy + C + C) + static_cast<double>(C) * (C + ldy) * 2.0;   // h1, y, x in; A out
+        op.bytes = n * 2.0 * (C + ldy + (pre_here ? 0 : C) + C) + (pre_here ? n * 4.0 : 0.0) + static_cast<double>(C) * (C + ldy) * 2.0;   // h1, y, x in; A out
         op.out_bytes[0] = 0;
         op.out_bytes[1] = bytes;
         c.release(H);
         c.release(Y);
-        c.release(X);
+        if (X.valid) c.release(X);
         break;
       }
       Buf Xn, An;
-      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An, rname);
+      plan_resblock(c, st.res[j], X, A, Ts, C, true, !last, last ? 1.f : st.res[j + 1].pre_scale, Xn, An, rname,
+                    (pre_mode && s == 0 && j == 0) ? &e.conv_pre : nullptr);
       X = Xn; A = An;
     }
     if (!fuse_spec)
@@ -1506,6 +1522,7 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         GemmArgs g = op.g;
         if (op.epi == EPI_L2NORM) g.out_f32_t = io.latent;
         if (g.last_mode) { g.last_x = io.x; g.last_wm = io.wm; g.last_y = io.y; }
+        if (g.pre_w != nullptr) g.pre_x = io.x;
         if (op.epi == EPI_HEAD) {
           g.logits = io.logits; g.mask_out = io.mask; g.probs = io.probs; g.presence = io.presence;
           if (!(io.bits || io.avg || io.conf || io.valid)) g.partial = nullptr;
