@@ -265,11 +265,39 @@ def run_ours(a):
     d2h = hy.numel() * 4 + hbits.numel() + hconf.numel() * 4 + hmask.numel()
     cnt2 = torch.zeros(6, dtype=torch.int64, device=dev)
 
+    # Every step copies its own inputs host -> device and its results device -> host; the copies run on two
+    # side streams with double-buffered device inputs, so step k+1's upload and step k-1's download overlap
+    # step k's kernels (what a serving loop does); all of them lie inside the timed region.
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    xd2 = [torch.empty_like(x) for _ in range(2)]
+    md2 = [torch.empty(B, 16, dtype=torch.float32, device=dev) for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]      # compute no longer reads input buffer i
+    ev_out = [torch.cuda.Event() for _ in range(3)]      # step k's download finished
+    e2e_k = [0]
+    alive = []                                           # outputs of the last steps: kept until their download is ordered before main
+
     def e2e_step():
-        xd = hx.to(dev, non_blocking=True); md = hm.to(dev, non_blocking=True)
-        y, d, l = step(xd, md, cnt2)
-        hy.copy_(y, non_blocking=True); hbits.copy_(d["bits"], non_blocking=True)
-        hconf.copy_(d["conf"], non_blocking=True); hmask.copy_(l["mask"], non_blocking=True)
+        k = e2e_k[0]; i = k & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(s_in):
+            if k >= 2:
+                s_in.wait_event(ev_free[i])
+            xd2[i].copy_(hx, non_blocking=True); md2[i].copy_(hm, non_blocking=True)
+            ev_in[i].record(s_in)
+        main.wait_event(ev_in[i])
+        if len(alive) == 2:                              # step k-2's outputs may be recycled once its download is done
+            main.wait_event(ev_out[(k - 2) % 3])
+            alive.pop(0)
+        y, d, l = step(xd2[i], md2[i], cnt2)
+        ev_free[i].record(main)                          # also marks the step's end for the download stream
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_free[i])
+            hy.copy_(y, non_blocking=True); hbits.copy_(d["bits"], non_blocking=True)
+            hconf.copy_(d["conf"], non_blocking=True); hmask.copy_(l["mask"], non_blocking=True)
+            ev_out[k % 3].record(s_out)
+        alive.append((y, d, l))
+        e2e_k[0] = k + 1
 
     for _ in range(2):
         e2e_step()
@@ -361,7 +389,9 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "clips_per_gpu": B, "clip_seconds": a.seconds,
                        "l2": "flushed between steps (256 MiB memset outside the per-step events); per-step activations >> L2",
                        "weights": "random-init conf/base.yml architecture (fixture weights)", "parallelism": f"dp{world} (clips sharded, no hot-loop collective; Locator on a side stream next to the Detector)",
-                       "chunk_seconds": a.chunk_seconds},
+                       "chunk_seconds": a.chunk_seconds,
+                       "e2e": "per step: pinned host -> device copy of x and msg, embed+detect+locate, device -> host copy of y, bits, "
+                              "confidence and mask; copies on two side streams, device inputs double-buffered; wall clock over the loop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * a.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
