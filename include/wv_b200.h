@@ -139,6 +139,10 @@ int wv_effect_suppress(float* audio, float* mask, const long long* idx, int B, i
 /* median_filter (:1246-1312, scipy.signal.medfilt: zero-padded ends), odd k <= 31. */
 int wv_effect_median(const float* in, int B, int T, int k, float* out, void* stream);
 
+/* julius low / high / band-pass as utils/effect_augmentation.py:1684-1871 calls them: odd-length FIR (taps on the
+ * device, designed by the host), replicate padding, out = subtract ? in - fir(in) : fir(in). */
+int wv_effect_fir(const float* in, const float* taps, int n_taps, int B, int T, int subtract, float* out, void* stream);
+
 /* ---- profiling / debugging (used by bench.py and the tests) ------------------------------- */
 /* When enabled, every launch of a forward is bracketed by CUDA events on the caller's stream. */
 int wv_net_set_profile(wv_net* net, int enable);

@@ -124,3 +124,67 @@ def median_filter(x: np.ndarray, kernel_size: int) -> np.ndarray:
             w = np.lib.stride_tricks.sliding_window_view(p, kernel_size)
             out[b, c] = np.sort(w, axis=1)[:, h]
     return out
+
+
+# ---- julius FIR filters (PARITY UNPINNED: julius is absent here; restated from its published algorithm) ----
+def julius_lowpass_taps(cutoffs, zeros=8):
+    """julius.LowPassFilters.__init__ (julius/lowpass.py, v0.2.x), float32 numpy."""
+    if min(cutoffs) < 0:
+        raise ValueError("Minimum cutoff must be larger than zero.")
+    if max(cutoffs) > 0.5:
+        raise ValueError("A cutoff above 0.5 does not make sense.")
+    half = int(zeros / min(c for c in cutoffs if c > 0) / 2)
+    n = 2 * half + 1
+    k = np.arange(n, dtype=np.float64)
+    window = (0.5 - 0.5 * np.cos(2 * np.pi * k / (n - 1))) if n > 1 else np.ones(1)   # hann, periodic=False
+    t = np.arange(-half, half + 1, dtype=np.float64)
+    out = []
+    for c in cutoffs:
+        if c == 0:
+            out.append(np.zeros(n))
+            continue
+        f = 2 * c * window * np.sinc(2 * c * t)          # np.sinc(x) = sin(pi x) / (pi x)
+        out.append(f / f.sum())
+    return np.stack(out)
+
+
+def julius_fir(x: np.ndarray, taps: np.ndarray) -> np.ndarray:
+    """julius.LowPassFilters.forward: replicate-pad by half on both sides, cross-correlate (float64 here)."""
+    half = len(taps) // 2
+    B, C, T = x.shape
+    out = np.empty((B, C, T), np.float64)
+    for b in range(B):
+        for c in range(C):
+            p = np.pad(x[b, c].astype(np.float64), (half, half), mode="edge")
+            out[b, c] = np.correlate(p, taps.astype(np.float64), mode="valid")
+    return out
+
+
+def lowpass_filter(x, cutoff_freq, sample_rate):
+    """utils/effect_augmentation.py:1728-1770 (cutoff normalised by the Nyquist frequency, as the reference does)."""
+    nyq = sample_rate / 2
+    c = max(0.0, min(cutoff_freq, nyq - 1e-5)) / nyq
+    try:
+        taps = julius_lowpass_taps([c])[0]
+    except Exception:
+        return x.astype(np.float64)
+    return julius_fir(x, taps)
+
+
+def highpass_filter(x, cutoff_freq, sample_rate):
+    """utils/effect_augmentation.py:1684-1726; julius: input - lowpass(input)."""
+    nyq = sample_rate / 2
+    c = max(0.0, min(cutoff_freq, nyq - 1e-5)) / nyq
+    try:
+        taps = julius_lowpass_taps([c])[0]
+    except Exception:
+        return x.astype(np.float64)
+    return x.astype(np.float64) - julius_fir(x, taps)
+
+
+def bandpass_filter(x, lo_freq, hi_freq, sample_rate):
+    """utils/effect_augmentation.py:1772-1871; julius.BandPassFilter: lowpass(high) - lowpass(low), shared length."""
+    nyq = sample_rate / 2
+    lo, hi = max(0.0, min(lo_freq, nyq - 1e-5)) / nyq, max(0.0, min(hi_freq, nyq - 1e-5)) / nyq
+    taps = julius_lowpass_taps([lo, hi])
+    return julius_fir(x, taps[1]) - julius_fir(x, taps[0])

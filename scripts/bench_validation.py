@@ -46,7 +46,10 @@ def main():
     for name, kw, traffic in (("amplitude_scaling", dict(scale=0.5), 2), ("quantization", dict(bit_depth=8), 2),
                               ("white_noise (in-kernel Philox)", dict(noise_std=0.01, seed=1), 2),
                               ("random_noise (supplied draw)", dict(noise_std=0.01, noise=x), 3),
-                              ("median_filter k=3", dict(kernel_size=3), 2), ("median_filter k=9", dict(kernel_size=9), 2)):
+                              ("median_filter k=3", dict(kernel_size=3), 2), ("median_filter k=9", dict(kernel_size=9), 2),
+                              ("lowpass_filter 3 kHz (21 taps)", dict(cutoff_freq=3000), 2),
+                              ("highpass_filter 500 Hz (129 taps)", dict(cutoff_freq=500), 2),
+                              ("bandpass_filter 1-3 kHz (65 taps)", dict(cutoff_freq_low=1000, cutoff_freq_high=3000), 2)):
         eff = name.split(" ")[0]
         t = timed(lambda: V.apply_effect(y, eff, **kw))
         rows.append((name, traffic * nbytes, t))

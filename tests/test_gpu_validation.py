@@ -201,3 +201,40 @@ def test_validation_pipeline_runs_and_counts():
     for r in results.values():
         assert 0.0 <= r["ber"] <= 1.0 and 0.0 <= r["miou"] <= 1.0
         assert r["mask"].shape == r["locator_mask"].shape
+
+
+def test_fir_effects_against_oracle():
+    """julius low / high / band-pass (parity unpinned: julius is absent; oracle = its published algorithm in
+    float64).  Tolerance: fp32 accumulation of <= 129 taps, |x| <= 0.5 -> 2e-6 absolute."""
+    sr = 16000
+    for B, T in ((3, 16000), (2, 4097), (1, 50), (2, 1)):
+        x, _ = inputs(31 + T, B, T)
+        xd = dev(x)
+        for name, kw, ref in (
+                ("lowpass_filter", dict(cutoff_freq=3000), lambda: VO.lowpass_filter(x, 3000, sr)),
+                ("lowpass_filter", dict(cutoff_freq=1000), lambda: VO.lowpass_filter(x, 1000, sr)),
+                ("highpass_filter", dict(cutoff_freq=500), lambda: VO.highpass_filter(x, 500, sr)),
+                ("highpass_filter", dict(cutoff_freq=1000), lambda: VO.highpass_filter(x, 1000, sr)),
+                ("bandpass_filter", dict(cutoff_freq_low=1000, cutoff_freq_high=3000), lambda: VO.bandpass_filter(x, 1000, 3000, sr))):
+            out, m = V.apply_effect(xd, name, sample_rate=sr, mask=None, **kw)
+            assert out.shape == xd.shape and m is None
+            assert np.abs(out.cpu().numpy().astype(np.float64) - ref()).max() <= 2e-6, (name, kw, B, T)
+    x, _ = inputs(5, 2, 8000)
+    xd = dev(x)
+    # the reference's quirks: a cutoff above half the Nyquist frequency makes julius raise -> low / high-pass return the
+    # input unchanged, band-pass re-raises the ValueError
+    out, _ = V.apply_effect(xd, "lowpass_filter", sample_rate=sr, cutoff_freq=5000)
+    assert out is xd
+    out, _ = V.apply_effect(xd, "highpass_filter", sample_rate=sr, cutoff_freq=0)
+    assert out is xd
+    with pytest.raises(ValueError):
+        V.apply_effect(xd, "bandpass_filter", sample_rate=sr, cutoff_freq_low=1000, cutoff_freq_high=5000)
+    with pytest.raises(ValueError):
+        V.apply_effect(xd, "bandpass_filter", sample_rate=sr, cutoff_freq_low=3000, cutoff_freq_high=1000)
+    # properties: DC gain 1 for the low-pass (taps sum to 1), low + high = identity
+    c = torch.full((1, 1, 4000), 0.25, device="cuda")
+    lo, _ = V.apply_effect(c, "lowpass_filter", sample_rate=sr, cutoff_freq=1000)
+    assert float((lo - 0.25).abs().max()) < 1e-6
+    lo, _ = V.apply_effect(xd, "lowpass_filter", sample_rate=sr, cutoff_freq=1000)
+    hi, _ = V.apply_effect(xd, "highpass_filter", sample_rate=sr, cutoff_freq=1000)
+    assert float((lo + hi - xd).abs().max()) < 1e-6

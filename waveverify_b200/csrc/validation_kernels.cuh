@@ -238,4 +238,69 @@ effect_median_kernel(const float* __restrict__ in, int B, int T, float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FIR effects: julius.lowpass_filter / highpass_filter / bandpass_filter as the reference calls them
+// (utils/effect_augmentation.py:1684-1871).  julius (third party, unpinned in requirements.txt, absent
+// from the reference tree) builds windowed-sinc low-pass filters of 2*half+1 taps, pads the signal with
+// `half` replicated samples on both sides and cross-correlates; high-pass = x - lowpass(x), band-pass =
+// lowpass_high(x) - lowpass_low(x) with a shared length (taps pre-subtracted on the host).
+//   y[t] = sum_k h[k] * x[clamp(t + k - half, 0, T-1)];   out = subtract ? x[t] - y[t] : y[t]
+// One block = FIR_TILE outputs of one clip; samples + halo and the taps live in shared memory; fp32 FMAs.
+constexpr int FIR_THREADS = 256;
+constexpr int FIR_PER_THREAD = 4;
+constexpr int FIR_TILE = FIR_THREADS * FIR_PER_THREAD;
+constexpr int FIR_MAX_TAPS = 2049;
+
+// A thread owns FIR_PER_THREAD = 4 CONSECUTIVE outputs and slides an 8-sample register window over its inputs: per four
+// taps one 16-byte shared-memory read of samples and one (broadcast) of taps feed 16 FMAs.
+__global__ void __launch_bounds__(FIR_THREADS)
+effect_fir_kernel(const float* __restrict__ in, const float* __restrict__ taps, int n_taps, int B, int T,
+                  int subtract, float* __restrict__ out) {
+  extern __shared__ __align__(16) float fir_sh[];   // [taps padded to 4] then [FIR_TILE + taps_pad] samples
+  const int taps_pad = (n_taps + 3) & ~3;
+  float* hs = fir_sh;
+  float* xs = fir_sh + taps_pad;
+  const int half = n_taps >> 1;
+  for (int i = threadIdx.x; i < taps_pad; i += FIR_THREADS) hs[i] = i < n_taps ? __ldg(taps + i) : 0.f;
+  const int tiles = (T + FIR_TILE - 1) / FIR_TILE;
+  for (long long tile = blockIdx.x; tile < static_cast<long long>(B) * tiles; tile += gridDim.x) {
+    const int b = static_cast<int>(tile / tiles);
+    const int t0 = static_cast<int>(tile - static_cast<long long>(b) * tiles) * FIR_TILE;
+    const float* row = in + static_cast<long long>(b) * T;
+    __syncthreads();
+    for (int i = threadIdx.x; i < FIR_TILE + taps_pad; i += FIR_THREADS) {
+      const int t = min(max(t0 - half + i, 0), T - 1);   // replicate padding
+      xs[i] = __ldg(row + t);
+    }
+    __syncthreads();
+    const float4* xv = reinterpret_cast<const float4*>(xs) + threadIdx.x;   // samples 4*tid .. of the tile
+    const float4* hv = reinterpret_cast<const float4*>(hs);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 lo = xv[0];
+    for (int j = 0; j < taps_pad / 4; ++j) {
+      const float4 hi = xv[j + 1];
+      const float4 h = hv[j];
+      const float w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(hh[kk], w[kk + u], acc[u]);
+      lo = hi;
+    }
+    const int l = threadIdx.x * 4;
+    float y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) y[u] = subtract ? xs[l + u + half] - acc[u] : acc[u];
+    float* op = out + static_cast<long long>(b) * T + t0 + l;
+    if ((T & 3) == 0 && t0 + l + 3 < T) {
+      __stcs(reinterpret_cast<float4*>(op), make_float4(y[0], y[1], y[2], y[3]));   // rows are 16-byte aligned when T % 4 == 0
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (t0 + l + u < T) __stcs(op + u, y[u]);
+    }
+  }
+}
+
 }  // namespace wv

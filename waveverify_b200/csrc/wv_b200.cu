@@ -1914,6 +1914,26 @@ int wv_effect_median(const float* in, int B, int T, int k, float* out, void* str
   });
 }
 
+int wv_effect_fir(const float* in, const float* taps, int n_taps, int B, int T, int subtract, float* out, void* stream) {
+  if (!in || !out || !taps || B < 0 || T <= 0) return fail(WV_ERR_INVALID, "bad FIR arguments");
+  if (n_taps < 1 || n_taps > FIR_MAX_TAPS || n_taps % 2 == 0) return failf(WV_ERR_INVALID, "FIR length %d: odd, 1..%d", n_taps, FIR_MAX_TAPS);
+  return guarded([&] {
+    init_device_once();
+    if (B == 0) return;
+    const size_t smem = static_cast<size_t>(2 * ((n_taps + 3) & ~3) + FIR_TILE) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      CK(cudaFuncSetAttribute(effect_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>((2 * ((FIR_MAX_TAPS + 3) & ~3) + FIR_TILE) * sizeof(float))));
+      attr = true;
+    }
+    const long long tiles = static_cast<long long>(B) * ceil_div(T, FIR_TILE);
+    const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(g_num_sms) * 8));
+    effect_fir_kernel<<<grid, FIR_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(in, taps, n_taps, B, T, subtract, out);
+    CK(cudaGetLastError());
+  });
+}
+
 // ---- profiling / debugging -----------------------------------------------------------------
 int wv_net_set_profile(wv_net* net, int enable) {
   if (!net) return fail(WV_ERR_INVALID, "null net");

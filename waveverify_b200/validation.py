@@ -12,14 +12,15 @@ through the CPU, watermarking.py:777-790).
   call order, so a seeded run selects the same segments as the reference; the data movement is one
   CUDA gather pass (`wv_augment_gather`).  `augment()` applies both plans in a single pass.
 * `apply_effect` covers the effects that need no third-party codec: identity, amplitude_scaling,
-  quantization, random_noise / white_noise, sample_suppression, median_filter
-  (utils/effect_augmentation.py).  The rest (sox / ffmpeg / encodec / julius based) raise
-  NotImplementedError: they are out of scope.
+  quantization, random_noise / white_noise, sample_suppression, median_filter and the julius
+  low / high / band-pass FIR filters (utils/effect_augmentation.py).  The rest (sox / ffmpeg / encodec,
+  resampling, echo, smooth) raise NotImplementedError: they are out of scope.
 
 No CPU fallback: tensors must live on a CUDA device.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -249,7 +250,44 @@ def augment(original: torch.Tensor, watermarked: torch.Tensor, loc: Optional[Loc
 
 # --------------------------------------------------------------------------------------------- effects
 SUPPORTED_EFFECTS = ("identity", "amplitude_scaling", "quantization", "random_noise", "white_noise",
-                     "sample_suppression", "median_filter")
+                     "sample_suppression", "median_filter", "lowpass_filter", "highpass_filter", "bandpass_filter")
+EPSILON = 1e-5   # utils/effect_augmentation.py:92
+
+
+def julius_lowpass_taps(cutoffs: Sequence[float], zeros: float = 8) -> torch.Tensor:
+    """The windowed-sinc low-pass filters of `julius.LowPassFilters(cutoffs, zeros=8)` (julius is a
+    third-party dependency of the reference, unpinned in requirements.txt and absent here; this restates
+    its published design): half = int(zeros / min(cutoff > 0) / 2) taps on each side, Hann window
+    (periodic=False), h = 2 f_c * window * sinc(2 pi f_c n), normalised to sum 1.  Same fp32 torch ops as
+    julius, so the taps are bit-identical to the ones it would build.  Returns [len(cutoffs), 2*half+1]."""
+    cutoffs = [float(c) for c in cutoffs]
+    if min(cutoffs) < 0:
+        raise ValueError("Minimum cutoff must be larger than zero.")
+    if max(cutoffs) > 0.5:
+        raise ValueError("A cutoff above 0.5 does not make sense.")
+    half = int(zeros / min(c for c in cutoffs if c > 0) / 2)     # ValueError on an empty sequence, like julius
+    window = torch.hann_window(2 * half + 1, periodic=False)
+    time = torch.arange(-half, half + 1)
+    out = []
+    for c in cutoffs:
+        if c == 0:
+            out.append(torch.zeros(2 * half + 1))
+            continue
+        arg = 2 * c * math.pi * time
+        sinc = torch.where(arg == 0, torch.tensor(1.0), torch.sin(arg) / arg)
+        f = 2 * c * window * sinc
+        out.append(f / f.sum())
+    return torch.stack(out)
+
+
+def _fir(x: torch.Tensor, taps: torch.Tensor, subtract: bool) -> torch.Tensor:
+    xin = _need_cuda(x, "audio").float().contiguous()
+    B, Cn, T = xin.shape
+    h = taps.to(device=xin.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(xin)
+    _lib.check(_lib.lib().wv_effect_fir(_ptr(xin), _ptr(h), int(h.numel()), B * Cn, T, 1 if subtract else 0, _ptr(out),
+                                        _stream(xin.device)), "wv_effect_fir")
+    return out
 
 
 def _pointwise(effect: int, x: torch.Tensor, p0: float, noise: Optional[torch.Tensor] = None, seed: int = 0):
@@ -320,6 +358,33 @@ def apply_effect(audio: torch.Tensor, effect_type: str, sample_rate: int = 16000
         _lib.check(_lib.lib().wv_effect_suppress(_ptr(out), _ptr(m), _ptr(idx), B * Cn, T, int(idx.shape[1]),
                                                  _stream(x.device)), "wv_effect_suppress")
         return out, mask
+    if effect_type in ("lowpass_filter", "highpass_filter"):               # :1684-1770
+        # the reference divides by the Nyquist frequency although julius expects cycles per sample: reproduced
+        cutoff_freq = float(params.get("cutoff_freq", 3000 if effect_type == "lowpass_filter" else 500))
+        nyquist = sample_rate / 2
+        cutoff = max(0.0, min(cutoff_freq, nyquist - EPSILON)) / nyquist
+        try:
+            taps = julius_lowpass_taps([cutoff])[0]
+        except Exception:  # noqa: BLE001  (julius raises -> the reference logs and returns the input unchanged)
+            return audio, mask
+        return _fir(x, taps, subtract=effect_type == "highpass_filter"), mask
+    if effect_type == "bandpass_filter":                                    # :1772-1871 (ValueErrors propagate)
+        if "cutoff_freq_low" not in params or "cutoff_freq_high" not in params:
+            raise TypeError("bandpass_filter needs cutoff_freq_low and cutoff_freq_high")
+        lo_f, hi_f = float(params["cutoff_freq_low"]), float(params["cutoff_freq_high"])
+        nyquist = sample_rate / 2
+        if lo_f < 0:
+            raise ValueError(f"Low cutoff frequency must be non-negative, got {lo_f} Hz")
+        if hi_f < 0:
+            raise ValueError(f"High cutoff frequency must be non-negative, got {hi_f} Hz")
+        lo_a, hi_a = max(0.0, min(lo_f, nyquist - EPSILON)), max(0.0, min(hi_f, nyquist - EPSILON))
+        if lo_a >= hi_a:
+            raise ValueError(f"Low cutoff {lo_a} Hz must be less than high cutoff {hi_a} Hz")
+        lo, hi = lo_a / nyquist, hi_a / nyquist
+        if not (0.0 < lo < 1.0) or not (0.0 < hi < 1.0):
+            raise ValueError(f"Normalized cutoffs must be between 0 and 1. Got low: {lo}, high: {hi}")
+        taps = julius_lowpass_taps([lo, hi])          # julius.BandPassFilter: lowpass(high) - lowpass(low), shared length
+        return _fir(x, taps[1] - taps[0], subtract=False), mask
     # median_filter                                                         # :1873-1902, 1246-1312
     k = int(params.get("kernel_size", 3))
     if k < 1:
