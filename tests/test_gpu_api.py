@@ -106,3 +106,36 @@ def test_metric_counters_allreduce_single_process():
     c = metric_counters(bits, None, bits.clone(), torch.ones(4, 1, 100, dtype=torch.uint8).cuda(),
                         torch.ones(4, 1, 100, dtype=torch.uint8).cuda())
     assert allreduce_counters(c).tolist() == [0, 64, 400, 400, 0, 0]
+
+
+def test_request_batcher_equals_single_requests():
+    """serving.RequestBatcher: clips of different lengths coalesced into one padded batch give the results of
+    one call per clip (embed: bit-exact - causal nets, independent clips; detect: bits equal, confidence to 1e-6;
+    locate: mask exact)."""
+    from waveverify_b200 import WaveVerify
+    from waveverify_b200.serving import RequestBatcher
+    kw = dict(bias=True, zero_init=False)
+    wv = WaveVerify(checkpoint=None, device="cuda", generator_kwargs=kw, detector_kwargs=kw, locator_kwargs=kw)
+    for kind, m in (("generator", wv.model.generator), ("detector", wv.model.detector), ("locator", wv.model.locator)):
+        _, sd = fixture_weights(kind, False, 3)
+        m.load_state_dict(sd)
+    rng = np.random.RandomState(8)
+    lens = [16000, 12345, 1600, 777, 16000, 3840, 12345, 32000]
+    clips = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in lens]
+    msgs = [rng.randint(0, 2, 16).astype(np.float32) for _ in lens]
+    with RequestBatcher(wv, max_batch=8, max_wait_s=0.5, hop=320) as rb:
+        fe = [rb.embed(c, m) for c, m in zip(clips, msgs)]
+        ys = [f.result(timeout=120) for f in fe]
+        fd = [rb.detect(y) for y in ys]
+        fl = [rb.locate(y) for y in ys]
+        dets = [f.result(timeout=120) for f in fd]
+        locs = [f.result(timeout=120) for f in fl]
+    assert max(rb.batches) >= 5                       # the five hop-aligned clips ran as one padded batch
+    dev = torch.device("cuda")
+    for c, m, y, (bits, conf), mask in zip(clips, msgs, ys, dets, locs):
+        x1 = torch.from_numpy(c).view(1, 1, -1).to(dev)
+        y1 = wv.embed_batch(x1, torch.from_numpy(m).view(1, -1).to(dev))
+        assert np.array_equal(y1.cpu().numpy()[0, 0], y)
+        b1, c1 = wv.detect_batch(y1)
+        assert np.array_equal(b1.cpu().numpy()[0], bits) and abs(float(c1[0]) - conf) < 1e-6
+        assert np.array_equal(wv.locate_batch(y1).cpu().numpy()[0], mask)
