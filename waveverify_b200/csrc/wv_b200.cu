@@ -132,6 +132,7 @@ int g_math_groups = 4;      // STAGED math warps as two groups of six, one per s
 int g_a_prefetch = 0;       // STAGED / STFT producers prefetch the A rows of the tile this many tiles ahead into L2 (WV_A_PREFETCH, 0 = off)
 bool g_pre_fuse = false;    // the first encoder resblock recomputes its residual (= conv_pre output) from the waveform instead of reading it
                             // (WV_PRE_FUSE=1; bit-identical; measured r01h: conv_pre 68 -> 61 us, r0.out 113 -> 121 us, +-0 overall: off)
+int g_res1_kb = 0;          // largest W tile (KB) kept resident next to a single staging tile (WV_RES1_KB; 0 = off)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
@@ -165,6 +166,7 @@ void init_device_once() {
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
+  if (const char* e = getenv("WV_RES1_KB")) g_res1_kb = atoi(e);
   if (const char* e = getenv("WV_PRE_FUSE")) g_pre_fuse = atoi(e) != 0;
   if (const char* e = getenv("WV_A_PREFETCH")) g_a_prefetch = atoi(e);
   if (const char* e = getenv("WV_MATH_GROUPS")) g_math_groups = atoi(e);
@@ -612,12 +614,21 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   const int num_kb = ceil_div(K, BK);
   const int tiles_n_ = w.N / w.block_n;
   const bool nt_fixed = tiles_n_ <= g_num_sms;   // the grid is rounded down to a multiple of tiles_n below
-  const bool resident = gemm_resident_b(w.block_n, num_kb, staged, nt_fixed);
+  bool resident = gemm_resident_b(w.block_n, num_kb, staged, nt_fixed);
+  // W tiles of 64..g_res1_kb KB (C = 512 layers: 128 KB) fit next to ONE staging tile: the ring then streams A only,
+  // which halves the L2 -> SM operand traffic of those layers (they are bound by it); the price is that the drain of
+  // a tile waits for the math of the previous one
+  bool res1 = false;
+  if (!resident && staged && nt_fixed && g_res1_kb > 0) {
+    const int w_bytes = num_kb * w.block_n * BK * 2;
+    res1 = w_bytes <= g_res1_kb * 1024 && (GEMM_SMEM_LIMIT - gemm_fixed_smem(w.block_n, true, 1) - w_bytes) / A_STAGE_BYTES >= 3;
+    resident = res1;
+  }
   g.resident_b = resident ? 1 : 0;
   // long-K layers (>= g_one_buf_kb k-blocks per tile, W streamed) could run with one staging tile and a deeper
   // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
   g.a_prefetch = staged ? g_a_prefetch : 0;
-  g.stage_bufs = (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb) ? 1 : STAGE_BUFS;
+  g.stage_bufs = (res1 || (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb)) ? 1 : STAGE_BUFS;
   {
     // measured per launch class (profiles/r01h_math_groups.md): two groups win for the 1x1 + dw5 launches without a
     // residual (resblock first halves, -5..-12 %) and for the 64-column tiles / the spec-fused launch with one;
