@@ -210,7 +210,7 @@ up_kernel(const act_t* __restrict__ in, const float* __restrict__ w,
 // ---------------------------------------------------------------------------------------
 // conv_pre: 1 -> C, k=5 causal, 1/wav_std folded into w (modules/seanet.py:657-664):
 //   v[t,c] = bias[c] + sum_j w[j][c] * x[t-4+j];  out_raw = v, out_act = ELU(v*act_scale)
-constexpr int PRE_TT = 4;   // consecutive time steps per thread (taps loaded once)
+constexpr int PRE_TT = 8;   // consecutive time steps per thread (taps loaded once)
 __global__ void __launch_bounds__(256)
 conv_pre_kernel(const float* __restrict__ x, const float* __restrict__ w,
                 const float* __restrict__ bias, act_t* __restrict__ out_raw,
