@@ -700,7 +700,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(w_full, 1);
     for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : (EPI == EPI_STFT && g.epi_groups == 2 ? EPI_WARPS / 2 : EPI_WARPS));  // one arrive per draining warp
+      mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : (EPI == EPI_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));  // one arrive per draining warp
     }
     fence_mbar_init();
   }
@@ -926,10 +926,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ epilogue (16 warps)
     const int e = warp - 4;
     const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
-    const bool two_groups = EPI == EPI_STFT && g.epi_groups == 2;
-    const int h = two_groups ? (e >> 2) & 1 : e >> 2;   // column split: this warp takes chunks c with c % split == h
-    const int split = two_groups ? 2 : EPI_SPLIT;
-    const int grp = e >> 3;                              // two_groups: group g owns accumulator stage g = every other tile
+    // STFT: the 16 epilogue warps may form 2 or 4 groups (of 8 / 4 warps: every group covers the four TMEM lane quarters);
+    // group g owns accumulator stage g = every epi_groups-th tile, so that several tiles are in the epilogue at once
+    const int n_groups = EPI == EPI_STFT ? g.epi_groups : 1;
+    const bool two_groups = n_groups > 1;
+    const int gw = EPI_WARPS / n_groups;                 // warps per group
+    const int h = two_groups ? (e % gw) >> 2 : e >> 2;   // column split: this warp takes chunks c with c % split == h
+    const int split = two_groups ? gw >> 2 : EPI_SPLIT;
+    const int grp = e / gw;
     int as = 0;
     uint32_t as_phase = 0;
     for (int k_ = 0;; ++k_) {
@@ -937,7 +941,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int l_ = seq_tile(g, k_, done);
       if (done) break;
       if (l_ < 0) continue;
-      if (two_groups && as != grp) {                     // the other group's tile (acc_stages == 2: stage = tile parity)
+      if (two_groups && as != grp) {                     // another group's tile (acc_stages == epi_groups: stage = tile index mod groups)
         if (++as == acc_stages) { as = 0; as_phase ^= 1; }
         continue;
       }

@@ -135,7 +135,8 @@ bool g_pre_fuse = false;    // the first encoder resblock recomputes its residua
 int g_res1_kb = 0;          // largest W tile (KB) kept resident next to a single staging tile (WV_RES1_KB; 0 = off)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
-bool g_epi_groups = true;   // STFT tiles of <= 64 columns: two epilogue groups, one per accumulator stage (WV_EPI_GROUPS=0 disables)
+int g_epi_groups = 2;       // STFT epilogue warp groups, one accumulator stage each (WV_EPI_GROUPS: 0/1 = one group of 16 warps, 2 = two groups for
+                            // tiles of <= 64 columns, 4 = additionally four groups for tiles of <= 128 columns)
 int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
 int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
 int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
@@ -180,7 +181,7 @@ void init_device_once() {
     }
   }
   if (const char* e = getenv("WV_LAST_GEMM")) g_last_gemm = atoi(e) != 0;
-  if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e) != 0;
+  if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e);
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
   if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
   if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
@@ -609,7 +610,9 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
   const bool staged = epi == EPI_STAGED;
   g.unit_rows = (staged && ((g_rows6_mask >> ((g.dual ? w.block_n / 2 : w.block_n) / 32)) & 1u) && !g.last_mode && g.down_r == 0) ? 6 : 4;
-  g.epi_groups = (epi == EPI_STFT && w.block_n <= 64 && g_epi_groups) ? 2 : 1;
+  g.epi_groups = 1;
+  if (epi == EPI_STFT && g_epi_groups >= 2 && w.block_n <= 64) g.epi_groups = 2;
+  if (epi == EPI_STFT && g_epi_groups >= 4 && w.block_n <= 128) g.epi_groups = 4;
   if (staged && g.taps != 1 && g.taps != 5) WV_THROW(WV_ERR_INVALID, "taps must be 1 or 5");
   const int num_kb = ceil_div(K, BK);
   const int tiles_n_ = w.N / w.block_n;
@@ -641,8 +644,8 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   // pair mode (two M tiles per W k-block) for the long-K layers whose W tile does not stay resident
   const bool pair = staged && !resident && g.down_r == 0 && g.a2_split == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
   g.pair = pair ? 1 : 0;
-  g.acc_stages = pair ? MAX_ACC_STAGES : ACC_STAGES;
-  g.acc_cols = pair ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
+  g.acc_stages = (pair || g.epi_groups == 4) ? MAX_ACC_STAGES : ACC_STAGES;   // four epilogue groups: one 128-column stage each
+  g.acc_cols = (pair || g.epi_groups == 4) ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
   g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs, pair);
   if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
   op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs, pair);
