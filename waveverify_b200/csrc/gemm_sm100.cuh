@@ -94,6 +94,7 @@ struct GemmArgs {
                       //   serial part of a group (tile coordinates, barrier hand-off, last partial pass) overlaps the other group's math
   int a_prefetch;     // > 0: the producer asks L2 for the A rows of the tile this many tiles ahead (cp.async.bulk.prefetch.tensor):
                       //   DRAM -> L2 runs further ahead than the shared-memory ring can hold
+  int res_early2;     // 1: the residual rows of a thread's second unit are requested before the hand-off barrier as well
   int unit_rows;      // STAGED math units: rows per unit (4, or 6 for tile widths whose 4-row groups leave the second pass mostly idle)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
@@ -442,8 +443,13 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     };
     int grp = grp0;
     bool have = active && grp < N_GROUPS && grp * R < rows_left;
+    bool early2 = false;                                           // second unit's residual already requested
     if constexpr (RES) {
       if (have) load_res(grp * R, rres);
+      if (!PRE && g.res_early2) {                                  // both units of the tile in flight across the barrier wait
+        const int gn0 = grp + gstride;
+        if (have && gn0 < N_GROUPS && gn0 * R < rows_left) { load_res(gn0 * R, rnext); early2 = true; }
+      }
     }
     if (et_all == 0) WV_DBG(7, dbg_it);                           // warp 0 reaches the hand-off barrier
     named_bar_sync(BAR_ST_FULL + sb, bar_threads);                 // drain warps staged tile sb
@@ -456,7 +462,8 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       const int gn = grp + gstride;
       const bool have_next = gn < N_GROUPS && gn * R < rows_left;
       if constexpr (RES) {
-        if (have_next) load_res(gn * R, rnext);
+        if (have_next && !early2) load_res(gn * R, rnext);
+        early2 = false;
       }
       const size_t off = base + static_cast<size_t>(ro) * g.ldo;
       const uint32_t srow = tile_u32 + ro * pitch;

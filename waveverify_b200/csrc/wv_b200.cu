@@ -133,6 +133,7 @@ int g_a_prefetch = 0;       // STAGED / STFT producers prefetch the A rows of th
 bool g_pre_fuse = false;    // the first encoder resblock recomputes its residual (= conv_pre output) from the waveform instead of reading it
                             // (WV_PRE_FUSE=1; bit-identical; measured r01h: conv_pre 68 -> 61 us, r0.out 113 -> 121 us, +-0 overall: off)
 int g_res1_kb = 0;          // largest W tile (KB) kept resident next to a single staging tile (WV_RES1_KB; 0 = off)
+bool g_res_early2 = true;   // residual rows of the second unit of a tile requested before the drain hand-off too (WV_RES_EARLY2=0: after it)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 int g_epi_groups = 2;       // STFT epilogue warp groups, one accumulator stage each (WV_EPI_GROUPS: 0/1 = one group of 16 warps, 2 = two groups for
@@ -167,6 +168,7 @@ void init_device_once() {
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
+  if (const char* e = getenv("WV_RES_EARLY2")) g_res_early2 = atoi(e) != 0;
   if (const char* e = getenv("WV_RES1_KB")) g_res1_kb = atoi(e);
   if (const char* e = getenv("WV_PRE_FUSE")) g_pre_fuse = atoi(e) != 0;
   if (const char* e = getenv("WV_A_PREFETCH")) g_a_prefetch = atoi(e);
@@ -631,6 +633,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   // long-K layers (>= g_one_buf_kb k-blocks per tile, W streamed) could run with one staging tile and a deeper
   // operand ring; measured: no gain (the deep stages are bound by L2 -> SM operand traffic, not ring depth): off
   g.a_prefetch = staged ? g_a_prefetch : 0;
+  g.res_early2 = g_res_early2 ? 1 : 0;
   g.stage_bufs = (res1 || (staged && !resident && g_one_buf_kb > 0 && num_kb >= g_one_buf_kb)) ? 1 : STAGE_BUFS;
   {
     // measured per launch class (profiles/r01h_math_groups.md): two groups win for the 1x1 + dw5 launches without a
