@@ -58,7 +58,8 @@ def test_knob_paths_agree(tmp_path):
     base = run(tmp_path, "default", {})
     # bit-identical alternatives: math-warp organisation and residual recomputation do not change any arithmetic
     for name, env in (("groups1", {"WV_MATH_GROUPS": "1"}), ("groups2", {"WV_MATH_GROUPS": "2"}),
-                      ("rows4", {"WV_ROWS6_BN": "0"}), ("pre", {"WV_PRE_FUSE": "1"}), ("prefetch", {"WV_A_PREFETCH": "4"})):
+                      ("rows4", {"WV_ROWS6_BN": "0"}), ("pre", {"WV_PRE_FUSE": "1"}), ("prefetch", {"WV_A_PREFETCH": "4"}),
+                      ("res_late", {"WV_RES_EARLY2": "0"}), ("epi4", {"WV_EPI_GROUPS": "4"}), ("res1", {"WV_RES1_KB": "128"})):
         alt = run(tmp_path, name, env)
         for k in base:
             assert np.array_equal(base[k], alt[k]), f"{name}: {k} differs"
