@@ -66,3 +66,21 @@ def test_wav_round_trip(tmp_path):
     assert float((y[0] - torch.clamp(x * 5, -1, 1)).abs().max()) < 2e-4
     with pytest.raises(FileNotFoundError):
         load_audio(tmp_path / "missing.wav")
+
+
+def test_load_audio_resamples_like_the_reference(tmp_path):
+    """waveverify/utils.py:205-216: mono mix-down, then torchaudio.transforms.Resample(sr, 16000)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import wave
+    from waveverify_b200 import load_audio
+    rng = np.random.RandomState(2)
+    sr, n = 22050, 4410
+    pcm = (rng.standard_normal((n, 2)) * 3000).astype("<i2")
+    p = tmp_path / "stereo.wav"
+    with wave.open(str(p), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(sr); f.writeframes(pcm.tobytes())
+    wav, out_sr = load_audio(p)
+    mono = torch.from_numpy(pcm.astype(np.float32) / 32768.0).T.mean(0, keepdim=True)
+    want = torchaudio.transforms.Resample(sr, 16000)(mono)
+    assert out_sr == 16000 and wav.shape == want.shape
+    assert torch.allclose(wav, want, atol=1e-6)

@@ -63,9 +63,15 @@ def tensor_to_message(tensor: torch.Tensor, threshold: float = 0.5) -> str:
     return "".join(str(int(b)) for b in (tensor >= threshold).int().tolist())
 
 
-def _resample_linear(w: torch.Tensor, sr: int, target: int) -> torch.Tensor:
-    n = int(round(w.shape[-1] * target / sr))
-    return torch.nn.functional.interpolate(w[None], size=n, mode="linear", align_corners=False)[0]
+def _resample(w: torch.Tensor, sr: int, target: int) -> torch.Tensor:
+    """The reference resamples with `torchaudio.transforms.Resample(sr, target)` (waveverify/utils.py:211-213: windowed-sinc
+    polyphase filter, pure torch - needs no codec backend).  Linear interpolation only when torchaudio is not importable."""
+    try:
+        import torchaudio  # type: ignore
+        return torchaudio.transforms.Resample(sr, target)(w)
+    except ImportError:
+        n = int(round(w.shape[-1] * target / sr))
+        return torch.nn.functional.interpolate(w[None], size=n, mode="linear", align_corners=False)[0]
 
 
 def load_audio(audio_path: Union[str, Path], target_sr: int = DEFAULT_SAMPLE_RATE) -> Tuple[torch.Tensor, int]:
@@ -101,7 +107,7 @@ def load_audio(audio_path: Union[str, Path], target_sr: int = DEFAULT_SAMPLE_RAT
             raise RuntimeError(f"Cannot load audio file: unsupported sample width {sw}")
         wav = torch.from_numpy(a.reshape(-1, nch).T.copy())
         if sr != target_sr:
-            wav = _resample_linear(wav.mean(0, keepdim=True), sr, target_sr)
+            wav = _resample(wav.mean(0, keepdim=True), sr, target_sr)
             sr = target_sr
     if wav.shape[0] > 1:
         wav = wav.mean(dim=0, keepdim=True)
