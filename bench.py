@@ -39,7 +39,9 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=1.0, help="clip length")
     ap.add_argument("--chunk-seconds", type=float, default=0.0,
                     help="internal sub-batch size in audio-seconds (0 = whole batch)")
-    ap.add_argument("--cpu-sample-clips", type=int, default=2)
+    ap.add_argument("--cpu-sample-clips", type=int, default=4,
+                    help="clips of the cpu_baseline leg inside the GPU run (the --impl reference arm times the full batch)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU legs (0 = os.cpu_count())")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     return ap.parse_args()
@@ -77,9 +79,26 @@ def synth(B, T, seed):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_oracle_rate(n_clips, T, iters, warm, seed=0):
-    """audio-s/s of the oracle port (fp32 PyTorch restatement of the reference) on host cores."""
+def cpu_threads(a):
+    return a.cpu_threads if a.cpu_threads > 0 else (os.cpu_count() or 1)
+
+
+# What the port does differently from the reference's own modules (model/generator.py:360, detector.py:366,
+# locator.py:268), which cannot travel to the GPU box: weight-norm is folded once instead of being recomputed in
+# every forward, and no padded copies are materialised per conv.  Timed side by side in the build container
+# (8 threads, 8 x 1 s clips, profiles/r02_reference_vs_port_cpu.md): the port is FASTER than the reference,
+# so a GPU / port ratio understates the GPU / reference ratio.
+PORT_NOTE = ("oracle port of the reference's PyTorch path (fp32): folds weight-norm once and skips the per-conv padded copies, "
+             "i.e. it is faster than the unmodified reference modules (profiles/r02_reference_vs_port_cpu.md)")
+
+
+def cpu_oracle_rate(n_clips, T, iters, warm, seed=0, threads=0, budget_s=0.0):
+    """audio-s/s of the oracle port (fp32 PyTorch restatement of the reference) on host cores.
+    threads: explicit intra-op thread count (torchrun exports OMP_NUM_THREADS=1, which would cripple this leg).
+    budget_s > 0: after the first step the number of timed steps is cut (>= 3) so that the run fits the budget."""
     import torch
+    if threads > 0:
+        torch.set_num_threads(threads)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import wv_oracle as O
     mods = make_models(None, seed)
@@ -100,8 +119,12 @@ def cpu_oracle_rate(n_clips, T, iters, warm, seed=0):
             mask = O.locator_mask(ll)
             return O.metric_counters(bits, valid, msg, mask, torch.from_numpy(gt))
 
-    for _ in range(warm):
+    t0 = time.perf_counter()
+    for _ in range(max(warm, 1)):
         step()
+    t1 = (time.perf_counter() - t0) / max(warm, 1)
+    if budget_s > 0:
+        iters = max(3, min(iters, int((budget_s - max(warm, 1) * t1) / max(t1, 1e-6))))
     times = []
     for _ in range(iters):
         t0 = time.perf_counter()
@@ -116,18 +139,22 @@ def run_reference(a):
     if rank != 0:
         return
     T = int(round(a.seconds * SR))
-    n = max(1, min(a.clips, a.cpu_sample_clips))
-    steps, warm = max(1, a.steps), max(0, a.warmup)
-    # bound the run to a few minutes: ~1 s of CPU per audio-second
-    while (steps + warm) * n * a.seconds > 120 and steps > 2:
-        steps -= 1
-    rate, cores, times = cpu_oracle_rate(n, T, steps, warm)
-    sample = f"{n} x {a.seconds:g} s clips per step (bounded sample of the {a.clips}-clip batch), embed+detect+locate, fp32"
+    # the SAME batch as the GPU arm (config 2: 64 x 1 s = ~4 s of CPU per step on 16 cores); only very large
+    # configurations are cut to a bounded sample of clips.  Steps are cut (>= 3) to keep the run within ~4 minutes.
+    n = a.clips
+    while n > 1 and n * a.seconds > 256:
+        n //= 2
+    steps, warm = max(1, a.steps), max(1, min(a.warmup, 2))
+    rate, cores, times = cpu_oracle_rate(n, T, steps, warm, threads=cpu_threads(a), budget_s=240.0)
+    steps = len(times)
+    sample = (f"{n} x {a.seconds:g} s clips per step (" + ("the full batch" if n == a.clips else f"bounded sample of the {a.clips}-clip batch") +
+              f"), embed+detect+locate, fp32, {cores} threads; {PORT_NOTE}")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "l2": "n/a (CPU)"},
+        "config": {"workload": workload_name(a), "clips_per_gpu": n, "clip_seconds": a.seconds, "l2": "n/a (CPU)",
+                   "host_threads": cores, "os_cpu_count": os.cpu_count()},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -178,7 +205,23 @@ class ClockSampler:
 
 CLS_NAMES = {100: "gemm_std", 101: "gemm_l2norm", 102: "gemm_stft", 103: "gemm_head", 1: "dw5", 2: "down", 3: "up",
              4: "conv_pre", 5: "conv_last", 6: "wav_stage", 7: "frames", 8: "film", 9: "bits_finish", 10: "conf",
-             11: "latent_in"}
+             11: "latent_in", 20: "resblock_fused", 104: "gemm_std_precise", 105: "gemm_l2norm_precise", 106: "gemm_stft_precise",
+             30: "conv_pre_precise", 31: "dw5_precise", 32: "wav_stage_precise"}
+
+# algorithmic work per audio-second (16 000 samples, one clip), 2*MAC, convs + STFT only
+SURVEY_GFLOP = {"path": 30.456, "gemm_1x1": 27.33, "stft": 2.30, "heads": 0.21, "depthwise": 0.57}
+SURVEY_IO_BYTES = 1.28e6      # embed 8 B/sample + detect/locate with fp32 logits 72 B/sample
+
+
+def build_id():
+    """sha256 prefix of the shared library the run loaded: stamps the ncu summaries so that staleness is visible."""
+    import hashlib
+    from waveverify_b200 import _lib
+    h = hashlib.sha256()
+    with open(_lib.LIB_PATH, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()[:12]
 
 
 def run_ours(a):
@@ -203,6 +246,10 @@ def run_ours(a):
         for m in mods.values():
             m.set_chunk_samples(int(a.chunk_seconds * SR))
     G, D, L = mods["generator"], mods["detector"], mods["locator"]
+    if os.environ.get("WV_EXACT_BITS") is not None:          # A/B switches for profiling; the defaults are the API's
+        D.exact_bits = os.environ["WV_EXACT_BITS"] != "0"
+    if os.environ.get("WV_EXACT_MASK") is not None:
+        L.exact = os.environ["WV_EXACT_MASK"] != "0"
     x_np, msg_np, gt_np = synth(B, T, 100 + rank)
     x = torch.from_numpy(x_np).to(dev); msg = torch.from_numpy(msg_np).to(dev); gt = torch.from_numpy(gt_np).to(dev)
     counters = torch.zeros(6, dtype=torch.int64, device=dev)
@@ -227,6 +274,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     launches_per_step = G.launches(B, T) + D.launches(B, T) + L.launches(B, T) + 1
     counters.zero_()
+    recheck0 = D.recheck_count
 
     def barrier():
         if world > 1:
@@ -251,12 +299,15 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
+    recheck_per_step = (D.recheck_count - recheck0) / max(1, a.steps)
     audio_s_per_step = B * T / SR * world
     value = audio_s_per_step * a.steps / (total_ms / 1e3)
     ber, miou = ber_miou(counters)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing ----
     hx = torch.from_numpy(x_np).pin_memory(); hm = torch.from_numpy(msg_np.astype("float32")).pin_memory()
+    x_np2, msg_np2, _ = synth(B, T, 200 + rank)
+    hx_alt = [hx, torch.from_numpy(x_np2).pin_memory()]; hm_alt = [hm, torch.from_numpy(msg_np2.astype("float32")).pin_memory()]
     hy = torch.empty(B, 1, T, dtype=torch.float32).pin_memory()
     hbits = torch.empty(B, 16, dtype=torch.uint8).pin_memory()
     hconf = torch.empty(B, dtype=torch.float32).pin_memory()
@@ -283,7 +334,7 @@ def run_ours(a):
         with torch.cuda.stream(s_in):
             if k >= 2:
                 s_in.wait_event(ev_free[i])
-            xd2[i].copy_(hx, non_blocking=True); md2[i].copy_(hm, non_blocking=True)
+            xd2[i].copy_(hx_alt[i], non_blocking=True); md2[i].copy_(hm_alt[i], non_blocking=True)
             ev_in[i].record(s_in)
         main.wait_event(ev_in[i])
         if len(alive) == 2:                              # step k-2's outputs may be recycled once its download is done
@@ -349,39 +400,61 @@ def run_ours(a):
                 c["ms"] = round(c["ms"], 4); c["gflop"] = round(c["gflop"], 3); c["mb"] = round(c["mb"], 2)
             dom = max(breakdown.items(), key=lambda kv: kv[1]["ms"])
             name, c = dom
-            f_t = c["tflops"] / peaks["bf16_tflops_sustained"]
-            f_h = c["gbs"] / peaks["hbm_gbs"]
+            audio_s_gpu = B * T / SR                       # audio-seconds one GPU processes per step
+            bid = build_id()
             # DRAM bytes per launch of this kernel from the committed ncu capture of the same step
-            # (profiles/ncu_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum), next to the
-            # algorithmic bytes per launch that `achieved` is computed from
-            traffic = None
+            # (profiles/ncu_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum per launch); the file is
+            # stamped with the build it was captured on
+            traffic, ncu_bid, dram_step = None, None, None
             tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tr) and B == 64 and T == SR:
-                ent = json.load(open(tr)).get(name)
+                tj = json.load(open(tr))
+                ncu_bid = tj.get("_build_id")
+                dram_step = tj.get("_dram_bytes_per_step")
+                ent = tj.get(name)
                 if isinstance(ent, dict) and ent.get("dram_bytes_per_launch"):
                     traffic = ent["dram_bytes_per_launch"]
-            if f_t >= f_h:
-                roofline = {"kernel": name, "bound": "tensor", "achieved": c["tflops"], "peak": peaks["bf16_tflops_sustained"],
-                            "unit": "TFLOP/s", "frac": round(f_t, 4), "traffic": traffic}
-            else:
-                roofline = {"kernel": name, "bound": "hbm", "achieved": c["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": round(f_h, 4), "traffic": traffic}
-            roofline["peak_src"] = peaks["src"] + (" (sustained)" if roofline["bound"] == "tensor" else "")
+            # The design as built is HBM-bound (its launches move ~300x the I/O bytes of SURVEY 8(d)), so the headline
+            # fraction is the dominant kernel's design bytes (in + out tensors of each launch once) over the copy peak;
+            # the tensor fraction of the same kernel and of the whole path against SURVEY 8(d)'s FLOPs stand beside it.
+            f_h = c["gbs"] / peaks["hbm_gbs"]
+            gemm_tflops = SURVEY_GFLOP["gemm_1x1"] * audio_s_gpu / max(c["ms"], 1e-9) if name == "gemm_std" else c["tflops"]
+            step_ms_dev = total_ms / a.steps
+            path_tflops = SURVEY_GFLOP["path"] * audio_s_gpu / step_ms_dev
+            design_bytes_step = 1e6 * sum(v["mb"] for v in breakdown.values())
+            roofline = {"kernel": name, "bound": "hbm", "achieved": c["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(f_h, 4), "traffic": traffic}
+            roofline["peak_src"] = peaks["src"]
             roofline["launches"] = c["launches"]
             roofline["avg_launch_us"] = round(1e3 * c["ms"] / max(1, c["launches"]), 2)
-            tp = os.path.join(ROOT, "profiles", "ncu_tensor_pipe.json")
-            if os.path.exists(tp):   # tensor-pipe utilisation of the largest launches, from the committed ncu capture
-                roofline["tensor_pipe_pct_ncu"] = {k: v for k, v in json.load(open(tp)).items() if not k.startswith("_")}
             roofline["alg_bytes_per_launch"] = round(1e6 * c["mb"] / max(1, c["launches"]))
             roofline["alg_gflop_per_launch"] = round(c["gflop"] / max(1, c["launches"]), 3)
+            roofline["tensor"] = {"achieved": round(gemm_tflops, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                  "frac": round(gemm_tflops / peaks["bf16_tflops_sustained"], 4),
+                                  "note": "SURVEY 8(d) 1x1-GEMM FLOPs (27.33 GFLOP per audio-second) of one step / this kernel's time"}
+            roofline["path"] = {"achieved": round(path_tflops, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                "frac": round(path_tflops / peaks["bf16_tflops_sustained"], 4),
+                                "note": "SURVEY 8(d) 30.456 GFLOP per audio-second / device time of the whole step (tensor roofline of the path: 46.7 k audio-s/s)",
+                                "io_bytes_survey_per_audio_s": SURVEY_IO_BYTES,
+                                "design_bytes_per_audio_s": round(design_bytes_step / audio_s_gpu),
+                                "dram_bytes_per_audio_s_ncu": round(dram_step / audio_s_gpu) if dram_step else None,
+                                "design_over_survey_io": round(design_bytes_step / audio_s_gpu / SURVEY_IO_BYTES, 1)}
+            roofline["build_id"] = bid
+            roofline["ncu_build_id"] = ncu_bid
+            roofline["ncu_stale"] = (ncu_bid != bid) if ncu_bid else None
+            tp = os.path.join(ROOT, "profiles", "ncu_tensor_pipe.json")
+            if os.path.exists(tp):   # tensor-pipe utilisation of the largest launches, from the committed ncu capture
+                tpj = json.load(open(tp))
+                roofline["tensor_pipe_pct_ncu"] = {k: v for k, v in tpj.items() if not k.startswith("_")}
+                roofline["tensor_pipe_build_id"] = tpj.get("_build_id")
             roofline["note"] = ("aggregate over all launches of this kernel in one step (profiled sub-batch x%d); "
-                                "achieved = algorithmic work / CUDA-event time" % n_sub)
+                                "achieved = design bytes (in + out tensors of each launch once) / CUDA-event time" % n_sub)
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             n = max(1, min(B, a.cpu_sample_clips))
-            rate, cores, times = cpu_oracle_rate(n, T, 3, 1)
+            rate, cores, times = cpu_oracle_rate(n, T, 3, 1, threads=cpu_threads(a))
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n} x {a.seconds:g} s clips, embed+detect+locate, fp32 oracle port, 1 warm-up + 3 timed"}
+                   "sample": f"{n} x {a.seconds:g} s clips, embed+detect+locate, 1 warm-up + 3 timed, {cores} threads; {PORT_NOTE}"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -390,6 +463,11 @@ def run_ours(a):
                        "l2": "flushed between steps (256 MiB memset outside the per-step events); per-step activations >> L2",
                        "weights": "random-init conf/base.yml architecture (fixture weights)", "parallelism": f"dp{world} (clips sharded, no hot-loop collective; Locator on a side stream next to the Detector)",
                        "chunk_seconds": a.chunk_seconds,
+                       "precision": "Generator / Detector body fp16 storage + fp32 accumulate; Locator on the fp32-accurate net "
+                                    "(split-fp16 operands); Detector bits re-checked on the fp32-accurate net near the threshold",
+                       "detector_rechecked_clips_per_step": round(recheck_per_step, 2),
+                       "exact_bits": bool(D.exact_bits), "exact_mask": bool(L.exact),
+                       "e2e_l2": "the e2e loop does not flush L2 between steps (serving conditions); it alternates two host input buffers",
                        "e2e": "per step: pinned host -> device copy of x and msg, embed+detect+locate, device -> host copy of y, bits, "
                               "confidence and mask; copies on two side streams, device inputs double-buffered; wall clock over the loop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -67,6 +67,9 @@ typedef struct wv_net_config {
   int embedding_dim;
   int embedding_layers;
   int freq_bands;
+  int precise;         /* 1: fp32-accurate arithmetic (split-fp16 tensor-core operands, fp32 epilogues) for the nets whose
+                          outputs are thresholded: the locator mask (model/watermarking.py:717) and the detector re-check of
+                          near-threshold bits (waveverify/core.py:577-586).  Detector / locator only. */
 } wv_net_config;
 
 /* One folded fp32 host tensor, keyed by the reference state_dict name with the weight-norm /

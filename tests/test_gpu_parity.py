@@ -2,18 +2,19 @@
 the reference itself (tests/golden) and (b) the CPU oracle on fresh inputs, plus
 size-independent properties at the benchmark sizes.
 
-Stated tolerances (fp16 activations and weights on the tensor cores, fp32 accumulation, packed
-half2 epilogues; cf. BASELINE.md section 4 - PyTorch's own bf16 autocast of the reference reaches
-31.5 dB on the residual).  Measured values are in profiles/r01_parity_fp16.md (58-62 dB residual,
-57-65 dB logits; every differing mask sample lies within 0.004 of the threshold):
+Stated tolerances.  Generator and Detector body: fp16 activations and weights on the tensor cores,
+fp32 accumulation, packed half2 epilogues (cf. BASELINE.md section 4 - PyTorch's own bf16 autocast of
+the reference reaches 31.5 dB on the residual).  The thresholded outputs run fp32-accurately: the
+Locator on the precise net (split-fp16 tensor-core operands, fp32 epilogues), the Detector's bit
+decisions re-evaluated on the precise net wherever a mean lies within 2e-4 of 0.5.  Measured values are
+in profiles/r02_parity.md:
   watermark residual / watermarked audio : SNR >= 46 dB, max-abs <= 4e-4
   latent                                 : SNR >= 50 dB
   detector logits                        : SNR >= 52 dB, max-abs <= 0.08 ; avg prob max-abs <= 2e-4
-  locator logits                         : SNR >= 52 dB, max-abs <= 0.08
-  decoded bits                           : exact wherever |avg_ref - 0.5| > 3e-4 (guard band)
-  locator mask                           : exact wherever |logit_ref - 0.5| > 0.04 (half the logit
-                                           max-abs bound; observed mismatches sit within 0.004);
-                                           inside the band at most 30 % of the samples may differ
+  locator logits                         : SNR >= 90 dB, p99.9 of |err| <= 3e-5, max-abs <= 5e-4
+  decoded bits                           : EXACT wherever |avg_ref - 0.5| > 1e-5  (the band inside which the fp32
+                                           oracle itself may differ from the reference, tests/test_oracle_golden.py)
+  locator mask                           : EXACT wherever |logit_ref - 0.5| > 1e-4 (same: the oracle's own band)
 """
 import os
 
@@ -50,19 +51,24 @@ def check_wave(ref, got, what):
 
 
 def check_bits(avg_ref, bits_ref, avg, bits, tol=2e-4):
-    """tol: bound on |avg - avg_ref|.  2e-4 holds for clips of >= 0.25 s (the time-mean averages the
-    per-sample logit error); very short clips are bounded by the logit error itself (0.25 * 0.008)."""
+    """tol: bound on |avg - avg_ref| of the fast path.  2e-4 holds for clips of >= 0.25 s (the time-mean
+    averages the per-sample logit error); very short clips are bounded by the logit error itself.
+    The bits come out of the default path (fast + precise re-check near 0.5): exact outside the fp32 band."""
     assert np.abs(avg - avg_ref).max() <= tol
-    safe = np.abs(avg_ref - 0.5) > 1.5 * tol
+    safe = np.abs(avg_ref - 0.5) > 1e-5
     assert (bits == bits_ref)[safe].all()
 
 
-def check_mask(logit_ref, mask_ref, mask):
-    safe = np.abs(logit_ref - 0.5) > 0.04
-    assert (mask == mask_ref)[safe].all(), "mask differs outside the guard band"
-    band = ~safe
-    if band.sum() > 50:
-        assert (mask != mask_ref)[band].mean() <= 0.30
+def check_mask(logit_ref, mask_ref, mask, logit=None):
+    safe = np.abs(logit_ref - 0.5) > 1e-4
+    assert (mask == mask_ref)[safe].all(), "mask differs from the reference outside the fp32 band"
+    if logit is not None:
+        # fp32-level noise: typical 1e-5; isolated samples reach ~1e-4 where a near-silent STFT bin (log of a
+        # cancelling sum) amplifies the last-bit differences between two fp32-accurate evaluations
+        err = np.abs(logit - logit_ref)
+        assert err.max() <= 5e-4, f"locator logits max-abs {err.max()}"
+        if err.size >= 1000:
+            assert np.quantile(err, 0.999) <= 3e-5, f"locator logits p99.9 {np.quantile(err, 0.999)}"
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
@@ -87,9 +93,8 @@ def test_cuda_path_matches_reference_golden(path):
     assert bool(d["valid"].all())
     l = m["locator"][0].locate_batch(yg, want_logits=True, want_probs=True)
     ll = l["logits"].cpu().numpy()
-    assert snr_db(z["loc_logits"], ll) >= 52.0
-    assert np.abs(ll - z["loc_logits"]).max() <= 0.08
-    check_mask(z["loc_logits"], z["loc_mask"], l["mask"].cpu().numpy())
+    assert snr_db(z["loc_logits"], ll) >= 90.0
+    check_mask(z["loc_logits"], z["loc_mask"], l["mask"].cpu().numpy(), ll)
     # fused outputs are consistent with the logits the same launch wrote
     assert torch.equal(l["mask"], (l["logits"] > 0.5).to(torch.uint8))
     np.testing.assert_allclose(l["probs"].cpu().numpy(), 1 / (1 + np.exp(-ll.astype(np.float64))), atol=2e-6)
@@ -119,8 +124,8 @@ def test_cuda_path_matches_oracle_fresh_batch():
     assert snr_db(lg_o.numpy(), d["logits"].cpu().numpy()) >= 52.0
     check_bits(avg_o.numpy(), bits_o.numpy(), d["avg"].cpu().numpy(), d["bits"].cpu().numpy())
     l = m["locator"][0].locate_batch(y, want_logits=True)
-    assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 52.0
-    check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy())
+    assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 90.0
+    check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy(), l["logits"].cpu().numpy())
 
 
 def test_masked_bit_decode_and_metric_counters():
@@ -147,7 +152,7 @@ def test_masked_bit_decode_and_metric_counters():
     # a clip with ONE unmasked sample exposes the raw logit error, not a time average
     assert np.abs(d["avg"].cpu().numpy() - avg_o.numpy())[v].max() <= 8e-3
     assert np.abs(d["avg"].cpu().numpy())[~v].max() == 0.0
-    safe = v & (np.abs(avg_o.numpy() - 0.5) > 1e-2)
+    safe = v & (np.abs(avg_o.numpy() - 0.5) > 1e-5)        # default path: fast + precise re-check near the threshold
     assert (d["bits"].cpu().numpy() == bits_o.numpy())[safe].all()
     # counters: feed identical bits/masks to both sides -> integers must be EXACT
     l = m["locator"][0].locate_batch(y.to(dev))
@@ -287,6 +292,6 @@ def test_cuda_path_matches_oracle_ragged_shapes(B, T):
         d = m["detector"][0].detect_batch(y, want_logits=True)
         l = m["locator"][0].locate_batch(y, want_logits=True)
         assert snr_db(lg_o.numpy(), d["logits"].cpu().numpy()) >= 50.0
-        assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 50.0
+        assert snr_db(ll_o.numpy(), l["logits"].cpu().numpy()) >= 90.0
         check_bits(avg_o.numpy(), bits_o.numpy(), d["avg"].cpu().numpy(), d["bits"].cpu().numpy(), tol=2e-4 if T >= 4000 else 2e-3)
-        check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy())
+        check_mask(ll_o.numpy(), O.locator_mask(ll_o).numpy(), l["mask"].cpu().numpy(), l["logits"].cpu().numpy())

@@ -19,6 +19,7 @@ class NetConfigC(C.Structure):
         ("strides", C.c_int * 8), ("res_scale_enc", C.c_float), ("res_scale_dec", C.c_float),
         ("nbits", C.c_int), ("output_dim", C.c_int), ("msg_dimension", C.c_int),
         ("embedding_dim", C.c_int), ("embedding_layers", C.c_int), ("freq_bands", C.c_int),
+        ("precise", C.c_int),
     ]
 
 

@@ -61,7 +61,7 @@ constexpr int P2_WARPS = 12;                // smem -> math -> global warps
 constexpr int P2_THREADS = P2_WARPS * 32;
 constexpr int EPI_THREADS = (P1_WARPS + P2_WARPS) * 32;   // participants of the drain <-> math barriers
 constexpr int STAGED_THREADS = 128 + EPI_THREADS;
-template <int EPI> constexpr int gemm_threads() { return EPI == 0 ? STAGED_THREADS : GEMM_THREADS; }
+template <int EPI> constexpr int gemm_threads() { return (EPI == 0 || EPI == 4) ? STAGED_THREADS : GEMM_THREADS; }
 constexpr int STAGE_BUFS = 2;               // staging tiles (drain of tile i+1 overlaps math of tile i)
 constexpr int STAGED_MAX_BN = 128;
 constexpr int BAR_TAPS = 1;                // named barrier ids: 1 = down-conv tap staging,
@@ -71,7 +71,11 @@ constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 512;
 constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [2r <= 16][block_n] fp16
 
-enum { EPI_STAGED = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3 };
+// Epilogues 4..6 are the PRECISE variants (fp32-accurate path for the thresholded outputs, see the
+// "precise mode" block below): split-fp16 operands (hi + lo) on the tensor cores, fp32 epilogue math.
+enum { EPI_STAGED = 0, EPI_L2NORM = 1, EPI_STFT = 2, EPI_HEAD = 3, EPI_STAGED_PM = 4, EPI_L2NORM_PM = 5, EPI_STFT_PM = 6 };
+constexpr int STAGED_PM_MAX_BN = 64;                       // fp32 staging tiles: 2 x 128 x (64*4+16) = 68 KB
+constexpr int DOWN_W_BYTES_PM = 16 * STAGED_PM_MAX_BN * 4;  // staged down-conv taps [2r <= 16][block_n] fp32
 
 struct GemmArgs {
   int rows_per_clip;  // rows of A per clip (flat: total M)
@@ -87,6 +91,8 @@ struct GemmArgs {
   int kb_split;       // > 0: k-blocks >= kb_split re-read the A rows shifted by one (row r-1) at k - kb_split*64:
                       //      [a[i] | a[i-1]] contraction of the fused transposed-conv + 1x1 (decoder upsample)
   int a2_split;       // > 0: k-blocks >= a2_split are read from a SECOND A tensor (tmR) at k - a2_split*64, same rows
+  int a3_split;       // > 0: k-blocks >= a3_split are read from the FIRST A tensor again at k - a3_split*64 (precise mode:
+                      //      [hi | lo | hi] x [Wh | Wh | Wl] contraction of the split-fp16 STFT)
   int dual;           // 1 (with a2_split): the tile's columns are [acc1 | acc2], block_n/2 channels each: acc1 = the 1x1 conv
                       //    that feeds the depthwise taps, acc2 = a second 1x1 conv over the second A tensor that is added
                       //    un-tapped (last encoder resblock + spectrogram branch in one launch, modules/seanet.py:936-943)
@@ -117,6 +123,11 @@ struct GemmArgs {
   act_t* out_act;
   float act_scale;
   int ldo;
+  // precise mode (EPI_*_PM): raw streams are fp32 [rows, ldo]; 16-bit tensors that feed a GEMM are SPLIT fp16
+  // [rows, ldo_act] = [hi (lo_off columns) | lo]: v = hi + lo to ~22 bits (hi = rn16(v), lo = rn16(v - hi))
+  const float* residual32;
+  float* out_raw32;
+  int ldo_act, lo_off;
   // STAGED, pre mode (pre_w != nullptr, residual == nullptr): the residual stream of the encoder's first resblock is the
   // output of conv_pre (1 -> C, k = 5 causal, modules/seanet.py:657-664); the math warps recompute it from five waveform
   // samples (same fp32 FMA order and fp16 rounding as conv_pre_kernel: bit-identical) instead of reading C channels
@@ -153,30 +164,30 @@ struct GemmArgs {
   int dbg_mode;     // -DWV_TIMELINE builds only: 1 = math warps skip global stores, 2 = skip the units, 3 = skip drain conversion+stores
 };
 
-__host__ __device__ inline int staged_pitch_bytes(int block_n) { return block_n * 2 + 16; }
+__host__ __device__ inline int staged_pitch_bytes(int block_n, bool pm = false) { return block_n * (pm ? 4 : 2) + 16; }
 // Shared-memory plan.  With resident_b the CTA's whole W tile (num_kb k-blocks) is loaded once and the
 // ring stages hold A k-blocks only (16 KB each): the ring then covers 4-5 tiles of loads in flight
 // instead of 3, which is what bounds the small-K layers (TMA issue -> data is ~8 000 cycles under load).
-__host__ inline int gemm_fixed_smem(int block_n, bool staged, int stage_bufs = STAGE_BUFS) {
-  return 1024 + GEMM_BAR_BYTES + (staged ? DOWN_W_BYTES + stage_bufs * BM * staged_pitch_bytes(block_n) : 0);
+__host__ inline int gemm_fixed_smem(int block_n, bool staged, int stage_bufs = STAGE_BUFS, bool pm = false) {
+  return 1024 + GEMM_BAR_BYTES + (staged ? (pm ? DOWN_W_BYTES_PM : DOWN_W_BYTES) + stage_bufs * BM * staged_pitch_bytes(block_n, pm) : 0);
 }
-__host__ inline bool gemm_resident_b(int block_n, int num_kb, bool staged, bool nt_fixed) {
+__host__ inline bool gemm_resident_b(int block_n, int num_kb, bool staged, bool nt_fixed, bool pm = false) {
   const int w_bytes = num_kb * block_n * BK * 2;
   return nt_fixed && w_bytes <= 64 * 1024 &&
-         (GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged) - w_bytes) / A_STAGE_BYTES >= 4;
+         (GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged, STAGE_BUFS, pm) - w_bytes) / A_STAGE_BYTES >= 4;
 }
 __host__ inline int gemm_stage_count(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS,
-                                     bool pair = false) {
-  const int avail = GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged, stage_bufs);
+                                     bool pair = false, bool pm = false) {
+  const int avail = GEMM_SMEM_LIMIT - gemm_fixed_smem(block_n, staged, stage_bufs, pm);
   const int a_bytes = pair ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
   int s = resident ? (avail - num_kb * block_n * BK * 2) / a_bytes : avail / (a_bytes + block_n * BK * 2);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
 __host__ inline int gemm_smem_bytes(int block_n, bool staged, int num_kb = 0, bool resident = false, int stage_bufs = STAGE_BUFS,
-                                    bool pair = false) {
-  const int s = gemm_stage_count(block_n, staged, num_kb, resident, stage_bufs, pair);
+                                    bool pair = false, bool pm = false) {
+  const int s = gemm_stage_count(block_n, staged, num_kb, resident, stage_bufs, pair, pm);
   const int a_bytes = pair ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
-  return gemm_fixed_smem(block_n, staged, stage_bufs) +
+  return gemm_fixed_smem(block_n, staged, stage_bufs, pm) +
          (resident ? s * a_bytes + num_kb * block_n * BK * 2 : s * (a_bytes + block_n * BK * 2));
 }
 
@@ -662,6 +673,178 @@ __device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_
 }
 
 // ---------------------------------------------------------------------------------------------
+// PRECISE MODE (EPI_STAGED_PM / EPI_L2NORM_PM / EPI_STFT_PM).  The thresholded outputs of the path
+// (locator mask = logit > 0.5, model/watermarking.py:717; decoded bits = mean sigmoid >= 0.5,
+// waveverify/core.py:577-586) must equal the fp32 reference's, so the nets that produce them can run
+// with fp32-accurate arithmetic on the same tensor-core pipeline:
+//   * every 16-bit GEMM operand is a SPLIT pair  v = hi + lo  (hi = rn16(v), lo = rn16(v - hi): ~22 bits);
+//     the contraction [hi | lo | hi] x [Wh | Wh | Wl] = (hi+lo)*Wh + hi*Wl drops only lo*Wl (2^-22 relative);
+//     products of fp16 operands are exact in the fp32 accumulator;
+//   * the STAGED epilogue stages the accumulator tile as fp32 and runs taps / bias / residual / ELU in fp32;
+//     raw residual streams are stored fp32, activated streams as split pairs for the next GEMM.
+// Same tile geometry, ring, TMEM staging and barriers as the fp16 path; the loops below are written for
+// accuracy, not for issue rate (the Locator is 2.6 % of the path's FLOPs).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+
+// STAGED_PM math warps: thread = (4-channel group, 3-row group) over the fp32 staging tile (42 / 43 row groups per
+// tile: one pass of the 384 math threads at 32 columns, two at 64).
+//   v = bias[c] + sum_j w[j][c] * S[r-taps+1+j][c]  (+ residual32);  out_raw32 = v;  out_act = split(ELU(v*s))
+template <int TAPS>
+__device__ __forceinline__ void pm_math_loop(const GemmArgs& g, const uint8_t* stage_tiles) {
+  constexpr int HALO = TAPS - 1;
+  constexpr int ROWS_OUT = BM - HALO;
+  constexpr int R = 3;
+  const int pitch = staged_pitch_bytes(g.block_n, true);
+  const int et = threadIdx.x - (128 + P1_WARPS * 32);
+  const int cgs = g.block_n >> 2;
+  const int gstride = P2_THREADS / cgs;
+  const int cg = et % cgs, grp0 = et / cgs;
+  const bool active = grp0 < gstride;
+  const float s_act = g.act_scale;
+  const bool has_res = g.residual32 != nullptr, has_raw = g.out_raw32 != nullptr, has_act = g.out_act != nullptr;
+  const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 16;
+  int cached_nt = -1;
+  float4 wt[TAPS], bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sb = 0;
+  int tiles_left = cta_tile_count(g);
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+    const int r_base = tc.mi * ROWS_OUT;
+    const int c = tc.nt * g.block_n + cg * 4;
+    if (active && tc.nt != cached_nt) {
+      cached_nt = tc.nt;
+      bs = g.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(g.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (TAPS > 1) {
+#pragma unroll
+        for (int j = 0; j < TAPS; ++j) wt[j] = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + c));
+      }
+    }
+    const int rows_left = min(g.rows_per_clip - r_base, ROWS_OUT);
+    const size_t row0 = static_cast<size_t>(tc.clip) * g.rows_per_clip + r_base;
+    // the residual rows of the first unit do not depend on the staged tile: requested before the hand-off barrier
+    float4 rr[R];
+    int ro = grp0 * R;
+    auto load_res = [&](int ro_) {
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        rr[i] = (has_res && ro_ + i < rows_left) ? __ldcg(reinterpret_cast<const float4*>(g.residual32 + (row0 + ro_ + i) * g.ldo + c))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (active && ro < rows_left) load_res(ro);
+    named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);
+    if (active) {
+      const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
+      for (; ro < rows_left; ro += gstride * R) {
+        float4 x[R + HALO];
+#pragma unroll
+        for (int j = 0; j < R + HALO; ++j) x[j] = lds_f4(tile_u32 + min(ro + j, BM - 1) * pitch);   // rows past 127 feed no valid output
+        float4 v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          if constexpr (TAPS > 1) {
+            v[i] = bs;
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+              v[i].x = fmaf(wt[j].x, x[i + j].x, v[i].x); v[i].y = fmaf(wt[j].y, x[i + j].y, v[i].y);
+              v[i].z = fmaf(wt[j].z, x[i + j].z, v[i].z); v[i].w = fmaf(wt[j].w, x[i + j].w, v[i].w);
+            }
+          } else {
+            v[i] = make_float4(x[i].x + bs.x, x[i].y + bs.y, x[i].z + bs.z, x[i].w + bs.w);
+          }
+          v[i].x += rr[i].x; v[i].y += rr[i].y; v[i].z += rr[i].z; v[i].w += rr[i].w;
+        }
+        const int ro_next = ro + gstride * R;
+        const int ro_cur = ro;
+        if (has_raw) {
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+            if (ro_cur + i < rows_left) *reinterpret_cast<float4*>(g.out_raw32 + (row0 + ro_cur + i) * g.ldo + c) = v[i];
+        }
+        if (ro_next < rows_left) load_res(ro_next);          // next unit's residual in flight during the ELUs
+        if (has_act) {
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+            if (ro_cur + i < rows_left)
+              st_split4(g.out_act + (row0 + ro_cur + i) * g.ldo_act + c, g.lo_off, elu_precise(v[i].x * s_act), elu_precise(v[i].y * s_act),
+                        elu_precise(v[i].z * s_act), elu_precise(v[i].w * s_act));
+        }
+      }
+    }
+    __syncwarp();
+    if (--tiles_left >= g.stage_bufs) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);
+    if (++sb == g.stage_bufs) sb = 0;
+  }
+}
+
+// STAGED_PM strided variant: causal depthwise down-conv k=2R, s=R (+ FiLM) in fp32 (cf. staged_down_loop)
+template <int R>
+__device__ __forceinline__ void pm_down_loop(const GemmArgs& g, const uint8_t* stage_tiles, uint8_t* down_w) {
+  constexpr int OUTS = BM / R - 1;
+  const int pitch = staged_pitch_bytes(g.block_n, true);
+  const int et = threadIdx.x - (128 + P1_WARPS * 32);
+  const int cgs = g.block_n >> 2;
+  const int gstride = P2_THREADS / cgs;
+  const int cg = et % cgs, row0 = et / cgs;
+  const bool active = row0 < gstride;
+  const float s_act = g.act_scale;
+  const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 16;
+  const uint32_t w_u32 = smem_u32(down_w) + cg * 16;             // taps staged as fp32 [2R][block_n]
+  const int band_w = g.film != nullptr ? g.N / g.film_bands : 1;
+  int cached_nt = -1;
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sb = 0;
+  int tiles_left = cta_tile_count(g);
+  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+    const int c = tc.nt * g.block_n + cg * 4;
+    if (tc.nt != cached_nt) {
+      cached_nt = tc.nt;
+      named_bar_sync(BAR_TAPS, P2_THREADS);
+      for (int i = et; i < 2 * R * cgs; i += P2_THREADS) {
+        const int j = i / cgs, q = i % cgs;
+        *reinterpret_cast<float4*>(down_w + (j * g.block_n + q * 4) * 4) =
+            __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + tc.nt * g.block_n + q * 4));
+      }
+      named_bar_sync(BAR_TAPS, P2_THREADS);
+      bs = g.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(g.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float gm = 1.f, bt = 0.f;
+    if (g.film != nullptr) {
+      const float* fp = g.film + static_cast<size_t>(tc.clip) * g.film_stride + (c / band_w) * 2;
+      gm = __ldcg(fp); bt = __ldcg(fp + 1);
+    }
+    named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);
+    if (active) {
+      const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
+      const int i_base = tc.mi * OUTS;
+      const int outs_left = g.rows_per_clip_out - i_base;
+      const size_t rowb = static_cast<size_t>(tc.clip) * g.rows_per_clip_out + i_base;
+      for (int lo = row0; lo < OUTS && lo < outs_left; lo += gstride) {
+        float4 v = bs;
+        const uint32_t srow = tile_u32 + lo * R * pitch;
+#pragma unroll
+        for (int j = 0; j < 2 * R; ++j) {
+          const float4 u = lds_f4(srow + j * pitch);
+          const float4 w = lds_f4(w_u32 + j * g.block_n * 4);
+          v.x = fmaf(w.x, u.x, v.x); v.y = fmaf(w.y, u.y, v.y); v.z = fmaf(w.z, u.z, v.z); v.w = fmaf(w.w, u.w, v.w);
+        }
+        if (g.film != nullptr) { v.x = fmaf(v.x, gm, bt); v.y = fmaf(v.y, gm, bt); v.z = fmaf(v.z, gm, bt); v.w = fmaf(v.w, gm, bt); }
+        const size_t row = rowb + lo;
+        if (g.out_raw32 != nullptr) *reinterpret_cast<float4*>(g.out_raw32 + row * g.ldo + c) = v;
+        if (g.out_act != nullptr)
+          st_split4(g.out_act + row * g.ldo_act + c, g.lo_off, elu_precise(v.x * s_act), elu_precise(v.y * s_act),
+                    elu_precise(v.z * s_act), elu_precise(v.w * s_act));
+      }
+    }
+    __syncwarp();
+    if (--tiles_left >= g.stage_bufs) named_bar_arrive(BAR_ST_EMPTY + sb, EPI_THREADS);
+    if (++sb == g.stage_bufs) sb = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -683,7 +866,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* w_full = acc_empty + MAX_ACC_STAGES;  // resident W tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   uint8_t* down_w = after + GEMM_BAR_BYTES;       // [2r][block_n] fp32 (STAGED down-conv only)
-  uint8_t* stage_tiles = down_w + DOWN_W_BYTES;   // [STAGE_BUFS][BM][pitch] fp16 (STAGED only)
+  constexpr bool STG = EPI == EPI_STAGED || EPI == EPI_STAGED_PM;
+  constexpr bool PM = EPI >= EPI_STAGED_PM;
+  constexpr bool IS_STFT = EPI == EPI_STFT || EPI == EPI_STFT_PM;
+  constexpr bool IS_L2N = EPI == EPI_L2NORM || EPI == EPI_L2NORM_PM;
+  uint8_t* stage_tiles = down_w + (PM ? DOWN_W_BYTES_PM : DOWN_W_BYTES);   // [STAGE_BUFS][BM][pitch] (STAGED only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -707,7 +894,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(w_full, 1);
     for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI == EPI_STAGED ? P1_WARPS : (EPI == EPI_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));  // one arrive per draining warp
+      mbar_init(&acc_empty[i], STG ? P1_WARPS : (IS_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));  // one arrive per draining warp
     }
     fence_mbar_init();
   }
@@ -722,7 +909,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if constexpr (EPI == EPI_STAGED) reg_dealloc<REGS_LIGHT>();
+    if constexpr (STG) reg_dealloc<REGS_LIGHT>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -781,8 +968,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           if (kb == 0) WV_DBG(0, dbg_it);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
-          if (g.phases > 1) tma_load_4d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip % g.phases, tc.clip / g.phases);
-          else if (g.a2_split > 0 && kb >= g.a2_split) tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmR, &full[stage], (kb - g.a2_split) * BK, r0, tc.clip);
+          // k-block -> (A tensor, column): [tmA | tmR from a2_split | tmA again from a3_split]
+          const CUtensorMap* mp = &tmA;
+          int kk = kb;
+          if (g.a3_split > 0 && kb >= g.a3_split) kk = kb - g.a3_split;
+          else if (g.a2_split > 0 && kb >= g.a2_split) { mp = &tmR; kk = kb - g.a2_split; }
+          if (g.phases > 1) tma_load_4d(smemA + stage * A_STAGE_BYTES, mp, &full[stage], kk * BK, r0, tc.clip % g.phases, tc.clip / g.phases);
+          else if (kk != kb) tma_load_3d(smemA + stage * A_STAGE_BYTES, mp, &full[stage], kk * BK, r0, tc.clip);
           else if (g.kb_split > 0 && kb >= g.kb_split) tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], (kb - g.kb_split) * BK, r0 - 1, tc.clip);
           else if (g.a_evict_first) tma_load_3d_hint(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip, pol);
           else tma_load_3d(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, r0, tc.clip);
@@ -794,7 +986,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if constexpr (EPI == EPI_STAGED) reg_dealloc<REGS_LIGHT>();
+    if constexpr (STG) reg_dealloc<REGS_LIGHT>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -862,10 +1054,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++as == acc_stages) { as = 0; as_phase ^= 1; }
       }
     }
-  } else if (EPI == EPI_STAGED && warp < 4) {
+  } else if (STG && warp < 4) {
     reg_dealloc<REGS_LIGHT>();   // warps 2 (TMEM allocator) and 3: the whole warpgroup must take part
-  } else if (EPI == EPI_STAGED && warp >= 4) {
-    const int pitch = staged_pitch_bytes(g.block_n);
+  } else if (STG && warp >= 4) {
+    const int pitch = staged_pitch_bytes(g.block_n, PM);
     const int chunks = g.block_n / 32;
     if (warp < 4 + P1_WARPS) {
       // ---------------------------------------------------------- drain warps: TMEM -> fp16 -> smem
@@ -891,6 +1083,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = 0; c < (WV_DBG_MODE(4) ? 0 : chunks); ++c) {
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
+          if constexpr (PM) {  // precise mode: the accumulator tile is staged as fp32
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sts_u4(rowp + c * 128 + i * 16, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            continue;
+          }
           if (g.last_mode) {   // output conv: the five tap columns stay fp32 (32 bytes per row)
             sts_u4(rowp, v[0], v[1], v[2], v[3]);
             sts_u4(rowp + 16, v[4], v[5], v[6], v[7]);
@@ -917,6 +1114,17 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
       // ---------------------------------------------------------- math warps: smem -> epilogue -> global
       reg_alloc<REGS_MATH>();
+      if constexpr (PM) {
+        if (g.down_r > 0) {
+          switch (g.down_r) {
+            case 2: pm_down_loop<2>(g, stage_tiles, down_w); break;
+            case 4: pm_down_loop<4>(g, stage_tiles, down_w); break;
+            case 5: pm_down_loop<5>(g, stage_tiles, down_w); break;
+            default: pm_down_loop<8>(g, stage_tiles, down_w); break;
+          }
+        } else if (g.taps == 5) pm_math_loop<5>(g, stage_tiles);
+        else pm_math_loop<1>(g, stage_tiles);
+      } else
       if (g.last_mode) {
         staged_last_loop(g, stage_tiles);
       } else if (g.down_r > 0) {
@@ -935,7 +1143,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = e & 3;    // TMEM lane quarter: warp (w % 4) may touch lanes [32q, 32q+32)
     // STFT: the 16 epilogue warps may form 2 or 4 groups (of 8 / 4 warps: every group covers the four TMEM lane quarters);
     // group g owns accumulator stage g = every epi_groups-th tile, so that several tiles are in the epilogue at once
-    const int n_groups = EPI == EPI_STFT ? g.epi_groups : 1;
+    const int n_groups = IS_STFT ? g.epi_groups : 1;
     const bool two_groups = n_groups > 1;
     const int gw = EPI_WARPS / n_groups;                 // warps per group
     const int h = two_groups ? (e % gw) >> 2 : e >> 2;   // column split: this warp takes chunks c with c % split == h
@@ -967,12 +1175,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int r = r_base + q * 32 + lane;
         bool row_ok = r < g.rows_per_clip;
         long long m = static_cast<long long>(clip) * g.rows_per_clip + r;
-        if (EPI == EPI_STFT && g.phases > 1) {      // row q of (clip, phase) is frame q*phases + phase of the clip
+        if (IS_STFT && g.phases > 1) {      // row q of (clip, phase) is frame q*phases + phase of the clip
           const int f = r * g.phases + clip % g.phases;
           row_ok = row_ok && f < g.frames_per_clip;
           m = static_cast<long long>(clip / g.phases) * g.frames_per_clip + f;
         }
-        if constexpr (EPI == EPI_L2NORM) {
+        if constexpr (IS_L2N) {
           if (h == 0) {
             float ss = 0.f;
             for (int c = 0; c < chunks; ++c) {
@@ -994,6 +1202,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                   f[i] = (__uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n + i) : 0.f)) * sc;
+                if constexpr (PM) {   // split latent [hi | lo], row pitch ldo, lo at + lo_off
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    st_split4(g.out_raw + m * g.ldo + n + 4 * i, g.lo_off, f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                } else {
                 uint4* op = reinterpret_cast<uint4*>(g.out_raw + m * g.ldo + n);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -1001,6 +1214,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                      pack_act2(f[8 * i + 2], f[8 * i + 3]),
                                      pack_act2(f[8 * i + 4], f[8 * i + 5]),
                                      pack_act2(f[8 * i + 6], f[8 * i + 7]));
+                }
                 if (g.out_f32_t != nullptr) {
                   const long long b = m / g.f32_F, fr = m % g.f32_F;
                   float* tp = g.out_f32_t + (b * g.N + n) * g.f32_F + fr;
@@ -1008,6 +1222,34 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   for (int i = 0; i < 32; ++i) tp[static_cast<long long>(i) * g.f32_F] = f[i];
                 }
               }
+            }
+          }
+        } else if constexpr (EPI == EPI_STFT_PM) {
+          // precise log-magnitude (logf, not MUFU.LG2) -> split pairs [hi | lo]
+          for (int c = h; c < chunks; c += split) {
+            const int p0 = (n0 + c * 32) >> 1;
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float y[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
+                y[i] = (0.5f * logf(fmaxf(re * re + im * im, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+              }
+              act_t* yp = g.out_raw + m * g.ldo;
+              if (p0 == 0) {
+                const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
+                y[0] = (0.5f * logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                const float yn = (0.5f * logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                uint32_t hn, ln;
+                split2(yn, 0.f, hn, ln);   // bin N/2 + 7 zero pad columns (row half-width = n_half + 8)
+                *reinterpret_cast<uint4*>(yp + g.n_half) = make_uint4(hn, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(yp + g.lo_off + g.n_half) = make_uint4(ln, 0u, 0u, 0u);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                st_split4(yp + p0 + 4 * i, g.lo_off, y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
             }
           }
         } else if constexpr (EPI == EPI_STFT) {

@@ -367,6 +367,115 @@ frames_kernel(const __half* __restrict__ wav16, __half* __restrict__ frames, int
 }
 
 // ---------------------------------------------------------------------------------------
+// Precise-mode glue (see gemm_sm100.cuh "PRECISE MODE"): fp32 raw streams, split-fp16 GEMM operands.
+// conv_pre: raw fp32 [B,T,C] + activated split [B,T,2C]
+__global__ void __launch_bounds__(256)
+conv_pre_pm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out_raw, act_t* __restrict__ out_act, float act_scale, int B, int T, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int C4 = C >> 2;
+  const int runs = (T + PRE_TT - 1) / PRE_TT;
+  const long long total = static_cast<long long>(B) * runs * C4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % C4);
+    const long long rr = idx / C4;
+    const int t0 = static_cast<int>(rr % runs) * PRE_TT;
+    const int b = static_cast<int>(rr / runs);
+    const int c = cg * 4;
+    const float* xp = x + static_cast<long long>(b) * T;
+    float xs[PRE_TT + 4];
+#pragma unroll
+    for (int j = 0; j < PRE_TT + 4; ++j) {
+      const int tt = t0 - 4 + j;
+      xs[j] = (tt >= 0 && tt < T) ? __ldcg(xp + tt) : 0.f;
+    }
+    float4 wt[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) wt[j] = __ldg(reinterpret_cast<const float4*>(w + j * C + c));
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+#pragma unroll
+    for (int s = 0; s < PRE_TT; ++s) {
+      const int t = t0 + s;
+      if (t >= T) break;
+      float4 o = bs;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        o.x = fmaf(wt[j].x, xs[s + j], o.x); o.y = fmaf(wt[j].y, xs[s + j], o.y);
+        o.z = fmaf(wt[j].z, xs[s + j], o.z); o.w = fmaf(wt[j].w, xs[s + j], o.w);
+      }
+      const long long row = static_cast<long long>(b) * T + t;
+      if (out_raw != nullptr) *reinterpret_cast<float4*>(out_raw + row * C + c) = o;
+      if (out_act != nullptr)
+        st_split4(out_act + row * 2 * C + c, C, elu_precise(o.x * act_scale), elu_precise(o.y * act_scale),
+                  elu_precise(o.z * act_scale), elu_precise(o.w * act_scale));
+    }
+  }
+}
+
+// causal depthwise k=5 on a split tensor [B,T,2C] -> split [B,T,2C] (conv_post of the encoder tail; no activation)
+__global__ void __launch_bounds__(256)
+dw5_pm_kernel(const act_t* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+              act_t* __restrict__ out, int B, int T, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int C4 = C >> 2;
+  const long long total = static_cast<long long>(B) * T * C4;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % C4);
+    const long long rr = idx / C4;
+    const int t = static_cast<int>(rr % T);
+    const int b = static_cast<int>(rr / T);
+    const int c = cg * 4;
+    float4 o = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int tt = t - 4 + j;
+      if (tt < 0) continue;
+      const act_t* ip = in + (static_cast<long long>(b) * T + tt) * 2 * C + c;
+      const uint2 h = __ldcg(reinterpret_cast<const uint2*>(ip));
+      const uint2 l = __ldcg(reinterpret_cast<const uint2*>(ip + C));
+      float h0, h1, h2, h3, l0, l1, l2, l3;
+      unpack_act2(h.x, h0, h1); unpack_act2(h.y, h2, h3);
+      unpack_act2(l.x, l0, l1); unpack_act2(l.y, l2, l3);
+      const float4 wj = __ldg(reinterpret_cast<const float4*>(w + j * C + c));
+      o.x = fmaf(wj.x, h0 + l0, o.x); o.y = fmaf(wj.y, h1 + l1, o.y);
+      o.z = fmaf(wj.z, h2 + l2, o.z); o.w = fmaf(wj.w, h3 + l3, o.w);
+    }
+    st_split4(out + (static_cast<long long>(b) * T + t) * 2 * C + c, C, o.x, o.y, o.z, o.w);
+  }
+}
+
+// waveform staging as split pairs: out_hi / out_lo [B][8 copies][pitch] (cf. wav_stage_kernel)
+__global__ void __launch_bounds__(256)
+wav_stage_pm_kernel(const float* __restrict__ x, __half* __restrict__ out_hi, __half* __restrict__ out_lo, float scale,
+                    int B, int T, int lead, int pitch) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int p8n = pitch >> 3;
+  const long long total = static_cast<long long>(B) * WAV_COPIES * p8n;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % p8n) * 8;
+    const long long bs = idx / p8n;
+    const int sft = static_cast<int>(bs % WAV_COPIES);
+    const int b = static_cast<int>(bs / WAV_COPIES);
+    const int t0 = p + sft - lead;
+    const float* xp = x + static_cast<long long>(b) * T;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (t0 + k >= 0 && t0 + k < T) ? __ldcg(xp + t0 + k) * scale : 0.f;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split2(v[2 * k], v[2 * k + 1], h[k], l[k]);
+    *reinterpret_cast<uint4*>(out_hi + bs * pitch + p) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(out_lo + bs * pitch + p) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Message MLP + FiLM scalars (modules/seanet.py:830-839, 518-550): one block of E threads per
 // clip.  e = ReLU(L3 ReLU(L2 (L1 m + b1) + b2) + b3);  film[b, s, band, {gamma,beta}].
 struct FilmArgs {

@@ -233,4 +233,22 @@ __device__ __forceinline__ __half2 elu_h2(__half2 x) {
   return __hmax2(x, __hmin2(m, h2_from(0.f, 0.f)));
 }
 
+// Precise mode: a value as a SPLIT fp16 pair  v = hi + lo,  hi = rn16(v), lo = rn16(v - hi)  (~22 significant bits;
+// v - hi is exact in fp32).  Below 2^-14 * 2^11 the lo half is subnormal: absolute error <= 2^-25.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_act2(a, b);
+  float ha, hb;
+  unpack_act2(hi, ha, hb);
+  lo = pack_act2(a - ha, b - hb);
+}
+__device__ __forceinline__ float elu_precise(float x) { return x > 0.f ? x : expm1f(x); }
+// split store of 4 consecutive channels: hi at p, lo at p + lo_off (elements)
+__device__ __forceinline__ void st_split4(act_t* p, int lo_off, float a, float b, float c, float d) {
+  uint32_t h0, l0, h1, l1;
+  split2(a, b, h0, l0);
+  split2(c, d, h1, l1);
+  *reinterpret_cast<uint2*>(p) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(p + lo_off) = make_uint2(l0, l1);
+}
+
 }  // namespace wv

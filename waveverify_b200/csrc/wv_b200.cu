@@ -148,6 +148,7 @@ int g_rb_maxc = 0;     // widest resblock that runs as ONE fused kernel (resbloc
                        // measured r01: correct, but bound by its three ELU passes (MUFU) - 280 vs 265 us at C=96
 bool g_pdl = false;  // programmatic dependent launch for every plan kernel (WV_PDL=1 enables; measured
                      // 1-2 % slower on the 64-clip batch, where launch gaps are already hidden)
+thread_local bool g_pm = false;   // weights are being built for a PRECISE net (split-fp16 operands, see gemm_sm100.cuh)
 void init_device_once() {
   static bool done = false;
   if (done) return;
@@ -164,6 +165,9 @@ void init_device_once() {
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STAGED_PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM_PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT_PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(resblock_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   if (const char* e = getenv("WV_GRAPH_MAX_SAMPLES")) g_graph_max_samples = atoll(e);
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
@@ -232,6 +236,8 @@ struct GemmW {          // B operand of a GEMM: 16-bit [N, ldw] K-major, zero pa
   int N = 0, K = 0, ldw = 0, block_n = 0;
   bool fp16 = true;
   CUtensorMap tm;
+  // precise nets: K = the split contraction length; a2 / a3 = first k-block of the 2nd / 3rd operand segment
+  int a2 = 0, a3 = 0, K_alg = 0;
 };
 struct DwW {            // depthwise taps fp32 [k][C]
   float* w = nullptr;
@@ -317,9 +323,39 @@ uint16_t f2h(float f) {
   return u;
 }
 
+// Precise nets: the A operand is a split tensor [rows, 2*Ka] = [hi | lo] (or, stft: separate hi / lo frame views of
+// K columns each).  Weight rows  [Wh | Wh] over the k-blocks of [hi | lo], then [Wl] over the hi k-blocks again:
+//   (hi + lo) Wh + hi Wl = v W - lo Wl   (the dropped term is 2^-22 relative).   Wh = rn16(w), Wl = rn16(w - Wh).
+GemmW make_gemm_w_pm(Weights& W, const std::vector<float>& rows, int N, int K, int Ka, int block_n,
+                     const float* bias, int n_bias, bool stft) {
+  GemmW g;
+  const int n1 = stft ? 2 * ceil_div(K, BK) : ceil_div(2 * Ka, BK), n2 = ceil_div(stft ? K : Ka, BK);
+  const int off2 = stft ? ceil_div(K, BK) * BK : Ka;      // column of the second Wh copy
+  g.N = N; g.K = (n1 + n2) * BK; g.ldw = g.K; g.block_n = block_n; g.fp16 = true; g.K_alg = K;
+  g.a2 = stft ? n1 / 2 : 0;
+  g.a3 = n1;
+  std::vector<uint16_t> h(static_cast<size_t>(N) * g.ldw, 0);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float w = rows[static_cast<size_t>(n) * K + k];
+      if (!(std::fabs(w) <= 65504.f)) WV_THROW(WV_ERR_UNSUPPORTED, "weight %g does not fit fp16", w);
+      const __half wh = __float2half_rn(w);
+      const __half wl = __float2half_rn(w - __half2float(wh));
+      uint16_t uh, ul;
+      memcpy(&uh, &wh, 2); memcpy(&ul, &wl, 2);
+      uint16_t* r = h.data() + static_cast<size_t>(n) * g.ldw;
+      r[k] = uh; r[off2 + k] = uh; r[n1 * BK + k] = ul;
+    }
+  g.w = W.dev.upload(h);
+  if (bias) g.bias = W.dev.upload(std::vector<float>(bias, bias + n_bias));
+  g.tm = make_tmap(g.w, 2, g.ldw, N, 1, g.ldw, 0, BK, block_n, true);
+  return g;
+}
+
 // rows[N][K] fp32 (already scaled) -> device 16-bit [N, ldw] + tensor map
 GemmW make_gemm_w(Weights& W, const std::vector<float>& rows, int N, int K, bool fp16, int block_n,
                   const float* bias, int n_bias) {
+  if (g_pm) return make_gemm_w_pm(W, rows, N, K, static_cast<int>(round_up(K, 8)), block_n, bias, n_bias, false);
   GemmW g;
   fp16 = true;   // activations and weights are fp16 throughout (bf16 packing is no longer used)
   g.N = N; g.K = K; g.fp16 = fp16;
@@ -352,7 +388,7 @@ GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias) {
     for (auto& v : bb) v *= scale;
   }
   // pointwise convs run through the STAGED epilogue (two staging tiles): tile width <= 128
-  return make_gemm_w(W, rows, N, K, false, pick_block_n(N, 0, STAGED_MAX_BN), b ? bb.data() : nullptr, N);
+  return make_gemm_w(W, rows, N, K, false, pick_block_n(N, 0, g_pm ? STAGED_PM_MAX_BN : STAGED_MAX_BN), b ? bb.data() : nullptr, N);
 }
 
 // depthwise [C,1,k] -> [k][C]; transposed conv weights have the same memory shape
@@ -407,7 +443,8 @@ SpecW spec_w(Weights& W, const std::string& p, int n_fft, int hop, float mean, f
     std::copy(re, re + n_fft, rows.begin() + static_cast<size_t>(2 * pr) * n_fft);
     std::copy(im, im + n_fft, rows.begin() + static_cast<size_t>(2 * pr + 1) * n_fft);
   }
-  s.dft = make_gemm_w(W, rows, n_fft, n_fft, true, pick_block_n(n_fft), nullptr, 0);
+  s.dft = g_pm ? make_gemm_w_pm(W, rows, n_fft, n_fft, n_fft, pick_block_n(n_fft), nullptr, 0, true)
+               : make_gemm_w(W, rows, n_fft, n_fft, true, pick_block_n(n_fft), nullptr, 0);
   const float sc = rs * W.scalar_or(p + ".scale_param", 1.f);            // seanet.py:499-505
   s.layer = pointwise(W, p + ".layer.conv.conv", sc, false);
   return s;
@@ -506,7 +543,7 @@ struct IoPtrs {
 };
 
 enum OpType { OP_RESBLOCK = 20, OP_GEMM = 0, OP_DW5, OP_DOWN, OP_UP, OP_CONV_PRE, OP_CONV_LAST, OP_WAV_STAGE, OP_FRAMES,
-              OP_FILM, OP_BITS, OP_CONF, OP_LATENT_IN };
+              OP_FILM, OP_BITS, OP_CONF, OP_LATENT_IN, OP_CONV_PRE_PM = 30, OP_DW5_PM, OP_WAV_STAGE_PM };
 
 struct Op {
   OpType type;
@@ -610,21 +647,24 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.K = K;
   g.block_n = w.block_n;
   g.idesc = make_idesc_f16(BM, w.block_n, w.fp16);
-  const bool staged = epi == EPI_STAGED;
+  const bool staged = epi == EPI_STAGED || epi == EPI_STAGED_PM;
+  const bool pm = epi == EPI_STAGED_PM;                      // fp32 staging tiles (smem plan)
+  if (w.a3 > 0) { g.a2_split = w.a2; g.a3_split = w.a3; }    // split-fp16 operand segments (precise nets)
   g.unit_rows = (staged && ((g_rows6_mask >> ((g.dual ? w.block_n / 2 : w.block_n) / 32)) & 1u) && !g.last_mode && g.down_r == 0) ? 6 : 4;
   g.epi_groups = 1;
-  if (epi == EPI_STFT && g_epi_groups >= 2 && w.block_n <= 64) g.epi_groups = 2;
-  if (epi == EPI_STFT && g_epi_groups >= 4 && w.block_n <= 128) g.epi_groups = 4;
+  const bool is_stft = epi == EPI_STFT || epi == EPI_STFT_PM;
+  if (is_stft && g_epi_groups >= 2 && w.block_n <= 64) g.epi_groups = 2;
+  if (is_stft && g_epi_groups >= 4 && w.block_n <= 128) g.epi_groups = 4;
   if (staged && g.taps != 1 && g.taps != 5) WV_THROW(WV_ERR_INVALID, "taps must be 1 or 5");
   const int num_kb = ceil_div(K, BK);
   const int tiles_n_ = w.N / w.block_n;
   const bool nt_fixed = tiles_n_ <= g_num_sms;   // the grid is rounded down to a multiple of tiles_n below
-  bool resident = gemm_resident_b(w.block_n, num_kb, staged, nt_fixed);
+  bool resident = gemm_resident_b(w.block_n, num_kb, staged, nt_fixed, pm);
   // W tiles of 64..g_res1_kb KB (C = 512 layers: 128 KB) fit next to ONE staging tile: the ring then streams A only,
   // which halves the L2 -> SM operand traffic of those layers (they are bound by it); the price is that the drain of
   // a tile waits for the math of the previous one
   bool res1 = false;
-  if (!resident && staged && nt_fixed && g_res1_kb > 0) {
+  if (!resident && staged && !pm && nt_fixed && g_res1_kb > 0) {
     const int w_bytes = num_kb * w.block_n * BK * 2;
     res1 = w_bytes <= g_res1_kb * 1024 && (GEMM_SMEM_LIMIT - gemm_fixed_smem(w.block_n, true, 1) - w_bytes) / A_STAGE_BYTES >= 3;
     resident = res1;
@@ -642,16 +682,16 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     const int bn_eff = g.dual ? w.block_n / 2 : w.block_n;
     const bool heur = g.residual == nullptr ? g.taps == 5 : (bn_eff == 64 || g.dual);
     const bool want = g_math_groups == 2 || (g_math_groups == 3 && g.residual == nullptr) || (g_math_groups == 4 && heur);
-    g.math_groups = (staged && want && g.stage_bufs == 2 && g.down_r == 0 && !g.last_mode) ? 2 : 1;
+    g.math_groups = (staged && !pm && want && g.stage_bufs == 2 && g.down_r == 0 && !g.last_mode) ? 2 : 1;
   }
   // pair mode (two M tiles per W k-block) for the long-K layers whose W tile does not stay resident
-  const bool pair = staged && !resident && g.down_r == 0 && g.a2_split == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
+  const bool pair = staged && !pm && !resident && g.down_r == 0 && g.a2_split == 0 && g.a3_split == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
   g.pair = pair ? 1 : 0;
   g.acc_stages = (pair || g.epi_groups == 4) ? MAX_ACC_STAGES : ACC_STAGES;   // four epilogue groups: one 128-column stage each
   g.acc_cols = (pair || g.epi_groups == 4) ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
-  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs, pair);
+  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs, pair, pm);
   if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
-  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs, pair);
+  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs, pair, pm);
   if (custom_tmA) {
     g.rows_per_clip = rows_per_clip;
     g.n_clips = n_clips;
@@ -659,7 +699,8 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   } else {
     g.rows_per_clip = static_cast<int>(M);
     g.n_clips = 1;
-    if (!c.dry()) op.tmA = make_tmap(A, 3, K, M, 1, lda, static_cast<uint64_t>(lda) * M, BK, BM, w.fp16);
+    // split operands: the tensor is lda wide (reads past it must zero-fill), the contraction K revisits its k-blocks
+    if (!c.dry()) op.tmA = make_tmap(A, 3, w.a3 > 0 ? lda : K, M, 1, lda, static_cast<uint64_t>(lda) * M, BK, BM, w.fp16);
   }
   op.tmB = w.tm;
   op.tmR = w.tm;
@@ -667,7 +708,7 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     op.tmR = make_tmap(g.residual, 3, g.ldo, g.rows_per_clip, g.n_clips, g.ldo,
                        static_cast<uint64_t>(g.ldo) * g.rows_per_clip, w.block_n, BM, false, false);
   op.g = g;
-  op.out0 = g.out_raw;
+  op.out0 = pm ? static_cast<void*>(g.out_raw32) : static_cast<void*>(g.out_raw);
   op.out1 = g.out_act;
   int rows_out = BM - (staged ? g.taps - 1 : 0);
   g.tile_halo = staged ? g.taps - 1 : 0;
@@ -697,8 +738,8 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     if (units < 4LL * g_num_sms) {   // too few units: wave quantisation costs more than the shared W loads save
       g.pair = 0;
       g.acc_stages = ACC_STAGES; g.acc_cols = MAX_BN;
-      g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs, false);
-      op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs, false);
+      g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs, false, pm);
+      op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs, false, pm);
       op.g = g;
     } else {
       op.grid = static_cast<int>(std::min<long long>(units, g_num_sms));
@@ -707,15 +748,15 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   if (g.resident_b && op.grid > g.tiles_n) op.grid -= op.grid % g.tiles_n;   // every CTA keeps one n tile
   if (g.resident_b && op.grid < g.tiles_n) {   // fewer tiles than n tiles: stream W through the ring
     g.resident_b = 0;
-    g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs);
-    op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs);
+    g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs, false, pm);
+    op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs, false, pm);
     op.g = g;
   }
   {
     const double Mt = static_cast<double>(g.rows_per_clip) * g.n_clips;
-    op.flops = 2.0 * Mt * w.N * K;
+    op.flops = 2.0 * Mt * w.N * (w.K_alg > 0 ? w.K_alg : K);   // algorithmic (the split contraction issues 3-4x the MMAs)
     double outs = 0;
-    if (epi == EPI_STFT) outs = Mt * (w.N / 2 + 1) * 2;
+    if (is_stft) outs = Mt * (w.N / 2 + 1) * 2;
     else if (epi == EPI_HEAD) outs = 0;   // logits / mask bytes are caller dependent, added at run time
     else outs = Mt * w.N * 2.0 * ((g.out_raw ? 1 : 0) + (g.out_act ? 1 : 0));
     // the strided STFT frame view re-reads each sample n_fft/hop times from L2; algorithmic = once
@@ -724,6 +765,12 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     const double Mo = static_cast<double>(g.rows_per_clip_out) * g.n_clips;
     op.out_bytes[0] = g.out_raw ? static_cast<size_t>(Mo) * g.ldo * 2 : 0;
     op.out_bytes[1] = g.out_act ? static_cast<size_t>(Mo) * g.ldo * 2 : 0;
+    if (pm) {
+      op.out_bytes[0] = g.out_raw32 ? static_cast<size_t>(Mo) * g.ldo * 4 : 0;
+      op.out_bytes[1] = g.out_act ? static_cast<size_t>(Mo) * g.ldo_act * 2 : 0;
+      op.bytes = Mt * (w.K_alg > 0 ? w.K_alg : K) * 4.0 + Mo * w.N * 4.0 * ((g.out_raw32 ? 1 : 0) + (g.out_act ? 1 : 0) + (g.residual32 ? 1 : 0)) +
+                 static_cast<double>(w.N) * K * 2.0;
+    }
   }
   c.push(op);
 }
@@ -922,7 +969,7 @@ void build_encoder_w(wv_net& n) {
     for (int j = 1; j <= cf.n_residual_enc; ++j)                                // idx=j, seanet.py:684
       st.res.push_back(resblock_w(W, p + ".blocks." + std::to_string(s) + "." + std::to_string(j - 1), j, rs));
     st.spec = spec_w(W, p + ".spec_blocks." + std::to_string(s), nfft, hop, SPEC_MEANS[s], SPEC_STDS[s], rs);
-    if (cf.n_residual_enc >= 1 && C <= g_spec_fuse_maxc)
+    if (cf.n_residual_enc >= 1 && C <= g_spec_fuse_maxc && !g_pm)
       build_dual_w(W, st, p + ".blocks." + std::to_string(s) + "." + std::to_string(cf.n_residual_enc - 1),
                    p + ".spec_blocks." + std::to_string(s), rs, C);
     st.down_pw = pointwise(W, p + ".downsample." + std::to_string(s) + ".2.conv.conv", 1.f, false);
@@ -1397,7 +1444,8 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   g.partial = n.cfg.kind == WV_KIND_DETECTOR ? c.ptr<float>(partial) : nullptr;
   g.hop = h.hop; g.T = c.T; g.n_out = h.n_out; g.head_F = F;
   c.tag("head.gemm");
-  add_gemm(c, EPI_HEAD, h.w, c.ptr<h16>(Z), h.w.K, M, h.w.K, g);
+  // precise nets: the latent is a split pair [M, 2*dim]
+  add_gemm(c, EPI_HEAD, h.w, c.ptr<h16>(Z), n.cfg.precise ? 2 * n.enc.dim : h.w.K, M, h.w.K, g);
   if (n.cfg.kind == WV_KIND_DETECTOR) {   // bit decode exists for the detector only
     Op op;
     op.type = OP_BITS;
@@ -1414,11 +1462,213 @@ void plan_head(PlanCtx& c, wv_net& n, const Buf& Z, int F) {
   c.release(partial);
 }
 
+// ------------------------------------------------------------------------------------------
+// PRECISE nets (cfg.precise): the same SEANet encoder + head with fp32-accurate arithmetic (gemm_sm100.cuh,
+// "PRECISE MODE").  Raw streams X are fp32 [B, T, C]; every tensor that feeds a GEMM is a split-fp16 pair
+// [B, T, 2C] = [hi | lo].  No launch fusion beyond the GEMM epilogues (1x1 + dw5, 1x1 + down-conv).
+GemmArgs pm_args(const float* bias, const float* res32, float* raw32, h16* act, float act_scale, int C) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.bias = bias; g.residual32 = res32; g.out_raw32 = raw32; g.out_act = act;
+  g.act_scale = act_scale; g.ldo = C; g.ldo_act = 2 * C; g.lo_off = C;
+  g.taps = 1;
+  return g;
+}
+
+// 1x1 conv over a split tensor A [B, T, 2K] + causal depthwise k=5 (+ fp32 residual) -> raw32 [B,T,N] / act split [B,T,2N]
+void add_gemm_dw_pm(PlanCtx& c, const GemmW& pw, const DwW& dw, const h16* A, int T, int Kc, const float* res32,
+                    float* raw32, h16* act, float act_scale) {
+  if (dw.k != 5 || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused depthwise conv must be k=5 over the GEMM's N");
+  GemmArgs g = pm_args(dw.bias, res32, raw32, act, act_scale, pw.N);
+  g.taps = 5;
+  g.dw_w = dw.w;
+  CUtensorMap tm;
+  if (!c.dry()) tm = make_tmap(A, 3, 2 * Kc, T, c.B, 2 * Kc, static_cast<uint64_t>(2 * Kc) * T, BK, BM, false);
+  add_gemm(c, EPI_STAGED_PM, pw, nullptr, 0, 0, pw.K, g, &tm, T, c.B);
+}
+
+void add_gemm_down_pm(PlanCtx& c, const GemmW& pw, const DwW& dw, int r, const h16* A, int T, int Kc, float* raw32,
+                      h16* act, float act_scale) {
+  if (dw.k != 2 * r || dw.C != pw.N) WV_THROW(WV_ERR_INVALID, "fused down-conv must be k=2r over the GEMM's N");
+  if (r != 2 && r != 4 && r != 5 && r != 8) WV_THROW(WV_ERR_UNSUPPORTED, "fused down-conv stride %d (2, 4, 5, 8)", r);
+  GemmArgs g = pm_args(dw.bias, nullptr, raw32, act, act_scale, pw.N);
+  g.down_r = r;
+  g.dw_w = dw.w;
+  CUtensorMap tm;
+  if (!c.dry()) tm = make_tmap(A, 3, 2 * Kc, T, c.B, 2 * Kc, static_cast<uint64_t>(2 * Kc) * T, BK, BM, false);
+  add_gemm(c, EPI_STAGED_PM, pw, nullptr, 0, 0, pw.K, g, &tm, T, c.B);
+}
+
+// STFT -> log-magnitude -> normalise as split pairs Y [B*F, 2*ldy]; frames of the hi / lo waveform copies
+Buf plan_spec_stft_pm(PlanCtx& c, const SpecW& s, const Buf& wavh, const Buf& wavl, int pitch, int lead, int F,
+                      const std::string& name, int& ldy_out) {
+  const long long M = static_cast<long long>(c.B) * F;
+  const int ldy = s.n_fft / 2 + 8;
+  Buf Y = c.alloc(static_cast<size_t>(M) * 2 * ldy * 2);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.out_raw = c.ptr<h16>(Y);
+  g.ldo = 2 * ldy;
+  g.lo_off = ldy;
+  g.log_offset = s.mean + std::log(WAV_FP16_SCALE);
+  g.inv_sigma = 1.f / s.stdv;
+  g.clamp_sq = (1e-5f * WAV_FP16_SCALE) * (1e-5f * WAV_FP16_SCALE);
+  g.n_half = s.n_fft / 2;
+  const int base = lead - (s.n_fft - 1);
+  const uint64_t clip_stride = static_cast<uint64_t>(WAV_COPIES) * pitch;
+  CUtensorMap tmh, tml;
+  c.tag(name + ".stft");
+  if ((s.hop * 2) % 16 == 0) {
+    if (!c.dry()) {
+      tmh = make_tmap(c.ptr<__half>(wavh) + base, 3, s.n_fft, F, c.B, s.hop, clip_stride, BK, BM, true);
+      tml = make_tmap(c.ptr<__half>(wavl) + base, 3, s.n_fft, F, c.B, s.hop, clip_stride, BK, BM, true);
+    }
+    add_gemm(c, EPI_STFT_PM, s.dft, nullptr, 0, 0, s.dft.K, g, &tmh, F, c.B);
+  } else if (WAV_COPIES % s.hop == 0) {
+    const int P = WAV_COPIES / s.hop;
+    const int Fq = ceil_div(F, P);
+    g.phases = P;
+    g.frames_per_clip = F;
+    if (!c.dry()) {
+      tmh = make_tmap4(c.ptr<__half>(wavh) + base, s.n_fft, Fq, P, c.B, 8, static_cast<uint64_t>(s.hop) * pitch, clip_stride, BK, BM);
+      tml = make_tmap4(c.ptr<__half>(wavl) + base, s.n_fft, Fq, P, c.B, 8, static_cast<uint64_t>(s.hop) * pitch, clip_stride, BK, BM);
+    }
+    add_gemm(c, EPI_STFT_PM, s.dft, nullptr, 0, 0, s.dft.K, g, &tmh, Fq, c.B * P);
+    c.ops->back().flops = 2.0 * static_cast<double>(M) * s.dft.N * s.n_fft;
+  } else {
+    WV_THROW(WV_ERR_UNSUPPORTED, "precise STFT with hop %d", s.hop);
+  }
+  Op& op = c.ops->back();
+  if (!c.dry()) op.tmR = tml;
+  op.bytes = static_cast<double>(M) * (4.0 * 8 + (s.dft.N / 2 + 1) * 4.0) + static_cast<double>(s.dft.N) * s.dft.K * 2.0;
+  op.out_bytes[0] = static_cast<size_t>(M) * 2 * ldy * 2;
+  ldy_out = ldy;
+  return Y;
+}
+
+// x += spec branch, then the activated split stream: Aout = split(ELU((X + Ws y) * act_scale)); releases X
+void plan_spec_pm(PlanCtx& c, const SpecW& s, const Buf& wavh, const Buf& wavl, int pitch, int lead, int F, Buf& X,
+                  int C, float act_scale, Buf& Aout, const std::string& name) {
+  const long long M = static_cast<long long>(c.B) * F;
+  int ldy = 0;
+  Buf Y = plan_spec_stft_pm(c, s, wavh, wavl, pitch, lead, F, name, ldy);
+  Aout = c.alloc(static_cast<size_t>(M) * 2 * C * 2);
+  c.tag(name + ".out");
+  add_gemm(c, EPI_STAGED_PM, s.layer, c.ptr<h16>(Y), 2 * ldy, M, s.layer.K,
+           pm_args(nullptr, c.ptr<float>(X), nullptr, c.ptr<h16>(Aout), act_scale, C));
+  c.release(Y);
+  c.release(X);
+}
+
+void plan_encoder_pm(PlanCtx& c, wv_net& n, Plan& plan) {
+  const EncoderW& e = n.enc;
+  const int B = c.B, T = c.T;
+  const int lead = e.nfft_max - 1;
+  const int pitch = static_cast<int>(round_up(lead + T, 8));
+  const size_t wav_bytes = static_cast<size_t>(B) * WAV_COPIES * pitch * 2 + 256;
+  Buf wavh = c.alloc(wav_bytes), wavl = c.alloc(wav_bytes);
+  {
+    Op op;
+    op.type = OP_WAV_STAGE_PM;
+    op.out0 = c.ptr<__half>(wavh); op.out1 = c.ptr<__half>(wavl);
+    op.fa = WAV_FP16_SCALE;
+    op.i[0] = B; op.i[1] = T; op.i[2] = lead; op.i[3] = pitch;
+    op.grid = elem_grid(static_cast<long long>(B) * WAV_COPIES * (pitch / 8));
+    op.bytes = static_cast<double>(B) * (T * 4.0 + 2.0 * WAV_COPIES * pitch * 2.0);
+    op.out_bytes[0] = op.out_bytes[1] = static_cast<size_t>(B) * WAV_COPIES * pitch * 2;
+    c.tag("enc.wav16");
+    c.push(op);
+  }
+  int Ts = T, C = e.C0;
+  auto xbytes = [&](int t, int ch) { return static_cast<size_t>(B) * t * ch * 4; };   // fp32 raw == split pair bytes
+  Buf X = c.alloc(xbytes(Ts, C)), A = c.alloc(xbytes(Ts, C));
+  {
+    Op op;
+    op.type = OP_CONV_PRE_PM;
+    op.out0 = c.ptr<float>(X); op.out1 = c.ptr<h16>(A);
+    op.w = e.conv_pre.w; op.bias = e.conv_pre.bias;
+    op.fa = e.stages[0].res[0].pre_scale;
+    op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
+    op.grid = elem_grid(static_cast<long long>(B) * ceil_div(Ts, PRE_TT) * (C / 4));
+    op.flops = 10.0 * B * Ts * C;
+    op.bytes = static_cast<double>(B) * Ts * (4.0 + 8.0 * C);
+    op.out_bytes[0] = op.out_bytes[1] = xbytes(Ts, C);
+    c.tag("enc.pre");
+    c.push(op);
+  }
+  const float down_scale = 1.f / std::sqrt(1.f + n.cfg.n_residual_enc * n.cfg.res_scale_enc * n.cfg.res_scale_enc);
+  const int S = static_cast<int>(e.stages.size());
+  for (int s = 0; s < S; ++s) {
+    const EncStageW& st = e.stages[s];
+    const int nres = static_cast<int>(st.res.size());
+    for (int j = 0; j < nres; ++j) {
+      const ResW& r = st.res[j];
+      const bool last = j == nres - 1;
+      const std::string rname = "enc.s" + std::to_string(s) + ".r" + std::to_string(j);
+      Buf H = c.alloc(xbytes(Ts, C));
+      c.tag(rname + ".h1");
+      add_gemm_dw_pm(c, r.pw1, r.dw1, c.ptr<h16>(A), Ts, C, nullptr, nullptr, c.ptr<h16>(H), 1.f);
+      c.release(A);
+      Buf Xn = c.alloc(xbytes(Ts, C));
+      Buf An = last ? Buf() : c.alloc(xbytes(Ts, C));
+      c.tag(rname + ".out");
+      add_gemm_dw_pm(c, r.pw2, r.dw2, c.ptr<h16>(H), Ts, C, c.ptr<float>(X), c.ptr<float>(Xn),
+                     last ? nullptr : c.ptr<h16>(An), last ? 1.f : st.res[j + 1].pre_scale);
+      c.release(H);
+      c.release(X);
+      X = Xn; A = An;
+    }
+    plan_spec_pm(c, st.spec, wavh, wavl, pitch, lead, Ts, X, C, down_scale, A, "enc.s" + std::to_string(s) + ".spec");
+    const int To = ceil_div(Ts, st.r);
+    const bool last_stage = s == S - 1;
+    Buf Ain = A;
+    X = c.alloc(xbytes(To, 2 * C));
+    A = last_stage ? Buf() : c.alloc(xbytes(To, 2 * C));
+    c.tag("enc.s" + std::to_string(s) + ".down");
+    add_gemm_down_pm(c, st.down_pw, st.down_dw, st.r, c.ptr<h16>(Ain), Ts, C, c.ptr<float>(X),
+                     last_stage ? nullptr : c.ptr<h16>(A), last_stage ? 1.f : e.stages[s + 1].res[0].pre_scale);
+    c.release(Ain);
+    Ts = To; C *= 2;
+  }
+  plan.F = Ts;
+  plan_spec_pm(c, e.spec_post, wavh, wavl, pitch, lead, Ts, X, C, 1.f, A, "enc.post.spec");
+  c.release(wavh);
+  c.release(wavl);
+  const long long M = static_cast<long long>(B) * Ts;
+  Buf D = c.alloc(static_cast<size_t>(M) * 2 * C * 2);
+  {
+    Op op;
+    op.type = OP_DW5_PM;
+    op.in = c.ptr<h16>(A); op.out0 = c.ptr<h16>(D);
+    op.w = e.post_dw.w; op.bias = e.post_dw.bias;
+    op.i[0] = B; op.i[1] = Ts; op.i[2] = C;
+    op.grid = elem_grid(M * (C / 4));
+    op.flops = 10.0 * M * C;
+    op.bytes = 8.0 * M * C;
+    op.out_bytes[0] = static_cast<size_t>(M) * 2 * C * 2;
+    c.tag("enc.post.dw");
+    c.push(op);
+  }
+  c.release(A);
+  plan.latent = c.alloc(static_cast<size_t>(M) * 2 * e.dim * 2);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.bias = e.post_pw.bias;
+  g.out_raw = c.ptr<h16>(plan.latent);
+  g.ldo = 2 * e.dim; g.lo_off = e.dim;
+  g.l2_scale = std::sqrt(static_cast<float>(e.dim));
+  g.f32_F = Ts;
+  c.tag("enc.latent");
+  add_gemm(c, EPI_L2NORM_PM, e.post_pw, c.ptr<h16>(D), 2 * C, M, e.post_pw.K, g);
+  c.release(D);
+}
+
 void build_plan_pass(wv_net& n, Plan& plan, uint8_t* base) {
   plan.ops.clear();
   PlanCtx c;
   c.base = base; c.ops = &plan.ops; c.B = plan.B; c.T = plan.T;
-  plan_encoder(c, n, plan);
+  if (n.cfg.precise) plan_encoder_pm(c, n, plan);
+  else plan_encoder(c, n, plan);
   if (n.cfg.kind == WV_KIND_GENERATOR) plan_decoder(c, n, plan.latent, plan.F, plan.T);
   else plan_head(c, n, plan.latent, plan.F);
   plan.ws_bytes = c.arena.high;
@@ -1516,6 +1766,9 @@ void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
     case EPI_STAGED: launch_k(gemm_sm100_kernel<EPI_STAGED>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
     case EPI_L2NORM: launch_k(gemm_sm100_kernel<EPI_L2NORM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
     case EPI_STFT: launch_k(gemm_sm100_kernel<EPI_STFT>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    case EPI_STAGED_PM: launch_k(gemm_sm100_kernel<EPI_STAGED_PM>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    case EPI_L2NORM_PM: launch_k(gemm_sm100_kernel<EPI_L2NORM_PM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    case EPI_STFT_PM: launch_k(gemm_sm100_kernel<EPI_STFT_PM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
     default: launch_k(gemm_sm100_kernel<EPI_HEAD>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
   }
 }
@@ -1537,7 +1790,7 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
     switch (op.type) {
       case OP_GEMM: {
         GemmArgs g = op.g;
-        if (op.epi == EPI_L2NORM) g.out_f32_t = io.latent;
+        if (op.epi == EPI_L2NORM || op.epi == EPI_L2NORM_PM) g.out_f32_t = io.latent;
         if (g.last_mode) { g.last_x = io.x; g.last_wm = io.wm; g.last_y = io.y; }
         if (g.pre_w != nullptr) g.pre_x = io.x;
         if (op.epi == EPI_HEAD) {
@@ -1587,6 +1840,15 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         break;
       case OP_CONF:
         if (io.conf && io.avg) launch_k(conf_kernel, ceil_div(op.i[0], 128), 128, 0, st, io.avg, io.conf, op.i[0], op.i[1]);
+        break;
+      case OP_CONV_PRE_PM:
+        launch_k(conv_pre_pm_kernel, op.grid, 256, 0, st, io.x, op.w, op.bias, static_cast<float*>(op.out0), static_cast<h16*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2]);
+        break;
+      case OP_DW5_PM:
+        launch_k(dw5_pm_kernel, op.grid, 256, 0, st, static_cast<const h16*>(op.in), op.w, op.bias, static_cast<h16*>(op.out0), op.i[0], op.i[1], op.i[2]);
+        break;
+      case OP_WAV_STAGE_PM:
+        launch_k(wav_stage_pm_kernel, op.grid, 256, 0, st, io.x, static_cast<__half*>(op.out0), static_cast<__half*>(op.out1), op.fa, op.i[0], op.i[1], op.i[2], op.i[3]);
         break;
       case OP_LATENT_IN:
         launch_k(latent_in_kernel, op.grid, 256, 0, st, io.z_in, static_cast<h16*>(op.out0), op.i[0], op.i[1], op.i[2]);
@@ -1649,6 +1911,8 @@ int wv_net_create(const wv_net_config* cfg, const wv_tensor* tensors, int n_tens
     if (cfg->n_strides < 1 || cfg->n_strides > 4) WV_THROW(WV_ERR_UNSUPPORTED, "n_strides must be 1..4");
     if (cfg->n_residual_enc < 1) WV_THROW(WV_ERR_UNSUPPORTED, "n_residual_enc must be >= 1");
     if (cfg->channels_enc % 32 != 0) WV_THROW(WV_ERR_UNSUPPORTED, "channels_enc must be a multiple of 32");
+    if (cfg->precise && cfg->kind == WV_KIND_GENERATOR) WV_THROW(WV_ERR_UNSUPPORTED, "precise mode covers the detector / locator (thresholded outputs) only");
+    struct PmScope { bool prev; explicit PmScope(bool v) : prev(g_pm) { g_pm = v; } ~PmScope() { g_pm = prev; } } pm_scope(cfg->precise != 0);
     for (int i = 0; i < n_tensors; ++i) {
       HostTensor t;
       t.data = tensors[i].data;

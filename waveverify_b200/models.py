@@ -29,7 +29,7 @@ logger = logging.getLogger(__name__)
 class _Net:
     """Owns one `wv_net*` (weights + plans + workspace on one device)."""
 
-    def __init__(self, cfg: NetConfig, folded: Dict[str, torch.Tensor], device_index: int):
+    def __init__(self, cfg: NetConfig, folded: Dict[str, torch.Tensor], device_index: int, precise: bool = False):
         L = _lib.lib()
         c = _lib.NetConfigC()
         c.kind = _lib.KIND[cfg.kind]
@@ -51,6 +51,7 @@ class _Net:
         c.embedding_dim = cfg.embedding_dim
         c.embedding_layers = cfg.embedding_layers
         c.freq_bands = cfg.freq_bands
+        c.precise = int(bool(precise))
         arr = (_lib.TensorC * len(folded))()
         keep = []
         for i, (name, t) in enumerate(folded.items()):
@@ -95,7 +96,7 @@ class _B200Module(nn.Module):
         init = default_init_state_dict(self.cfg)
         for name, (shape, role) in self._spec.items():
             self._register(name, init[name], buffer=(role == "dft"))
-        self._net: Optional[_Net] = None
+        self._nets: Dict[bool, _Net] = {}      # precise flag -> native net (fp16 fast path / fp32-accurate path)
         self._net_sig = None
         self._chunk_samples = 0
         self.eval()
@@ -136,27 +137,37 @@ class _B200Module(nn.Module):
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
-    def _native(self) -> _Net:
+    PRECISE_DEFAULT = False     # Locator: True (its thresholded mask must equal the fp32 reference's)
+
+    def _native(self, precise: Optional[bool] = None) -> _Net:
+        """The native net (built lazily, rebuilt when a parameter changes).  precise=True selects the
+        fp32-accurate twin (split-fp16 tensor-core operands, fp32 epilogues; include/wv_b200.h)."""
+        if precise is None:
+            precise = self.PRECISE_DEFAULT
+        precise = bool(precise)
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError(
                 f"waveverify_b200 {self.KIND} must live on a CUDA device (got {dev}); there is no "
                 "CPU fallback - call .cuda() first")
         sig = (dev.index, self._signature())
-        if self._net is None or self._net_sig != sig:
+        if self._net_sig != sig:
+            self._nets = {}
+            self._net_sig = sig
+        if precise not in self._nets:
             folded = fold_state_dict(self.state_dict())
             idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            self._net = _Net(self.cfg, folded, idx)
+            net = _Net(self.cfg, folded, idx, precise=precise)
             if self._chunk_samples:
-                _lib.check(_lib.lib().wv_net_set_chunk(self._net.handle, int(self._chunk_samples)), "set_chunk")
-            self._net_sig = sig
-        return self._net
+                _lib.check(_lib.lib().wv_net_set_chunk(net.handle, int(self._chunk_samples)), "set_chunk")
+            self._nets[precise] = net
+        return self._nets[precise]
 
     def set_chunk_samples(self, n: int):
         """Process at most ~n samples (clips x T) per internal sub-batch; 0 = whole batch."""
         self._chunk_samples = int(n)
-        if self._net is not None:
-            _lib.check(_lib.lib().wv_net_set_chunk(self._net.handle, int(n)), "set_chunk")
+        for net in self._nets.values():
+            _lib.check(_lib.lib().wv_net_set_chunk(net.handle, int(n)), "set_chunk")
 
     def set_profile(self, enable: bool):
         _lib.check(_lib.lib().wv_net_set_profile(self._native().handle, int(bool(enable))), "set_profile")
@@ -316,11 +327,21 @@ class Detector(_HeadModel):
     ships no mixture-of-experts)."""
     KIND = "detector"
 
+    # Bit decisions (mean sigmoid >= 0.5) of the fp16 fast path are re-evaluated with the fp32-accurate net
+    # wherever a clip has a bit whose mean lies within this distance of 0.5: 5x the measured fast-path
+    # error on the mean (4e-5 for clips / masks of >= 4000 samples; short clips do not average the per-sample
+    # logit error (<= 0.008) down: |d sigmoid| <= 0.25 * 0.008 = 2e-3).
+    EXACT_TAU = 2e-4
+    EXACT_TAU_SHORT = 5e-3
+    EXACT_SHORT_SAMPLES = 4000
+
     def __init__(self, **kwargs):
         if kwargs.get("nbits", 16) <= 0:
             raise ValueError(f"Invalid nbits: {kwargs['nbits']}. Must be positive.")
         super().__init__(**kwargs)
         self.nbits = self.cfg.nbits
+        self.exact_bits = True      # False: fp16 fast path only (bits exact outside a 3e-4 guard band)
+        self.recheck_count = 0      # clips re-evaluated by the precise net so far (diagnostic)
 
     def preprocess(self, audio_data: torch.Tensor, sample_rate: Optional[int] = None):
         """model/detector.py:222-276."""
@@ -332,12 +353,7 @@ class Detector(_HeadModel):
             raise ValueError(f"Expected 3D tensor, got {audio_data.dim()}D")
         return self._pad(audio_data, sample_rate)
 
-    @torch.no_grad()
-    def detect_batch(self, audio: torch.Tensor, presence: Optional[torch.Tensor] = None,
-                     want_logits: bool = False):
-        """audio [B,1,T] -> dict(bits u8 [B,nbits], avg, conf [B], valid, logits?).  Bit decode =
-        sigmoid -> (masked) time mean -> >= 0.5 (waveverify/core.py:577-586, evaluate.py:471-494)."""
-        x = self._check_audio(audio)
+    def _run(self, x, pm, want_logits, precise):
         B, _, T = x.shape
         dev = x.device
         nb = self.nbits
@@ -346,16 +362,55 @@ class Detector(_HeadModel):
         avg = torch.empty(B, nb, device=dev, dtype=torch.float32)
         conf = torch.empty(B, device=dev, dtype=torch.float32)
         valid = torch.empty(B, nb, device=dev, dtype=torch.uint8)
+        _lib.check(_lib.lib().wv_detector_forward(self._native(precise).handle, _ptr(x), B, T, _ptr(logits), _ptr(bits),
+                                                  _ptr(avg), _ptr(conf), _ptr(valid), _ptr(pm), _stream(dev)),
+                   "wv_detector_forward")
+        return dict(bits=bits, avg=avg, conf=conf, valid=valid, logits=logits)
+
+    @torch.no_grad()
+    def detect_batch(self, audio: torch.Tensor, presence: Optional[torch.Tensor] = None,
+                     want_logits: bool = False, precise: Optional[bool] = None):
+        """audio [B,1,T] -> dict(bits u8 [B,nbits], avg, conf [B], valid, logits?).  Bit decode =
+        sigmoid -> (masked) time mean -> >= 0.5 (waveverify/core.py:577-586, evaluate.py:471-494).
+
+        The batch runs on the fp16 fast path; with `exact_bits` (default) every clip that has a bit whose mean
+        lies within EXACT_TAU of the 0.5 threshold is re-evaluated by the fp32-accurate net and its
+        bits / avg / conf / valid (and logits) are replaced, so the decoded bits equal the fp32 reference's.
+        precise=True runs the whole batch on the fp32-accurate net."""
+        x = self._check_audio(audio)
+        B, _, T = x.shape
+        dev = x.device
         pm = None
         if presence is not None:
             pm = presence.to(dev).reshape(B, -1)
             if pm.shape[1] != T:
                 raise ValueError(f"presence mask must have {T} samples per clip, got {pm.shape[1]}")
             pm = (pm != 0).to(torch.uint8).contiguous()
-        _lib.check(_lib.lib().wv_detector_forward(self._native().handle, _ptr(x), B, T, _ptr(logits), _ptr(bits),
-                                                  _ptr(avg), _ptr(conf), _ptr(valid), _ptr(pm), _stream(dev)),
-                   "wv_detector_forward")
-        return dict(bits=bits, avg=avg, conf=conf, valid=valid, logits=logits)
+        if precise:
+            return self._run(x, pm, want_logits, True)
+        out = self._run(x, pm, want_logits, False)
+        if not self.exact_bits:
+            return out
+        n_eff = pm.sum(dim=1, dtype=torch.int64) if pm is not None else None
+        if n_eff is None:
+            tau = self.EXACT_TAU if T >= self.EXACT_SHORT_SAMPLES else self.EXACT_TAU_SHORT
+            near = ((out["avg"] - 0.5).abs() < tau).any(dim=1)
+        else:
+            tau = torch.where(n_eff >= self.EXACT_SHORT_SAMPLES, self.EXACT_TAU, self.EXACT_TAU_SHORT).to(torch.float32)
+            near = (((out["avg"] - 0.5).abs() < tau[:, None]) & (out["valid"] != 0)).any(dim=1)
+        idx = near.nonzero().flatten()          # one small device -> host read per call
+        if idx.numel() > 0:
+            self.recheck_count += int(idx.numel())
+            n = int(idx.numel())
+            n_pad = min(B, 1 << (n - 1).bit_length())   # few distinct sub-batch shapes (plans / graphs are cached per shape)
+            if n_pad > n:
+                idx = torch.cat([idx, idx[-1:].expand(n_pad - n)])
+            sub = self._run(x[idx].contiguous(), None if pm is None else pm[idx].contiguous(), want_logits, True)
+            for k in ("bits", "avg", "conf", "valid"):
+                out[k][idx] = sub[k]
+            if want_logits:
+                out["logits"][idx] = sub["logits"]
+        return out
 
     def decode(self, audio_data: torch.Tensor, orig_nframes: int) -> torch.Tensor:
         """model/detector.py:278-318 -> raw logits [B, nbits, orig_nframes]."""
@@ -388,8 +443,18 @@ class Detector(_HeadModel):
 
 
 class Locator(_HeadModel):
-    """Drop-in for model/locator.py:Locator."""
+    """Drop-in for model/locator.py:Locator.  Runs on the fp32-accurate ("precise") net by default: its mask is a
+    threshold on raw logits (model/watermarking.py:717), which the fp16 fast path reproduces only outside a
+    +-0.004 band; `exact = False` selects the fast path."""
     KIND = "locator"
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.exact = True
+
+    @property
+    def PRECISE_DEFAULT(self):   # noqa: N802 - overrides the class attribute of _B200Module
+        return bool(getattr(self, "exact", True))
 
     def preprocess(self, audio_data: torch.Tensor, sample_rate: Optional[int] = None):
         """model/locator.py:186-226."""
