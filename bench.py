@@ -290,6 +290,7 @@ def run_ours(a):
         s.record()
         step(x, msg, counters)
         e.record()
+    local_counters = counters.clone()
     if world > 1:
         allreduce_counters(counters)           # the path's only collective: 6 x int64
     barrier()
@@ -303,6 +304,24 @@ def run_ours(a):
     audio_s_per_step = B * T / SR * world
     value = audio_s_per_step * a.steps / (total_ms / 1e3)
     ber, miou = ber_miou(counters)
+    # N > 1: the all-reduced counters must equal the sum of every rank's counters, recomputed by rank 0 alone from the
+    # ranks' seeds (the path is deterministic: same inputs -> same integers), outside the timed region
+    counters_check = None
+    if world > 1 and rank == 0:
+        expect = torch.zeros(6, dtype=torch.int64, device=dev)
+        for r in range(world):
+            xr, mr, gr = synth(B, T, 100 + r)
+            xr = torch.from_numpy(xr).to(dev); mr = torch.from_numpy(mr).to(dev); gr = torch.from_numpy(gr).to(dev)
+            _, yr, _ = G.embed_batch(xr, mr, want_wm=False)
+            dr = D.detect_batch(yr); lr = L.locate_batch(yr)
+            one = metric_counters(dr["bits"], dr["valid"], mr, lr["mask"], gr)
+            if r == 0 and not torch.equal(one * a.steps, local_counters):
+                raise RuntimeError("rank 0: recomputed counters differ from the timed loop's")
+            expect += one * a.steps
+        counters_check = {"allreduced": counters.tolist(), "recomputed_on_rank0": expect.tolist(),
+                          "equal": bool(torch.equal(expect, counters))}
+        if not counters_check["equal"]:
+            raise RuntimeError(f"all-reduced BER/MIoU counters differ from the per-rank recomputation: {counters_check}")
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing ----
     hx = torch.from_numpy(x_np).pin_memory(); hm = torch.from_numpy(msg_np.astype("float32")).pin_memory()
@@ -474,7 +493,8 @@ def run_ours(a):
             "gpu_launches": launches_per_step * a.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "kernel_breakdown": breakdown, "wall_s_timed_region": t_wall,
-            "quality": {"ber": ber, "miou": miou, "note": "random-init weights: values are only a checksum of the counters path"},
+            "quality": {"ber": ber, "miou": miou, "counters": counters.tolist(), "counters_check": counters_check,
+                        "note": "random-init weights: values are only a checksum of the counters path"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -146,6 +146,13 @@ int wv_effect_median(const float* in, int B, int T, int k, float* out, void* str
  * device, designed by the host), replicate padding, out = subtract ? in - fir(in) : fir(in). */
 int wv_effect_fir(const float* in, const float* taps, int n_taps, int B, int T, int subtract, float* out, void* stream);
 
+/* torchaudio.transforms.Resample(orig, new) as the `resample` effect uses it (utils/effect_augmentation.py:1451-1502) and
+ * the resampling half of `speed` (:1381-1449).  orig / nw = the two rates divided by their gcd; taps [nw][2*width + orig]
+ * (device, designed by the host); T_mid = ceil(T*nw/orig) = resampled length.  lerp = 1 additionally stretches the
+ * resampled signal to T_out samples by linear interpolation (align_corners = False), as `speed` does (:187-215). */
+int wv_effect_resample(const float* in, const float* taps, int B, int T, int orig, int nw, int width, int T_mid, int T_out,
+                       int lerp, float* out, void* stream);
+
 /* ---- profiling / debugging (used by bench.py and the tests) ------------------------------- */
 /* When enabled, every launch of a forward is bracketed by CUDA events on the caller's stream. */
 int wv_net_set_profile(wv_net* net, int enable);

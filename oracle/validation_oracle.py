@@ -188,3 +188,65 @@ def bandpass_filter(x, lo_freq, hi_freq, sample_rate):
     lo, hi = max(0.0, min(lo_freq, nyq - 1e-5)) / nyq, max(0.0, min(hi_freq, nyq - 1e-5)) / nyq
     taps = julius_lowpass_taps([lo, hi])
     return julius_fir(x, taps[1]) - julius_fir(x, taps[0])
+
+
+# ---- resample / speed (utils/effect_augmentation.py:1381-1502) ------------------------------------------------
+def sinc_resample_taps(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """torchaudio.functional._get_sinc_resample_kernel (sinc_interp_hann) in float64 numpy ->
+    (taps [new, 2*width + orig] float64, width, orig, new), rates divided by their gcd."""
+    import math
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    t = (np.arange(0, -new, -1, dtype=np.float32)[:, None] / np.float32(new)).astype(np.float64) + idx   # torchaudio: fp32 phases
+    t = np.clip(t * base, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    with np.errstate(divide="ignore", invalid="ignore"):
+        k = np.where(t == 0, 1.0, np.sin(t) / t)
+    return (k * window * (base / orig)).astype(np.float32).astype(np.float64), width, orig, new
+
+
+def sinc_resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
+    """torchaudio.functional.resample: zero-pad (width, width + orig), strided correlation with the filter bank,
+    interleave the `new` phases, keep ceil(new * T / orig) samples.  float64 accumulation."""
+    if orig_freq == new_freq:
+        return x.astype(np.float32)
+    h, width, orig, new = sinc_resample_taps(orig_freq, new_freq)
+    T = x.shape[-1]
+    xp = np.pad(x.astype(np.float64), [(0, 0)] * (x.ndim - 1) + [(width, width + orig)])
+    n_fr = (xp.shape[-1] - h.shape[1]) // orig + 1
+    out = np.zeros(x.shape[:-1] + (n_fr, new))
+    for q in range(n_fr):
+        seg = xp[..., q * orig:q * orig + h.shape[1]]
+        out[..., q, :] = seg @ h.T
+    T_out = -(-T * new // orig)
+    return out.reshape(x.shape[:-1] + (n_fr * new,))[..., :T_out].astype(np.float32)
+
+
+def resample_effect(x: np.ndarray, new_sample_rate: int, sample_rate: int) -> np.ndarray:
+    return sinc_resample(sinc_resample(x, sample_rate, new_sample_rate), new_sample_rate, sample_rate)
+
+
+def linear_stretch(y: np.ndarray, T_out: int) -> np.ndarray:
+    """torch.nn.functional.interpolate(mode='linear', align_corners=False) with its fp32 index arithmetic."""
+    T_in = y.shape[-1]
+    scale = np.float32(T_in) / np.float32(T_out)
+    src = (np.arange(T_out, dtype=np.float32) + np.float32(0.5)) * scale - np.float32(0.5)
+    src = np.maximum(src, np.float32(0))
+    i0 = src.astype(np.int64)
+    i1 = i0 + (i0 < T_in - 1)
+    l1 = (src - i0.astype(np.float32)).astype(np.float64)
+    return ((1 - l1) * y[..., i0].astype(np.float64) + l1 * y[..., i1].astype(np.float64)).astype(np.float32)
+
+
+def speed_effect(x: np.ndarray, speed: float, sample_rate: int) -> np.ndarray:
+    """SoX speed + rate as a windowed-sinc resample from sr*speed to sr (PARITY UNPINNED against SoX itself), then the
+    reference's linear stretch back to the input length (utils/effect_augmentation.py:187-215, 583-590)."""
+    src = int(round(sample_rate * speed))
+    if src == sample_rate:
+        return x.astype(np.float32)
+    return linear_stretch(sinc_resample(x, src, sample_rate), x.shape[-1])
+

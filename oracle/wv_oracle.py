@@ -140,11 +140,13 @@ def causal_stft_mag(wav: Tensor, weight: Tensor, hop: int) -> Tensor:
 
 
 def spec_branch(x: Tensor, wav: Tensor, W: Dict[str, Tensor], p: str, hop: int, mean: float,
-                std: float, res_scale: float) -> Tensor:
+                std: float, res_scale: float, taps: Optional[dict] = None, tap_name: str = "") -> Tensor:
     """SpecBlock.forward (modules/seanet.py:463-507), compression='log', inout_norm."""
     y = causal_stft_mag(wav, W[f"{p}.spec.weight"], hop)
     y = y.clamp_min(1e-5).log()
     y = (y - mean) / std
+    if taps is not None:
+        taps[tap_name + "_y"] = y
     y = F.conv1d(y, W[f"{p}.layer.conv.conv.weight"])
     scale = res_scale
     sp = W.get(f"{p}.scale_param")
@@ -195,7 +197,11 @@ def encoder_forward(wav: Tensor, msg: Optional[Tensor], W: Dict[str, Tensor], cf
     for s, r in enumerate(ratios):
         for j in range(1, n_res + 1):                   # idx = j because spec != "" (seanet.py:684)
             x = resblock(x, W, f"{p}.blocks.{s}.{j - 1}", j, rs)
-        x = spec_branch(x, wav, W, f"{p}.spec_blocks.{s}", hop, SPEC_MEANS[s], SPEC_STDS[s], rs)
+        if taps is not None:
+            taps[f"enc_s{s}_res"] = x
+        x = spec_branch(x, wav, W, f"{p}.spec_blocks.{s}", hop, SPEC_MEANS[s], SPEC_STDS[s], rs, taps, f"enc_s{s}")
+        if taps is not None:
+            taps[f"enc_s{s}_spec"] = x
         hop *= r
         # downsample: Scale, ELU, 1x1 (no bias), strided depthwise (bias)  seanet.py:745-771
         x = elu(x * (1.0 + n_res * rs ** 2) ** -0.5)
@@ -213,13 +219,17 @@ def encoder_forward(wav: Tensor, msg: Optional[Tensor], W: Dict[str, Tensor], cf
             x = x * g + b
         if taps is not None:
             taps[f"enc_s{s}"] = x
-    x = spec_branch(x, wav, W, f"{p}.spec_post", hop, SPEC_MEANS[-1], SPEC_STDS[-1], rs)
+    x = spec_branch(x, wav, W, f"{p}.spec_post", hop, SPEC_MEANS[-1], SPEC_STDS[-1], rs, taps, "enc_post")
+    if taps is not None:
+        taps["enc_post_spec"] = x
     # conv_post: ELU, dw k5 (no bias), 1x1 (bias), L2Norm * sqrt(dim)   seanet.py:797-823
     x = elu(x)
     wd = W[f"{p}.conv_post.1.conv.conv.weight"]
     x = causal_conv1d(x, wd, None, groups=wd.shape[0])
     x = F.conv1d(x, W[f"{p}.conv_post.2.conv.conv.weight"], W.get(f"{p}.conv_post.2.conv.conv.bias"))
     x = F.normalize(x, p=2.0, dim=1, eps=1e-12) * (cfg["dimension"] ** 0.5)   # seanet.py:288-318
+    if taps is not None:
+        taps["enc_latent"] = x
     return x
 
 
@@ -284,9 +294,9 @@ def detector_forward(y: Tensor, W: Dict[str, Tensor], cfg: dict) -> Tensor:
     return _head(encoder_forward(y, None, W, cfg, "encoder"), W, y.shape[-1])
 
 
-def locator_forward(y: Tensor, W: Dict[str, Tensor], cfg: dict) -> Tensor:
+def locator_forward(y: Tensor, W: Dict[str, Tensor], cfg: dict, taps: Optional[dict] = None) -> Tensor:
     """Locator.forward/decode (model/locator.py:268-299, 228-265) -> logits [B,1,T]."""
-    return _head(encoder_forward(y, None, W, cfg, "encoder"), W, y.shape[-1])
+    return _head(encoder_forward(y, None, W, cfg, "encoder", taps), W, y.shape[-1])
 
 
 # --------------------------------------------------------------------------------------

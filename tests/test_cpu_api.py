@@ -84,3 +84,94 @@ def test_load_audio_resamples_like_the_reference(tmp_path):
     want = torchaudio.transforms.Resample(sr, 16000)(mono)
     assert out_sr == 16000 and wav.shape == want.shape
     assert torch.allclose(wav, want, atol=1e-6)
+
+
+# ---- checkpoint formats (waveverify/core.py:141-168, 225-469): host-side model construction + load ----------
+def _fixture_models(bias, zero_init):
+    from waveverify_b200 import Detector, Generator, Locator, fixture_state_dict
+    loc = dict(dimension=64, channels_enc=32, n_residual_enc=1, strides=[8, 4])
+    out = {}
+    for name, cls, kw in (("generator", Generator, {}), ("detector", Detector, {}), ("locator", Locator, loc)):
+        m = cls(**{**kw, "bias": bias, "zero_init": zero_init})
+        m.load_state_dict(fixture_state_dict(m.cfg, 3))
+        out[name] = m
+    return out
+
+
+def _same_params(a, b):
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+
+
+def test_atomic_checkpoint_builds_models_from_its_config(tmp_path):
+    """conf/base.yml trains with zero_init=False / bias as configured: the architecture must come from
+    checkpoint['config'] (core.py:230-276), not from the class defaults (zero_init=True adds scale parameters)."""
+    from waveverify_b200 import WaveVerify
+    src = _fixture_models(bias=True, zero_init=False)
+    config = {"Generator.zero_init": False, "Generator.bias": True, "Generator.channels_enc": 64,
+              "Detector.zero_init": False, "Detector.bias": True, "Detector.nbits": 16,
+              "Locator.zero_init": False, "Locator.bias": True, "Locator.nbits": 16, "Locator.strides": [8, 4],
+              "Locator.channels_enc": 32, "Locator.dimension": 64, "Locator.n_residual_enc": 1, "train.lr": 1e-4}
+    f = tmp_path / "latest.pth"
+    torch.save({"models": {k: m.state_dict() for k, m in src.items()}, "config": config, "step": 7}, str(f))
+    g, d, l = WaveVerify.build_models(f)
+    assert g.cfg.zero_init is False and not any(k.endswith("scale_param") for k in g.state_dict())
+    for m, name in ((g, "generator"), (d, "detector"), (l, "locator")):
+        _same_params(m, src[name])
+    # a directory holding best.pth / latest.pth is the reference's normal layout (core.py:141-168): best.pth wins
+    other = _fixture_models(bias=True, zero_init=True)
+    torch.save({"models": {k: m.state_dict() for k, m in other.items()}}, str(tmp_path / "best.pth"))
+    g2, d2, l2 = WaveVerify.build_models(tmp_path)
+    assert g2.cfg.zero_init is True                       # no config stored: inferred from the *scale_param keys
+    _same_params(g2, other["generator"])
+    _same_params(l2, other["locator"])
+
+
+def test_checkpoint_without_config_infers_bias_and_zero_init(tmp_path):
+    from waveverify_b200 import WaveVerify
+    from waveverify_b200.fold import fold_state_dict
+    src = _fixture_models(bias=True, zero_init=False)
+    # parametrizations removed before saving (scripts/train.py:1624-1629): plain `weight` keys
+    plain = {k: fold_state_dict(m.state_dict()) for k, m in src.items()}
+    f = tmp_path / "ck.pth"
+    torch.save({"models": plain}, str(f))
+    g, d, l = WaveVerify.build_models(f)
+    assert g.cfg.zero_init is False and g.cfg.bias is True
+    a, b = fold_state_dict(g.state_dict()), plain["generator"]
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.allclose(a[k], b[k], atol=1e-6), k
+    # a checkpoint that does not match the architecture fails loudly instead of leaving parameters at their init
+    broken = {k: dict(v) for k, v in plain.items()}
+    drop = next(k for k in broken["detector"] if k.startswith("encoder.blocks.0.0.block.1"))
+    del broken["detector"][drop]
+    torch.save({"models": broken}, str(tmp_path / "broken.pth"))
+    with pytest.raises(RuntimeError, match="parameters missing"):
+        WaveVerify.build_models(tmp_path / "broken.pth")
+
+
+def test_legacy_checkpoint_layout(tmp_path):
+    """<dir>/{generator,detector,locator}/model.pth, strict loading (core.py:428-469)."""
+    from waveverify_b200 import WaveVerify
+    src = _fixture_models(bias=True, zero_init=True)
+    for name, m in src.items():
+        (tmp_path / name).mkdir()
+        torch.save(m.state_dict(), str(tmp_path / name / "model.pth"))
+    g, d, l = WaveVerify.build_models(tmp_path)
+    for m, name in ((g, "generator"), (d, "detector"), (l, "locator")):
+        _same_params(m, src[name])
+    (tmp_path / "locator" / "model.pth").unlink()
+    with pytest.raises(FileNotFoundError):
+        WaveVerify.build_models(tmp_path)
+
+
+def test_plain_weight_with_zero_rows_folds_to_zeros():
+    """zero-initialised '1x1_zero' / pruned channels: g*v/||v|| must stay 0, not 0*0/0 = NaN."""
+    from waveverify_b200.fold import _WN_G, _WN_V, fold_state_dict, unfold_plain_weight
+    w = torch.randn(6, 4, 5)
+    w[2] = 0
+    g, v = unfold_plain_weight(w)
+    out = fold_state_dict({"a" + _WN_G: g, "a" + _WN_V: v})["a.weight"]
+    assert torch.isfinite(out).all() and torch.allclose(out, w, atol=1e-6) and float(out[2].abs().max()) == 0.0

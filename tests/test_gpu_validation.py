@@ -238,3 +238,62 @@ def test_fir_effects_against_oracle():
     lo, _ = V.apply_effect(xd, "lowpass_filter", sample_rate=sr, cutoff_freq=1000)
     hi, _ = V.apply_effect(xd, "highpass_filter", sample_rate=sr, cutoff_freq=1000)
     assert float((lo + hi - xd).abs().max()) < 1e-6
+
+
+def test_resample_and_speed_effects():
+    """`resample` against outputs of the reference itself (tests/golden/validation/resample.npz: the reference's
+    apply_effect -> torchaudio.transforms.Resample down and up) and `speed` against torchaudio's resampler + the reference's
+    linear stretch (SoX itself: parity unpinned); then the float64 oracle at full clip length.  Tolerance 2e-6 absolute
+    (fp32 FIR of <= 30 taps, |x| <= 0.5)."""
+    z = np.load(os.path.join(GOLDEN, "validation", "resample.npz"))
+    for i, (seed, B, T, sr, new_sr) in enumerate(z["resample_cases"]):
+        x, _ = inputs(int(seed), int(B), int(T))
+        m = torch.ones(int(B), 1, int(T), device="cuda")
+        out, m2 = V.apply_effect(dev(x), "resample", sample_rate=int(sr), mask=m, new_sample_rate=int(new_sr))
+        assert m2 is m and out.shape == z[f"resample{i}"].shape
+        assert np.abs(out.cpu().numpy() - z[f"resample{i}"]).max() <= (2e-6 if int(new_sr) in (32000, 8000) else 1e-5), i
+    for i, (seed, B, T, sr, sp) in enumerate(z["speed_cases"]):
+        x, _ = inputs(int(seed), int(B), int(T))
+        out, _ = V.apply_effect(dev(x), "speed", sample_rate=int(sr), speed=float(sp) / 1000.0)
+        assert out.shape == x.shape
+        assert np.abs(out.cpu().numpy() - z[f"speed{i}"]).max() <= 5e-6, i
+    x, _ = inputs(77, 4, 16000)
+    xd = dev(x)
+    out, _ = V.apply_effect(xd, "resample", sample_rate=16000, new_sample_rate=32000)       # conf/effects_config.yml:70-91
+    assert np.abs(out.cpu().numpy() - VO.resample_effect(x, 32000, 16000)).max() <= 2e-6
+    out, _ = V.apply_effect(xd, "speed", sample_rate=16000, speed=0.8)
+    assert np.abs(out.cpu().numpy() - VO.speed_effect(x, 0.8, 16000)).max() <= 2e-6
+    # error behaviour of the reference: bad rate -> ValueError; non-positive speed -> logged, input returned unchanged
+    with pytest.raises(ValueError):
+        V.apply_effect(xd, "resample", sample_rate=16000, new_sample_rate=0)
+    with pytest.raises(ValueError):
+        V.apply_effect(xd, "resample", sample_rate=16000, new_sample_rate=8000.0)
+    out, _ = V.apply_effect(xd, "speed", sample_rate=16000, speed=-1.0)
+    assert out is xd
+    out, _ = V.apply_effect(xd, "speed", sample_rate=16000, speed=1.0)
+    assert out is xd
+
+
+def test_validation_pipeline_runs_the_references_eval_effects():
+    """conf/effects_config.yml:70-91 `eval_effects` end to end on the device (model/watermarking.py:443-483)."""
+    from helpers import BASE_KW, fixture_weights
+    from waveverify_b200 import AudioSignal, Detector, Generator, Locator
+    mods = {}
+    for kind, cls in (("generator", Generator), ("detector", Detector), ("locator", Locator)):
+        _, sd = fixture_weights(kind, False, 0)
+        m = cls(**{**BASE_KW[kind], "bias": True, "zero_init": False})
+        m.load_state_dict(sd)
+        mods[kind] = m.cuda()
+    eval_effects = [("identity", {}), ("resample", {"new_sample_rate": 32000}), ("speed", {"speed": 0.8}),
+                    ("random_noise", {"noise_std": 0.001}), ("lowpass_filter", {"cutoff_freq": 2000}),
+                    ("highpass_filter", {"cutoff_freq": 3500}), ("bandpass_filter", {"cutoff_freq_low": 300, "cutoff_freq_high": 4000})]
+    pipe = V.ValidationPipeline(mods["generator"], mods["detector"], mods["locator"], effects=eval_effects)
+    rng = np.random.RandomState(3)
+    x = torch.from_numpy((0.1 * rng.standard_normal((4, 1, 16000))).astype(np.float32)).cuda()
+    msg = torch.from_numpy(rng.randint(0, 2, (4, 16))).cuda()
+    np.random.seed(1); torch.manual_seed(1)
+    wm, y, results, stats = pipe(AudioSignal(x, 16000), msg)
+    assert list(results) == [n for n, _ in eval_effects]
+    for name, r in results.items():
+        assert 0.0 <= r["ber"] <= 1.0 and 0.0 <= r["miou"] <= 1.0, name
+        assert r["locator_mask"].shape == r["mask"].shape

@@ -170,11 +170,81 @@ def embed_streaming(generator: Generator, audio: torch.Tensor, msg: torch.Tensor
     return out
 
 
+# ---- checkpoints (waveverify/core.py:141-168, 225-469) -------------------------------------------
+_LOC_DEFAULT_KW = dict(dimension=64, channels_enc=32, n_residual_enc=1, strides=[8, 4])
+_CFG_KEYS = ("sample_rate", "channels_audio", "dimension", "msg_dimension", "channels_enc", "channels_dec", "n_fft_base",
+             "n_residual_enc", "n_residual_dec", "res_scale_enc", "res_scale_dec", "res_scale", "strides", "kernel_size",
+             "last_kernel_size", "residual_kernel_size", "norm", "bias", "zero_init", "nbits", "output_dim", "embedding_dim",
+             "embedding_layers", "freq_bands",
+             # reference kwargs with one supported value: passed on so that an unsupported setting is rejected loudly
+             "activation", "activation_kwargs", "norm_kwargs", "dilation_base", "skip", "act_all", "expansion", "groups",
+             "encoder_l2norm", "spec", "spec_compression", "pad_mode", "causal", "inout_norm", "final_activation",
+             "spec_layer", "spec_learnable")
+
+
+def find_atomic_checkpoint(path: Path) -> Optional[Path]:
+    """core.py:141-168 / 295-322: a .pth file, or the best.pth / latest.pth / first *.pth of a directory that holds
+    a dict with a 'models' entry.  None = not an atomic checkpoint (legacy per-component layout)."""
+    if path.is_file():
+        return path
+    if not path.is_dir():
+        raise FileNotFoundError(f"checkpoint path not found: {path}")
+    files = sorted(path.glob("*.pth"))
+    ordered = [f for n in ("best.pth", "latest.pth") for f in files if f.name == n] + \
+              [f for f in files if f.name not in ("best.pth", "latest.pth")]
+    for f in ordered:
+        try:
+            ck = torch.load(str(f), map_location="cpu", weights_only=False)
+        except Exception:  # noqa: BLE001 - the reference skips unreadable files too
+            continue
+        if isinstance(ck, dict) and "models" in ck:
+            return f
+    return None
+
+
+def kwargs_from_checkpoint_config(config: Optional[dict], cls_name: str) -> dict:
+    """The reference builds G / D / L from checkpoint['config'] (an argbind scope: 'Generator.channels_enc': 64, ...;
+    core.py:230-276) before loading the weights."""
+    if not config:
+        return {}
+    out = {}
+    for k, v in config.items():
+        if isinstance(k, str) and k.startswith(cls_name + "."):
+            name = k[len(cls_name) + 1:]
+            if name in _CFG_KEYS:
+                out[name] = v
+    if cls_name == "Locator":
+        out.pop("nbits", None)            # conf/base.yml lists it, model/locator.py has no such kwarg (SURVEY F5)
+    return out
+
+
+def infer_kwargs_from_state_dict(sd: dict) -> dict:
+    """Without a stored config: `bias` and `zero_init` change the parameter inventory (modules/seanet.py:151-243: the
+    *scale_param entries exist only with zero_init, conv biases only with bias), so they are read off the keys.
+    Loading a zero_init=False checkpoint into a zero_init=True model would leave every scale parameter at 0."""
+    keys = list(sd.keys())
+    return dict(bias=any(k.startswith("encoder.conv_pre.") and k.endswith(".bias") for k in keys),
+                zero_init=any(k.endswith("scale_param") for k in keys))
+
+
+def _load_component(m, sd: dict, name: str, strict: bool):
+    res = m.load_state_dict(sd, strict=strict)
+    missing = [k for k in getattr(res, "missing_keys", []) if not k.endswith(".spec.weight")]   # fixed DFT buffers
+    if missing:
+        raise RuntimeError(f"checkpoint does not match the {name} architecture: {len(missing)} parameters missing "
+                           f"(e.g. {missing[0]}); outputs would be silently wrong")
+    unexpected = list(getattr(res, "unexpected_keys", []))
+    if unexpected:
+        logger.warning("%s: %d unexpected keys in the checkpoint (e.g. %s)", name, len(unexpected), unexpected[0])
+
+
 class WaveVerify:
     """Drop-in for waveverify/core.py:WaveVerify.  `checkpoint` may be a path to an "atomic" .pth
-    (dict with models/{generator,detector,locator} state dicts, parametrizations removed or not;
-    waveverify/core.py:324-408), a directory with generator/detector/locator sub-folders holding
-    model.pth / weights.pth (legacy layout, core.py:428-469), or None for random-init models.
+    (dict with models/{generator,detector,locator} state dicts, parametrizations removed or not, optional 'config';
+    waveverify/core.py:324-408), a directory holding best.pth / latest.pth / any atomic *.pth (core.py:141-168),
+    a directory with generator/detector/locator sub-folders holding model.pth / weights.pth (legacy layout,
+    core.py:428-469), or None for random-init models.  The networks are built from the checkpoint's 'config' when it
+    has one (core.py:230-276), else `bias` / `zero_init` are inferred from the stored keys; explicit *_kwargs win.
     The reference's default "base" checkpoint has no published URL (waveverify/utils.py:45-52)."""
 
     def __init__(self, checkpoint: Optional[Union[str, Path]] = None, device: str = "auto",
@@ -187,36 +257,52 @@ class WaveVerify:
             raise RuntimeError("waveverify_b200.WaveVerify needs a CUDA device (sm_100a); there is no CPU fallback")
         self.sample_rate = DEFAULT_SAMPLE_RATE
         self.watermark_bits = DEFAULT_BITS
-        loc_kw = dict(dimension=64, channels_enc=32, n_residual_enc=1, strides=[8, 4])
-        g = Generator(**(generator_kwargs or {}))
-        d = Detector(**(detector_kwargs or {}))
-        l = Locator(**{**loc_kw, **(locator_kwargs or {})})
-        if checkpoint is not None and str(checkpoint) != "base":
-            self._load_checkpoint(Path(checkpoint), g, d, l)
-        elif str(checkpoint) == "base":
+        if str(checkpoint) == "base":
             raise RuntimeError("the reference publishes no 'base' checkpoint URL (waveverify/utils.py:45-52); "
                                "pass a checkpoint path or None for random-init models")
+        user_kw = {"generator": generator_kwargs or {}, "detector": detector_kwargs or {}, "locator": locator_kwargs or {}}
+        g, d, l = self.build_models(None if checkpoint is None else Path(checkpoint), user_kw)
         self.model = AudioWatermarking(g.to(self.device), d.to(self.device), l.to(self.device)).eval()
 
     @staticmethod
-    def _load_checkpoint(path: Path, g, d, l):
-        if path.is_file():
-            ck = torch.load(str(path), map_location="cpu", weights_only=False)
-            models = ck.get("models", ck)
-            for name, m in (("generator", g), ("detector", d), ("locator", l)):
-                if name not in models:
-                    raise RuntimeError(f"checkpoint {path} has no '{name}' state dict")
-                m.load_state_dict(models[name], strict=False)
-            return
-        for name, m in (("generator", g), ("detector", d), ("locator", l)):
-            for fn in ("model.pth", "weights.pth"):
-                f = path / name / fn
-                if f.exists():
-                    sd = torch.load(str(f), map_location="cpu", weights_only=False)
-                    m.load_state_dict(sd.get("state_dict", sd), strict=True)
-                    break
-            else:
-                raise FileNotFoundError(f"no {name}/model.pth under {path}")
+    def build_models(path: Optional[Path], user_kw: Optional[dict] = None):
+        """Construct Generator / Detector / Locator for a checkpoint (config-driven) and load it.  Host only."""
+        user_kw = user_kw or {}
+        classes = (("generator", Generator, "Generator"), ("detector", Detector, "Detector"), ("locator", Locator, "Locator"))
+        states, config, strict = {}, None, False
+        if path is not None:
+            atomic = find_atomic_checkpoint(path)
+            if atomic is not None:
+                ck = torch.load(str(atomic), map_location="cpu", weights_only=False)
+                models = ck.get("models", ck) if isinstance(ck, dict) else ck
+                config = ck.get("config") if isinstance(ck, dict) else None
+                for name, _, _ in classes:
+                    if name not in models:
+                        raise RuntimeError(f"checkpoint {atomic} has no '{name}' state dict")
+                    states[name] = models[name]
+            else:                                     # legacy: <dir>/<component>/model.pth, strict (core.py:428-469)
+                strict = True
+                for name, _, _ in classes:
+                    for fn in ("model.pth", "weights.pth"):
+                        f = path / name / fn
+                        if f.exists():
+                            sd = torch.load(str(f), map_location="cpu", weights_only=False)
+                            states[name] = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+                            break
+                    else:
+                        raise FileNotFoundError(f"no {name}/model.pth under {path}")
+        out = []
+        for name, cls, cls_name in classes:
+            kw = dict(_LOC_DEFAULT_KW) if name == "locator" else {}
+            if name in states:
+                kw.update(infer_kwargs_from_state_dict(states[name]))
+            kw.update(kwargs_from_checkpoint_config(config, cls_name))
+            kw.update(user_kw.get(name, {}))
+            m = cls(**kw)
+            if name in states:
+                _load_component(m, states[name], name, strict)
+            out.append(m)
+        return tuple(out)
 
     # ---- batched tensor API (new) -------------------------------------------------------------
     @torch.no_grad()

@@ -27,15 +27,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DWV_TIMELINE"] if os.environ.get("WV_TIMELINE_BUILD") else []   # scripts/timeline.py probes
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB, SRC]
+    out = os.environ.get("WV_LIB_OUT") or LIB          # A/B and probe builds go to their own file (loaded via WV_LIB_PATH)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libwv_b200.so")
-    with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
-        f.write(r.stdout + r.stderr)
-    return LIB
+    if out == LIB:
+        with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as f:
+            f.write(r.stdout + r.stderr)
+    return out
 
 
 if __name__ == "__main__":

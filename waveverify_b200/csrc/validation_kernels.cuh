@@ -303,4 +303,49 @@ effect_fir_kernel(const float* __restrict__ in, const float* __restrict__ taps, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Polyphase windowed-sinc resampler = torchaudio.transforms.Resample as the reference's `resample` effect calls it
+// (utils/effect_augmentation.py:1451-1502: down to new_sample_rate and back), and the resampling half of `speed`
+// (:1381-1449: SoX speed + rate, then utils/effect_augmentation.py:187-215 stretches the result back to the input
+// length by linear interpolation).  With orig / new reduced by their gcd and ntaps = 2*width + orig:
+//   y[b, q*new + p] = sum_k h[p][k] * x[b, q*orig + k - width]          (x zero outside [0, T))
+// lerp != 0: out[j] = linear interpolation of y (length T_mid) at PyTorch's align_corners=False source index
+// (src = (j + 0.5) * T_mid / T_out - 0.5, clamped at 0), i.e. the two steps of `speed` in one pass.
+__global__ void __launch_bounds__(256)
+effect_resample_kernel(const float* __restrict__ in, const float* __restrict__ taps, int B, int T, int orig, int nw,
+                       int width, int ntaps, int T_mid, int T_out, int lerp, float* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * T_out;
+  const float scale = static_cast<float>(T_mid) / static_cast<float>(T_out);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx % T_out);
+    const int b = static_cast<int>(idx / T_out);
+    const float* xp = in + static_cast<long long>(b) * T;
+    auto fir = [&](int i) {
+      const int p = i % nw, q = i / nw;
+      const float* h = taps + static_cast<long long>(p) * ntaps;
+      const int t0 = q * orig - width;
+      float acc = 0.f;
+      for (int k = 0; k < ntaps; ++k) {
+        const int t = t0 + k;
+        if (t >= 0 && t < T) acc = fmaf(__ldg(h + k), __ldg(xp + t), acc);
+      }
+      return acc;
+    };
+    float v;
+    if (!lerp) {
+      v = fir(j);
+    } else {
+      float src = (static_cast<float>(j) + 0.5f) * scale - 0.5f;
+      if (src < 0.f) src = 0.f;
+      const int i0 = static_cast<int>(src);
+      const int i1 = i0 + (i0 < T_mid - 1 ? 1 : 0);
+      const float l1 = src - static_cast<float>(i0), l0 = 1.f - l1;
+      v = l0 * fir(i0) + l1 * fir(i1);
+    }
+    out[idx] = v;
+  }
+}
+
 }  // namespace wv

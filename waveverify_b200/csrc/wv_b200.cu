@@ -12,6 +12,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -149,11 +151,14 @@ int g_rb_maxc = 0;     // widest resblock that runs as ONE fused kernel (resbloc
 bool g_pdl = false;  // programmatic dependent launch for every plan kernel (WV_PDL=1 enables; measured
                      // 1-2 % slower on the 64-clip batch, where launch gaps are already hidden)
 thread_local bool g_pm = false;   // weights are being built for a PRECISE net (split-fp16 operands, see gemm_sm100.cuh)
+// Per-device initialisation (kernel attributes belong to the device's context); guarded for concurrent first use.
 void init_device_once() {
-  static bool done = false;
-  if (done) return;
+  static std::mutex mu;
+  static std::set<int> inited;
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   CK(cudaGetDevice(&dev));
+  if (inited.count(dev)) return;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10)
@@ -196,7 +201,7 @@ void init_device_once() {
   if (const char* e = getenv("WV_SERPENTINE")) g_serpentine = atoi(e) != 0;
   if (const char* e = getenv("WV_RB_MAXC")) g_rb_maxc = atoi(e);   // 0 disables the fused resblock kernel
   CK(cudaFuncSetAttribute(conv_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  done = true;
+  inited.insert(dev);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -588,7 +593,10 @@ struct Plan {
   Buf latent;          // h16 [B*F, dim]
   int F = 0;
   std::map<uint32_t, PlanGraph> graphs;   // keyed by the set of non-null I/O pointers
+  std::map<uint32_t, int> graph_seen;     // calls per I/O signature: a graph is captured on the second one
+  unsigned long long stamp = 0;           // last use (LRU eviction of cached plans)
   ~Plan() {
+    for (auto ev : events) cudaEventDestroy(ev);
     for (auto& kv : graphs) {
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
       if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
@@ -937,10 +945,11 @@ struct wv_net {
   bool profile = false;
   const Plan* last_plan = nullptr;   // plan whose events hold the last profiled run
   cudaStream_t cap_stream = nullptr; // capture stream for the small-batch CUDA graphs
+  unsigned long long clock = 0;      // LRU clock of the plan caches
   ~wv_net() {
     if (cap_stream) cudaStreamDestroy(cap_stream);
-    for (auto& kv : plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
-    for (auto& kv : dec_plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
+    plans.clear();
+    dec_plans.clear();
     if (ws) cudaFree(ws);
   }
 };
@@ -1677,8 +1686,7 @@ void build_plan_pass(wv_net& n, Plan& plan, uint8_t* base) {
 void ensure_ws(wv_net& n, size_t bytes) {
   if (bytes <= n.ws_bytes) return;
   n.last_plan = nullptr;
-  for (auto& kv : n.plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
-  for (auto& kv : n.dec_plans) for (auto ev : kv.second->events) cudaEventDestroy(ev);
+  CK(cudaDeviceSynchronize());   // launches of cached plans may still be in flight on the old workspace
   // the workspace moves: every cached plan holds pointers/tensor maps into the old one
   n.plans.clear();
   n.dec_plans.clear();
@@ -1688,11 +1696,30 @@ void ensure_ws(wv_net& n, size_t bytes) {
   n.ws_bytes = bytes;
 }
 
+// The file API and the request batcher feed arbitrary clip lengths: every distinct (B, T) costs a plan (launch list
+// with encoded tensor maps) and, for small calls, CUDA graphs with their own I/O staging.  The caches are bounded:
+// least-recently-used plans beyond MAX_CACHED_PLANS are dropped (the two plans of one sub-batched call are always the
+// most recent ones).
+constexpr size_t MAX_CACHED_PLANS = 24;
+template <typename Map>
+void evict_plans(wv_net& n, Map& plans) {
+  while (plans.size() > MAX_CACHED_PLANS) {
+    auto victim = plans.begin();
+    for (auto it = plans.begin(); it != plans.end(); ++it)
+      if (it->second->stamp < victim->second->stamp) victim = it;
+    if (n.last_plan == victim->second.get()) n.last_plan = nullptr;
+    CK(cudaDeviceSynchronize());   // its graphs / staging buffers may still be in flight
+    plans.erase(victim);
+  }
+}
+
 Plan& get_plan(wv_net& n, int B, int T) {
   auto key = std::make_pair(B, T);
   auto it = n.plans.find(key);
-  if (it != n.plans.end()) return *it->second;
+  if (it != n.plans.end()) { it->second->stamp = ++n.clock; return *it->second; }
+  evict_plans(n, n.plans);
   auto plan = std::make_unique<Plan>();
+  plan->stamp = ++n.clock;
   plan->B = B; plan->T = T;
   build_plan_pass(n, *plan, nullptr);
   ensure_ws(n, plan->ws_bytes);
@@ -1705,7 +1732,8 @@ Plan& get_plan(wv_net& n, int B, int T) {
 Plan& get_dec_plan(wv_net& n, int B, int F) {
   auto key = std::make_pair(B, F);
   auto it = n.dec_plans.find(key);
-  if (it != n.dec_plans.end()) return *it->second;
+  if (it != n.dec_plans.end()) { it->second->stamp = ++n.clock; return *it->second; }
+  evict_plans(n, n.dec_plans);
   auto build = [&](Plan& plan, uint8_t* base) {
     plan.ops.clear();
     PlanCtx c;
@@ -1721,6 +1749,7 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
     plan.ws_bytes = c.arena.high;
   };
   auto plan = std::make_unique<Plan>();
+  plan->stamp = ++n.clock;
   plan->B = B; plan->T = F * n.enc.hop; plan->F = F;
   build(*plan, nullptr);
   ensure_ws(n, plan->ws_bytes);
@@ -1934,7 +1963,7 @@ int wv_net_create(const wv_net_config* cfg, const wv_tensor* tensors, int n_tens
 
 int wv_net_destroy(wv_net* net) {
   if (!net) return WV_OK;
-  cudaSetDevice(net->device);
+  DeviceGuard dg(net->device);   // restores the caller's current device (this runs from Python finalisers)
   cudaDeviceSynchronize();
   delete net;
   return WV_OK;
@@ -1973,6 +2002,13 @@ int wv_net_set_chunk(wv_net* net, int max_clip_samples) {
   return WV_OK;
 }
 
+static uint32_t io_key(const IoPtrs& io) {
+  const void* user[13] = {io.x, io.msg, io.presence, io.wm, io.y, io.latent, io.logits, io.bits, io.avg, io.conf, io.valid, io.mask, io.probs};
+  uint32_t key = 0;
+  for (int i = 0; i < 13; ++i) if (user[i]) key |= 1u << i;
+  return key;
+}
+
 // Run `plan` through a CUDA graph (captured on first use for this set of requested outputs).
 static void run_plan_graph(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st) {
   const int B = plan.B, T = plan.T, nb = n.cfg.nbits;
@@ -2004,6 +2040,8 @@ static void run_plan_graph(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t
       cudaGraph_t dead = nullptr;
       cudaStreamEndCapture(n.cap_stream, &dead);
       if (dead) cudaGraphDestroy(dead);
+      cudaFree(pg.mem);
+      plan.graphs.erase(key);
       throw;
     }
     CK(cudaStreamEndCapture(n.cap_stream, &pg.graph));
@@ -2045,10 +2083,15 @@ static int forward_common(wv_net* net, int B, int T, const IoPtrs& io0, cudaStre
       if (io.presence) io.presence += so;
       if (io.mask) io.mask += so;
       if (io.probs) io.probs += so;
-      if (bn == B && !net->profile && g_graph_max_samples > 0 && static_cast<long long>(B) * T <= g_graph_max_samples)
-        run_plan_graph(*net, plan, io, st);
-      else
-        run_plan(*net, plan, io, st);
+      // small (launch-bound) calls replay a CUDA graph; it is captured the second time a shape + output set is seen,
+      // so one-off clip lengths (file API) do not pay capture + instantiation + staging memory for a single use
+      bool graph = bn == B && !net->profile && g_graph_max_samples > 0 && static_cast<long long>(B) * T <= g_graph_max_samples;
+      if (graph) {
+        const uint32_t key = io_key(io);
+        graph = plan.graphs.count(key) > 0 || ++plan.graph_seen[key] >= 2;
+      }
+      if (graph) run_plan_graph(*net, plan, io, st);
+      else run_plan(*net, plan, io, st);
     }
   });
 }
@@ -2211,6 +2254,22 @@ int wv_effect_fir(const float* in, const float* taps, int n_taps, int B, int T, 
     const long long tiles = static_cast<long long>(B) * ceil_div(T, FIR_TILE);
     const int grid = static_cast<int>(std::min<long long>(tiles, static_cast<long long>(g_num_sms) * 8));
     effect_fir_kernel<<<grid, FIR_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(in, taps, n_taps, B, T, subtract, out);
+    CK(cudaGetLastError());
+  });
+}
+
+int wv_effect_resample(const float* in, const float* taps, int B, int T, int orig, int nw, int width, int T_mid, int T_out,
+                       int lerp, float* out, void* stream) {
+  if (!in || !out || !taps || B < 0 || T <= 0) return fail(WV_ERR_INVALID, "bad resample arguments");
+  if (orig < 1 || nw < 1 || width < 0 || T_mid < 1 || T_out < 1) return fail(WV_ERR_INVALID, "bad resample geometry");
+  if (!lerp && T_out != T_mid) return fail(WV_ERR_INVALID, "T_out must equal T_mid without the interpolation step");
+  if (static_cast<long long>(T_mid) > (static_cast<long long>(T) * nw + orig - 1) / orig)
+    return failf(WV_ERR_INVALID, "T_mid=%d exceeds ceil(T*new/orig)", T_mid);
+  return guarded([&] {
+    init_device_once();
+    if (B == 0) return;
+    effect_resample_kernel<<<elem_grid(static_cast<long long>(B) * T_out), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, taps, B, T, orig, nw, width, 2 * width + orig, T_mid, T_out, lerp, out);
     CK(cudaGetLastError());
   });
 }

@@ -50,5 +50,10 @@ def fold_state_dict(sd: Dict[str, torch.Tensor]) -> "OrderedDict[str, torch.Tens
 
 def unfold_plain_weight(w: torch.Tensor):
     """Plain weight -> (g, v) with g*v/||v|| == w, for loading parametrization-free checkpoints."""
-    g = torch.linalg.vector_norm(w.reshape(w.shape[0], -1), dim=1).reshape(-1, *([1] * (w.dim() - 1)))
-    return g, w.clone()
+    flat = w.reshape(w.shape[0], -1)
+    g = torch.linalg.vector_norm(flat, dim=1).reshape(-1, *([1] * (w.dim() - 1)))
+    v = w.clone()
+    zero = g.reshape(-1) == 0                 # all-zero rows (zero-initialised / pruned channels): g = 0 with a unit-norm v,
+    if bool(zero.any()):                      # so that g * v / ||v|| stays 0 instead of 0 * 0 / 0 = NaN
+        v.reshape(v.shape[0], -1)[zero] = flat.shape[1] ** -0.5
+    return g, v

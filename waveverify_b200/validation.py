@@ -250,7 +250,8 @@ def augment(original: torch.Tensor, watermarked: torch.Tensor, loc: Optional[Loc
 
 # --------------------------------------------------------------------------------------------- effects
 SUPPORTED_EFFECTS = ("identity", "amplitude_scaling", "quantization", "random_noise", "white_noise",
-                     "sample_suppression", "median_filter", "lowpass_filter", "highpass_filter", "bandpass_filter")
+                     "sample_suppression", "median_filter", "lowpass_filter", "highpass_filter", "bandpass_filter",
+                     "resample", "speed")
 EPSILON = 1e-5   # utils/effect_augmentation.py:92
 
 
@@ -278,6 +279,46 @@ def julius_lowpass_taps(cutoffs: Sequence[float], zeros: float = 8) -> torch.Ten
         f = 2 * c * window * sinc
         out.append(f / f.sum())
     return torch.stack(out)
+
+
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """The polyphase filter bank of `torchaudio.transforms.Resample(orig_freq, new_freq)` (sinc_interp_hann, the
+    defaults the reference uses, utils/effect_augmentation.py:1481-1493): restates torchaudio's
+    `_get_sinc_resample_kernel` with the same float64 torch ops, so the fp32 taps are bit-identical to torchaudio's
+    (tests/test_validation_oracle.py checks that when torchaudio is importable).
+    Returns (taps [new, 2*width + orig] fp32, width, orig, new) with the rates divided by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = torch.arange(-width, width + orig, dtype=torch.float64)[None, None] / orig
+    t = torch.arange(0, -new, -1)[:, None, None] / new + idx     # integer arange / int -> float32 phases, as in torchaudio
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0, dtype=torch.float64), t.sin() / t)
+    kernels *= window * scale
+    return kernels.to(torch.float32)[:, 0, :].contiguous(), width, orig, new
+
+
+def _resample(x: torch.Tensor, orig_freq: int, new_freq: int, stretch_to: Optional[int] = None) -> torch.Tensor:
+    """x [B, C, T] -> torchaudio-style resampled [B, C, ceil(T*new/orig)]; stretch_to = L additionally interpolates the
+    result linearly to L samples (the `speed` effect's length restore) in the same kernel."""
+    xin = _need_cuda(x, "audio").float().contiguous()
+    B, Cn, T = xin.shape
+    if orig_freq == new_freq and stretch_to in (None, T):
+        return xin
+    taps, width, orig, new = sinc_resample_kernel(orig_freq, new_freq)
+    T_mid = -(-T * new // orig)
+    T_out = T_mid if stretch_to is None else int(stretch_to)
+    out = torch.empty(B, Cn, T_out, device=xin.device, dtype=torch.float32)
+    h = taps.to(xin.device)
+    _lib.check(_lib.lib().wv_effect_resample(_ptr(xin), _ptr(h), B * Cn, T, orig, new, width, T_mid, T_out,
+                                             0 if stretch_to is None else 1, _ptr(out), _stream(xin.device)),
+               "wv_effect_resample")
+    return out
 
 
 def _fir(x: torch.Tensor, taps: torch.Tensor, subtract: bool) -> torch.Tensor:
@@ -358,6 +399,27 @@ def apply_effect(audio: torch.Tensor, effect_type: str, sample_rate: int = 16000
         _lib.check(_lib.lib().wv_effect_suppress(_ptr(out), _ptr(m), _ptr(idx), B * Cn, T, int(idx.shape[1]),
                                                  _stream(x.device)), "wv_effect_suppress")
         return out, mask
+    if effect_type == "resample":                                           # :1451-1502
+        new_sr = params.get("new_sample_rate")
+        if not isinstance(new_sr, int) or isinstance(new_sr, bool) or new_sr <= 0:
+            raise ValueError(f"new_sample_rate must be positive int, got {new_sr}")
+        # down to new_sample_rate and back up: two torchaudio.transforms.Resample passes (windowed-sinc polyphase)
+        return _resample(_resample(x, sample_rate, new_sr), new_sr, sample_rate), mask
+    if effect_type == "speed":                                              # :1381-1449
+        speed = params.get("speed", 1.0)
+        if isinstance(speed, tuple):
+            import random
+            speed = random.uniform(*speed)
+        if speed <= 0:            # the reference raises inside its try block, logs and returns the input unchanged
+            return audio, mask
+        # SoX `speed s` + `rate sr` = resampling from sr*s to sr (T/s samples), then the reference stretches the result
+        # back to the input length by linear interpolation (mode 'stretch', :187-215); the mask keeps its length.
+        # SoX is a third-party binary absent here (PARITY UNPINNED for its `rate` filter): the resampling step uses the
+        # same windowed-sinc design as torchaudio.transforms.Resample(round(sr*s), sr).
+        src_rate = int(round(sample_rate * float(speed)))
+        if src_rate == sample_rate:
+            return audio, mask
+        return _resample(x, src_rate, sample_rate, stretch_to=x.shape[-1]), mask
     if effect_type in ("lowpass_filter", "highpass_filter"):               # :1684-1770
         # the reference divides by the Nyquist frequency although julius expects cycles per sample: reproduced
         cutoff_freq = float(params.get("cutoff_freq", 3000 if effect_type == "lowpass_filter" else 500))
