@@ -110,6 +110,15 @@ int wv_generator_decode(wv_net* net, const float* z, int B, int F, float* wav_ou
 int wv_detector_forward(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* bits,
                         float* avg, float* conf, uint8_t* valid, const uint8_t* presence,
                         void* stream);
+/* Exact bit decisions without a host round trip (waveverify/core.py:577-586, scripts/evaluate.py:471-494): `net` is the
+ * PRECISE detector net; bits / avg / conf / valid (/ logits) hold the fp16 fast path's results for y and are overwritten
+ * for every clip that has a (valid) bit with |avg - 0.5| < tau (tau_short for clips / masks shorter than short_samples).
+ * Selection, the re-evaluation of the selected clips `slots` at a time and the write-back run inside one CUDA graph with a
+ * device-side WHILE node; counters (device int[2], nullable) += {clips re-evaluated, passes}.  Nothing runs when no clip
+ * is near the threshold. */
+int wv_detector_refine(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* bits, float* avg,
+                       float* conf, uint8_t* valid, const uint8_t* presence, float tau, float tau_short,
+                       int short_samples, int slots, int* counters, void* stream);
 /* y [B,T] fp32.  logits [B,T] fp32 raw, mask [B,T] u8 = (logit > 0.5), probs = sigmoid(logit). */
 int wv_locator_forward(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* mask,
                        float* probs, void* stream);

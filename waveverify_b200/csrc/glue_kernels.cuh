@@ -623,3 +623,125 @@ __global__ void latent_in_kernel(const float* __restrict__ z, act_t* __restrict_
 }
 
 }  // namespace wv
+
+// ---------------------------------------------------------------------------------------------
+// Detector refine (wv_detector_refine): the decoded bits of the fp16 fast path are re-evaluated by the
+// fp32-accurate net for every clip with a bit whose (masked) mean lies within tau of the 0.5 threshold
+// (waveverify/core.py:577-586, scripts/evaluate.py:471-494).  Everything runs on the device inside one CUDA
+// graph: a selection kernel compacts the near clips and sets the condition of a WHILE node whose body
+// (gather K clips -> precise plan -> scatter) runs ceil(count / K) times; no host round trip.
+namespace wv {
+
+struct RefineIo {              // per-call pointers (device block written by refine_params_kernel)
+  const float* y;              // [B, T]
+  const uint8_t* presence;     // [B, T] or null
+  float* logits;               // [B, nbits, T] or null
+  uint8_t* bits;               // [B, nbits]
+  float* avg;                  // [B, nbits]
+  float* conf;                 // [B] or null
+  uint8_t* valid;              // [B, nbits] or null
+  int* counters;               // device int[2]: += {clips re-evaluated, passes of the precise net}, or null
+  float tau, tau_short;
+  int short_samples;
+};
+struct RefineState { int count, it; };
+
+__global__ void refine_params_kernel(RefineIo* dst, RefineIo v) { *dst = v; }
+
+// unmasked samples per clip (masked decode only): the threshold band depends on how many samples the mean averages
+__global__ void __launch_bounds__(256)
+refine_neff_kernel(const RefineIo* __restrict__ io, int T, int* __restrict__ neff) {
+  const uint8_t* p = io->presence + static_cast<long long>(blockIdx.x) * T;
+  int c = 0;
+  for (int t = threadIdx.x; t < T; t += 256) c += __ldcg(p + t) ? 1 : 0;
+  __shared__ int s[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int i = 0; i < 8; ++i) tot += s[i];
+    neff[blockIdx.x] = tot;
+  }
+}
+
+// one warp: ordered list of the clips that need the precise net, their count, the loop condition
+__global__ void __launch_bounds__(32)
+refine_select_kernel(cudaGraphConditionalHandle loop, const RefineIo* __restrict__ io, int B, int nbits, int T,
+                     const int* __restrict__ neff /* null: unmasked */, int* __restrict__ list, RefineState* __restrict__ st) {
+  const int lane = threadIdx.x;
+  const float tau = io->tau, tau_s = io->tau_short;
+  const int short_n = io->short_samples;
+  const float* avg = io->avg;
+  const uint8_t* valid = io->valid;
+  int count = 0;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int b = b0 + lane;
+    bool near = false;
+    if (b < B) {
+      const int n = neff != nullptr ? neff[b] : T;
+      const float tb = n >= short_n ? tau : tau_s;
+      for (int i = 0; i < nbits; ++i) {
+        const bool ok = valid == nullptr || neff == nullptr || valid[b * nbits + i] != 0;
+        near = near || (ok && fabsf(avg[b * nbits + i] - 0.5f) < tb);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, near);
+    if (near) list[count + __popc(m & ((1u << lane) - 1u))] = b;
+    count += __popc(m);
+  }
+  if (lane == 0) {
+    st->count = count;
+    st->it = 0;
+    if (io->counters != nullptr && count > 0) atomicAdd(io->counters, count);
+    cudaGraphSetConditional(loop, count > 0 ? 1u : 0u);
+  }
+}
+
+// slot k of pass `it` <- clip list[it*K + k] (slots past the end repeat the last listed clip: same values, never scattered)
+__global__ void __launch_bounds__(256)
+refine_gather_kernel(const RefineIo* __restrict__ io, const int* __restrict__ list, const RefineState* __restrict__ st,
+                     int K, int T, float* __restrict__ ysub, uint8_t* __restrict__ psub) {
+  const int k = blockIdx.y;
+  const int j = min(st->it * K + k, st->count - 1);
+  const long long src = static_cast<long long>(list[j]) * T, dst = static_cast<long long>(k) * T;
+  const float* y = io->y;
+  const uint8_t* p = io->presence;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < T; t += gridDim.x * 256) {
+    ysub[dst + t] = __ldcg(y + src + t);
+    if (psub != nullptr) psub[dst + t] = p != nullptr ? __ldcg(p + src + t) : 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+refine_scatter_kernel(const RefineIo* __restrict__ io, const int* __restrict__ list, const RefineState* __restrict__ st,
+                      int K, int T, int nbits, const uint8_t* __restrict__ bits_s, const float* __restrict__ avg_s,
+                      const float* __restrict__ conf_s, const uint8_t* __restrict__ valid_s, const float* __restrict__ logits_s) {
+  const int k = blockIdx.y;
+  const int j = st->it * K + k;
+  if (j >= st->count) return;
+  const int b = list[j];
+  if (blockIdx.x == 0 && threadIdx.x < nbits) {
+    const int i = threadIdx.x;
+    io->bits[b * nbits + i] = bits_s[k * nbits + i];
+    io->avg[b * nbits + i] = avg_s[k * nbits + i];
+    if (io->valid != nullptr) io->valid[b * nbits + i] = valid_s[k * nbits + i];
+    if (i == 0 && io->conf != nullptr) io->conf[b] = conf_s[k];
+  }
+  if (io->logits != nullptr && logits_s != nullptr) {
+    const long long n = static_cast<long long>(nbits) * T;
+    float* dst = io->logits + static_cast<long long>(b) * n;
+    const float* src = logits_s + static_cast<long long>(k) * n;
+    for (long long t = blockIdx.x * 256 + threadIdx.x; t < n; t += static_cast<long long>(gridDim.x) * 256) dst[t] = src[t];
+  }
+}
+
+__global__ void refine_advance_kernel(cudaGraphConditionalHandle loop, const RefineIo* __restrict__ io, RefineState* st, int K) {
+  const int it = st->it + 1;
+  st->it = it;
+  if (io->counters != nullptr) atomicAdd(io->counters + 1, 1);
+  cudaGraphSetConditional(loop, it * K < st->count ? 1u : 0u);
+}
+
+}  // namespace wv

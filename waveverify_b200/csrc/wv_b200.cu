@@ -605,6 +605,20 @@ struct Plan {
   }
 };
 
+// Device-side re-evaluation of near-threshold detector clips (wv_detector_refine): one CUDA graph per shape with a WHILE
+// node around {gather K clips, precise plan, scatter}; see glue_kernels.cuh.
+struct RefineGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint8_t* mem = nullptr;
+  RefineIo* io = nullptr;
+  ~RefineGraph() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (mem) cudaFree(mem);
+  }
+};
+
 struct PlanCtx {
   Arena arena;
   uint8_t* base = nullptr;   // nullptr => sizing pass (no tensor maps encoded)
@@ -946,7 +960,9 @@ struct wv_net {
   const Plan* last_plan = nullptr;   // plan whose events hold the last profiled run
   cudaStream_t cap_stream = nullptr; // capture stream for the small-batch CUDA graphs
   unsigned long long clock = 0;      // LRU clock of the plan caches
+  std::map<std::vector<int>, std::unique_ptr<RefineGraph>> refine;   // keyed by (B, T, K, logits, presence)
   ~wv_net() {
+    refine.clear();
     if (cap_stream) cudaStreamDestroy(cap_stream);
     plans.clear();
     dec_plans.clear();
@@ -1690,6 +1706,7 @@ void ensure_ws(wv_net& n, size_t bytes) {
   // the workspace moves: every cached plan holds pointers/tensor maps into the old one
   n.plans.clear();
   n.dec_plans.clear();
+  n.refine.clear();
   if (n.ws) CK(cudaFree(n.ws));
   n.ws = nullptr; n.ws_bytes = 0;
   CK(cudaMalloc(reinterpret_cast<void**>(&n.ws), bytes));
@@ -2139,6 +2156,118 @@ int wv_locator_forward(wv_net* net, const float* y, int B, int T, float* logits,
   IoPtrs io;
   io.x = y; io.logits = logits; io.mask = mask; io.probs = probs;
   return forward_common(net, B, T, io, static_cast<cudaStream_t>(stream));
+}
+
+
+namespace {
+RefineGraph& get_refine(wv_net& n, int B, int T, int K, bool want_logits, bool masked) {
+  const std::vector<int> key = {B, T, K, want_logits ? 1 : 0, masked ? 1 : 0};
+  get_plan(n, K, T);                       // may move the workspace, which drops every cached refine graph
+  auto it = n.refine.find(key);
+  if (it != n.refine.end()) return *it->second;
+  if (n.refine.size() >= MAX_CACHED_PLANS) { CK(cudaDeviceSynchronize()); n.refine.clear(); }
+  Plan& plan = get_plan(n, K, T);
+  auto rg = std::make_unique<RefineGraph>();
+  const int nb = n.cfg.nbits;
+  const size_t KT = static_cast<size_t>(K) * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(std::max<size_t>(bytes, 16), 256); return o; };
+  const size_t o_io = take(sizeof(RefineIo)), o_st = take(sizeof(RefineState)), o_list = take(static_cast<size_t>(B) * 4),
+               o_neff = take(static_cast<size_t>(B) * 4), o_y = take(KT * 4), o_p = take(masked ? KT : 0),
+               o_bits = take(static_cast<size_t>(K) * nb), o_avg = take(static_cast<size_t>(K) * nb * 4), o_conf = take(static_cast<size_t>(K) * 4),
+               o_valid = take(static_cast<size_t>(K) * nb), o_lg = take(want_logits ? KT * nb * 4 : 0);
+  CK(cudaMalloc(reinterpret_cast<void**>(&rg->mem), off));
+  CK(cudaMemset(rg->mem, 0, off));
+  uint8_t* m = rg->mem;
+  rg->io = reinterpret_cast<RefineIo*>(m + o_io);
+  RefineIo* io_d = rg->io;
+  RefineState* st_d = reinterpret_cast<RefineState*>(m + o_st);
+  int* list_d = reinterpret_cast<int*>(m + o_list);
+  int* neff_d = masked ? reinterpret_cast<int*>(m + o_neff) : nullptr;
+  float* ysub = reinterpret_cast<float*>(m + o_y);
+  uint8_t* psub = masked ? m + o_p : nullptr;
+  IoPtrs sub;
+  sub.x = ysub; sub.presence = psub; sub.bits = m + o_bits; sub.avg = reinterpret_cast<float*>(m + o_avg);
+  sub.conf = reinterpret_cast<float*>(m + o_conf); sub.valid = m + o_valid;
+  sub.logits = want_logits ? reinterpret_cast<float*>(m + o_lg) : nullptr;
+
+  CK(cudaGraphCreate(&rg->graph, 0));
+  cudaGraphConditionalHandle loop;
+  CK(cudaGraphConditionalHandleCreate(&loop, rg->graph, 0, cudaGraphCondAssignDefault));
+  std::vector<cudaGraphNode_t> deps;
+  int Bv = B, Tv = T, nbv = nb;
+  if (masked) {
+    cudaKernelNodeParams kp = {};
+    void* args[3] = {&io_d, &Tv, &neff_d};
+    kp.func = reinterpret_cast<void*>(refine_neff_kernel); kp.gridDim = dim3(B); kp.blockDim = dim3(256); kp.kernelParams = args;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddKernelNode(&node, rg->graph, nullptr, 0, &kp));
+    deps.push_back(node);
+  }
+  {
+    cudaKernelNodeParams kp = {};
+    void* args[8] = {&loop, &io_d, &Bv, &nbv, &Tv, &neff_d, &list_d, &st_d};
+    kp.func = reinterpret_cast<void*>(refine_select_kernel); kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.kernelParams = args;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddKernelNode(&node, rg->graph, deps.data(), deps.size(), &kp));
+    deps.assign(1, node);
+  }
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = loop;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t cond;
+  CK(cudaGraphAddNode(&cond, rg->graph, deps.data(), deps.size(), &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  if (!n.cap_stream) CK(cudaStreamCreateWithFlags(&n.cap_stream, cudaStreamNonBlocking));
+  const bool prof = n.profile;
+  n.profile = false;
+  CK(cudaStreamBeginCaptureToGraph(n.cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  try {
+    const dim3 gg(std::max(1, std::min(64, ceil_div(T, 1024))), K);
+    refine_gather_kernel<<<gg, 256, 0, n.cap_stream>>>(io_d, list_d, st_d, K, T, ysub, psub);
+    run_plan(n, plan, sub, n.cap_stream);
+    const dim3 gs(want_logits ? std::max(1, std::min(128, ceil_div(T * nb, 2048))) : 1, K);
+    refine_scatter_kernel<<<gs, 256, 0, n.cap_stream>>>(io_d, list_d, st_d, K, T, nb, sub.bits, sub.avg, sub.conf, sub.valid, sub.logits);
+    refine_advance_kernel<<<1, 1, 0, n.cap_stream>>>(loop, io_d, st_d, K);
+    CK(cudaGetLastError());
+  } catch (...) {
+    cudaGraph_t dead = nullptr;
+    cudaStreamEndCapture(n.cap_stream, &dead);
+    n.profile = prof;
+    throw;
+  }
+  n.profile = prof;
+  cudaGraph_t same = nullptr;
+  CK(cudaStreamEndCapture(n.cap_stream, &same));
+  CK(cudaGraphInstantiate(&rg->exec, rg->graph, 0));
+  RefineGraph& ref = *rg;
+  n.refine[key] = std::move(rg);
+  return ref;
+}
+}  // namespace
+
+int wv_detector_refine(wv_net* net, const float* y, int B, int T, float* logits, uint8_t* bits, float* avg, float* conf,
+                       uint8_t* valid, const uint8_t* presence, float tau, float tau_short, int short_samples, int slots,
+                       int* counters, void* stream) {
+  if (!net || net->cfg.kind != WV_KIND_DETECTOR || !net->cfg.precise) return fail(WV_ERR_INVALID, "refine needs a precise detector net");
+  if (!y || !bits || !avg) return fail(WV_ERR_INVALID, "y, bits and avg are required");
+  if (presence && !valid) return fail(WV_ERR_INVALID, "masked refine needs valid");
+  if (B < 1 || T < 1 || slots < 1) return fail(WV_ERR_INVALID, "bad refine shape");
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    int K = std::min(slots, B);
+    if (net->chunk_samples > 0) K = static_cast<int>(std::max<long long>(1, std::min<long long>(K, net->chunk_samples / std::max(1, T))));
+    RefineGraph& rg = get_refine(*net, B, T, K, logits != nullptr, presence != nullptr);
+    RefineIo v;
+    v.y = y; v.presence = presence; v.logits = logits; v.bits = bits; v.avg = avg; v.conf = conf; v.valid = valid;
+    v.counters = counters; v.tau = tau; v.tau_short = tau_short; v.short_samples = short_samples;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    refine_params_kernel<<<1, 1, 0, st>>>(rg.io, v);
+    CK(cudaGetLastError());
+    CK(cudaGraphLaunch(rg.exec, st));
+  });
 }
 
 int wv_metrics_accumulate(const uint8_t* bits, const uint8_t* valid, const uint8_t* msg_bits, int B, int nbits,

@@ -341,7 +341,17 @@ class Detector(_HeadModel):
         super().__init__(**kwargs)
         self.nbits = self.cfg.nbits
         self.exact_bits = True      # False: fp16 fast path only (bits exact outside a 3e-4 guard band)
-        self.recheck_count = 0      # clips re-evaluated by the precise net so far (diagnostic)
+        self.refine_slots = 0       # clips per pass of the precise net (0 = max(2, B/16))
+        self._refine_counters = None   # device int32[2]: {clips re-evaluated, precise passes} (diagnostic)
+
+    @property
+    def recheck_count(self) -> int:
+        """Clips re-evaluated by the precise net so far (reads a device counter: synchronises)."""
+        return 0 if self._refine_counters is None else int(self._refine_counters[0].item())
+
+    @property
+    def recheck_passes(self) -> int:
+        return 0 if self._refine_counters is None else int(self._refine_counters[1].item())
 
     def preprocess(self, audio_data: torch.Tensor, sample_rate: Optional[int] = None):
         """model/detector.py:222-276."""
@@ -376,6 +386,7 @@ class Detector(_HeadModel):
         The batch runs on the fp16 fast path; with `exact_bits` (default) every clip that has a bit whose mean
         lies within EXACT_TAU of the 0.5 threshold is re-evaluated by the fp32-accurate net and its
         bits / avg / conf / valid (and logits) are replaced, so the decoded bits equal the fp32 reference's.
+        The re-evaluation is enqueued on the stream like everything else (no host synchronisation).
         precise=True runs the whole batch on the fp32-accurate net."""
         x = self._check_audio(audio)
         B, _, T = x.shape
@@ -391,25 +402,16 @@ class Detector(_HeadModel):
         out = self._run(x, pm, want_logits, False)
         if not self.exact_bits:
             return out
-        n_eff = pm.sum(dim=1, dtype=torch.int64) if pm is not None else None
-        if n_eff is None:
-            tau = self.EXACT_TAU if T >= self.EXACT_SHORT_SAMPLES else self.EXACT_TAU_SHORT
-            near = ((out["avg"] - 0.5).abs() < tau).any(dim=1)
-        else:
-            tau = torch.where(n_eff >= self.EXACT_SHORT_SAMPLES, self.EXACT_TAU, self.EXACT_TAU_SHORT).to(torch.float32)
-            near = (((out["avg"] - 0.5).abs() < tau[:, None]) & (out["valid"] != 0)).any(dim=1)
-        idx = near.nonzero().flatten()          # one small device -> host read per call
-        if idx.numel() > 0:
-            self.recheck_count += int(idx.numel())
-            n = int(idx.numel())
-            n_pad = min(B, 1 << (n - 1).bit_length())   # few distinct sub-batch shapes (plans / graphs are cached per shape)
-            if n_pad > n:
-                idx = torch.cat([idx, idx[-1:].expand(n_pad - n)])
-            sub = self._run(x[idx].contiguous(), None if pm is None else pm[idx].contiguous(), want_logits, True)
-            for k in ("bits", "avg", "conf", "valid"):
-                out[k][idx] = sub[k]
-            if want_logits:
-                out["logits"][idx] = sub["logits"]
+        # device-side re-evaluation (no host round trip): selection, the precise net over the selected clips
+        # `slots` at a time and the write-back are one CUDA graph with a WHILE node (wv_detector_refine)
+        slots = self.refine_slots if self.refine_slots > 0 else max(2, -(-B // 16))
+        if self._refine_counters is None or self._refine_counters.device != dev:
+            self._refine_counters = torch.zeros(2, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().wv_detector_refine(
+            self._native(True).handle, _ptr(x), B, T, _ptr(out["logits"]), _ptr(out["bits"]), _ptr(out["avg"]),
+            _ptr(out["conf"]), _ptr(out["valid"]), _ptr(pm), float(self.EXACT_TAU), float(self.EXACT_TAU_SHORT),
+            int(self.EXACT_SHORT_SAMPLES), int(min(slots, B)), _ptr(self._refine_counters), _stream(dev)),
+            "wv_detector_refine")
         return out
 
     def decode(self, audio_data: torch.Tensor, orig_nframes: int) -> torch.Tensor:
