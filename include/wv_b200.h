@@ -184,9 +184,10 @@ int wv_op_gemm_dw5(const void* A, const void* W, int B, int T, int N, int K, con
                    const float* bias, const void* residual, void* out_raw, void* out_act,
                    float act_scale, void* stream);
 /* One fused SEANet residual block (modules/seanet.py:245-281), C <= 128, C % 32 == 0:
- * x' = dw5(W2 ELU(dw5(W1 ELU(X*pre_scale)) + b1)) + b2 + X ; out_raw = x', out_act = ELU(x'*act_scale).
- * X, out_* are [B,T,C] fp16; W1, W2 [C,C] fp16; taps [5][C], biases [C] fp32 (RS folded into dw2). */
-int wv_op_resblock(const void* X, const void* W1, const float* dw1_w5c, const float* dw1_b,
+ * x' = dw5(W2 ELU(dw5(W1 A) + b1)) + b2 + X ; out_raw = x', out_act = ELU(x'*act_scale), with A = ELU(X*pre_scale) as the
+ * producing launch stores it.  X, A, out_* are [B,T,C] fp16; W1, W2 [C,C] fp16; taps [5][C], biases [C] fp32 (RS folded
+ * into dw2). */
+int wv_op_resblock(const void* X, const void* A, const void* W1, const float* dw1_w5c, const float* dw1_b,
                    const void* W2, const float* dw2_w5c, const float* dw2_b, int B, int T, int C,
                    float pre_scale, void* out_raw, void* out_act, float act_scale, void* stream);
 int wv_op_dw5(const void* in, const float* w5c, const float* bias, const void* residual,

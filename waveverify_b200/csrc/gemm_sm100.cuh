@@ -1225,7 +1225,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         } else if constexpr (EPI == EPI_STFT_PM) {
-          // precise log-magnitude (logf, not MUFU.LG2) -> split pairs [hi | lo]
+          // log-magnitude -> split pairs [hi | lo].  __logf = MUFU.LG2 * ln 2: absolute error ~1e-7 on ln, i.e. 2e-8 on the
+          // normalised value (an fp32 rounding of an O(1) quantity is 6e-8); the libdevice logf cost ~20 instructions per bin
+          // and made this epilogue the bound of the precise STFT launches
           for (int c = h; c < chunks; c += split) {
             const int p0 = (n0 + c * 32) >> 1;
             tmem_ld32(taddr + c * 32, v);
@@ -1235,13 +1237,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float re = __uint_as_float(v[2 * i]), im = __uint_as_float(v[2 * i + 1]);
-                y[i] = (0.5f * logf(fmaxf(re * re + im * im, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                y[i] = (0.5f * __logf(fmaxf(re * re + im * im, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
               }
               act_t* yp = g.out_raw + m * g.ldo;
               if (p0 == 0) {
                 const float re0 = __uint_as_float(v[0]), ren = __uint_as_float(v[1]);
-                y[0] = (0.5f * logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
-                const float yn = (0.5f * logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                y[0] = (0.5f * __logf(fmaxf(re0 * re0, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
+                const float yn = (0.5f * __logf(fmaxf(ren * ren, g.clamp_sq)) - g.log_offset) * g.inv_sigma;
                 uint32_t hn, ln;
                 split2(yn, 0.f, hn, ln);   // bin N/2 + 7 zero pad columns (row half-width = n_half + 8)
                 *reinterpret_cast<uint4*>(yp + g.n_half) = make_uint4(hn, 0u, 0u, 0u);

@@ -241,20 +241,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   unpack_act2(hi, ha, hb);
   lo = pack_act2(a - ha, b - hb);
 }
-// fp32-accurate ELU without the libdevice expm1f call (~25 instructions): e^x - 1 by MUFU.EX2 (2 ulp of e^x) away from zero,
-// a degree-6 Taylor polynomial on (-0.25, 0] where the subtraction would cancel (x^7/5040 < 1.3e-8 relative to |x|).
-__device__ __forceinline__ float elu_precise(float x) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-  float p = fmaf(x, 1.f / 720.f, 1.f / 120.f);
-  p = fmaf(p, x, 1.f / 24.f);
-  p = fmaf(p, x, 1.f / 6.f);
-  p = fmaf(p, x, 0.5f);
-  p = fmaf(p, x, 1.f);
-  p *= x;
-  const float neg = x > -0.25f ? p : e - 1.f;
-  return x > 0.f ? x : neg;
-}
+// ELU for the fp32-accurate nets: e^x - 1 by MUFU.EX2 (2 ulp of e^x, i.e. <= 2.4e-7 ABSOLUTE on the (-1, 0] branch - the
+// size of two fp32 roundings of an O(1) activation; the libdevice expm1f call it replaces costs ~25 instructions per
+// element and made the precise launches issue-bound).  The identity branch is exact.
+__device__ __forceinline__ float elu_precise(float x) { return elu1(x); }
 // split store of 4 consecutive channels: hi at p, lo at p + lo_off (elements)
 __device__ __forceinline__ void st_split4(act_t* p, int lo_off, float a, float b, float c, float d) {
   uint32_t h0, l0, h1, l1;

@@ -1,10 +1,12 @@
 // Fused SEANet residual block for sm_100a (modules/seanet.py:245-281):
-//   a  = ELU(x * pre_scale)                      (computed in shared memory, never stored)
+//   a  = ELU(x * pre_scale)                      (the activated stream the producing launch already wrote: TMA operand)
 //   h  = ELU(dw5(W1 a) + b1)                     (stays in shared memory as the second GEMM's operand)
-//   x' = RS * (dw5(W2 h) + b2) + x               (RS folded into the taps / bias)
+//   x' = RS * (dw5(W2 h) + b2) + x               (RS folded into the taps / bias; x = the raw stream)
 //   out_raw = x' ;  out_act = ELU(x' * act_scale)        (each optional)
-// HBM traffic: read x once, write the requested outputs once: 2C bytes per element and resblock
+// HBM traffic: read a and x once, write the requested outputs once: 4C bytes per element and resblock
 // instead of the 6C of the two-launch form (h1: read a, write h; out: read h and x, write x' and a').
+// (Round 1 activated x in shared memory instead of reading a - 2C bytes - but that extra pass over the
+// tile made the math warps, not HBM, the bound: 290 us against 236 us for the two launches at C = 96.)
 //
 // One persistent 640-thread CTA per SM; channels-last fp16 [clip, time, C] with C <= 128.  A tile is
 // 128 time rows of one clip starting 8 rows before its first output row (two causal k=5 halos):
@@ -16,12 +18,11 @@
 //   warp 1       MMA issuer:   MMA1(a) MMA1(b) MMA2(a) MMA2(b) per pair; accumulators in TMEM
 //                (one 256-column slot per tile of the pair, reused by both GEMMs of the tile)
 //   warps 4-7    drain:        TMEM -> saturating fp16 -> staging tile of the slot
-//   warps 8-19   math:         T0: x tile -> ELU(x * pre_scale) in place (elementwise on the swizzled
-//                              bytes);  M1: taps + bias + ELU on the staged GEMM1 tile, written back
-//                              into the x buffer in the SWIZZLE_128B operand layout (rows before the
-//                              clip start as zeros = the causal padding of the second depthwise
-//                              conv);  M2: taps + bias + residual (x re-read through L2, which still
-//                              holds the tile) + ELU -> global
+//   warps 8-19   math:         M1: taps + bias + ELU on the staged GEMM1 tile, written back into the
+//                              operand buffer in the SWIZZLE_128B layout (rows before the clip start
+//                              as zeros = the causal padding of the second depthwise conv);
+//                              M2: taps + bias + residual + ELU -> global; the residual rows of a
+//                              thread's first two units are requested before the hand-off barrier
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -124,28 +125,41 @@ __device__ __forceinline__ void rb_unit_m1(uint32_t srow, int pitch, uint32_t xa
   }
 }
 
-template <bool RAW, bool ACT>
-__device__ __forceinline__ void rb_m2_tile(const ResblockArgs& g, const GemmArgs& gf, uint32_t tile_u32, int pitch, int cg,
-                                           int grp0, int gstride, bool active, size_t base, int rows_left,
-                                           const __half2 (&wt)[5][2], const __half2 (&bs)[2], uint2 (&rres)[4]) {
+// M2 over one tile.  A thread owns up to three 4-row units (row groups grp0, grp0 + gstride, grp0 + 2 gstride); the
+// residual rows of the first two arrive in r0 / r1 (requested before the hand-off barrier), those of a third unit are
+// requested while the first is being computed.
+__device__ __forceinline__ void rb_load_res(const ResblockArgs& g, size_t base, int oo, int rows_left, uint2 (&r)[4]) {
+  const char* rp = reinterpret_cast<const char*>(g.x + base + static_cast<size_t>(oo) * g.C);
   const size_t row_bytes = static_cast<size_t>(g.C) * 2;
-  if (!active) return;
-  for (int grp = grp0; grp < RB_ROWS_OUT / 4; grp += gstride) {
-    const int oo = grp * 4;                       // output row relative to the tile's first output row
-    if (oo >= rows_left) break;
-    const size_t off = base + static_cast<size_t>(oo) * g.C;
-    {   // the residual rows were read by this tile's TMA load a moment ago: L2 hits
-      const char* rp = reinterpret_cast<const char*>(g.x + off);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        rres[i] = oo + i < rows_left ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
-    }
-    const uint32_t srow = tile_u32 + static_cast<uint32_t>(oo + 4) * pitch;   // staged rows oo+4 .. oo+11
-    if (oo + 4 <= rows_left)
-      staged_unit<5, 4, true, RAW, ACT, true, true>(gf, srow, pitch, off, row_bytes, 4, wt, bs, g.act_scale, rres);
-    else
-      staged_unit<5, 4, true, RAW, ACT, false, true>(gf, srow, pitch, off, row_bytes, rows_left - oo, wt, bs, g.act_scale, rres);
-  }
+  for (int i = 0; i < 4; ++i)
+    r[i] = oo + i < rows_left ? __ldcg(reinterpret_cast<const uint2*>(rp + i * row_bytes)) : make_uint2(0u, 0u);
+}
+template <bool RAW, bool ACT>
+__device__ __forceinline__ void rb_m2_unit(const ResblockArgs& g, const GemmArgs& gf, uint32_t tile_u32, int pitch, size_t base,
+                                           int oo, int rows_left, const __half2 (&wt)[5][2], const __half2 (&bs)[2],
+                                           const uint2 (&rres)[4]) {
+  const size_t row_bytes = static_cast<size_t>(g.C) * 2;
+  const size_t off = base + static_cast<size_t>(oo) * g.C;
+  const uint32_t srow = tile_u32 + static_cast<uint32_t>(oo + 4) * pitch;   // staged rows oo+4 .. oo+11
+  if (oo + 4 <= rows_left)
+    staged_unit<5, 4, true, RAW, ACT, true, true>(gf, srow, pitch, off, row_bytes, 4, wt, bs, g.act_scale, rres);
+  else
+    staged_unit<5, 4, true, RAW, ACT, false, true>(gf, srow, pitch, off, row_bytes, rows_left - oo, wt, bs, g.act_scale, rres);
+}
+template <bool RAW, bool ACT>
+__device__ __forceinline__ void rb_m2_tile(const ResblockArgs& g, const GemmArgs& gf, uint32_t tile_u32, int pitch,
+                                           int grp0, int gstride, bool active, size_t base, int rows_left,
+                                           const __half2 (&wt)[5][2], const __half2 (&bs)[2], uint2 (&r0)[4], uint2 (&r1)[4]) {
+  if (!active) return;
+  constexpr int NG = RB_ROWS_OUT / 4;
+  const int o0 = grp0 * 4, o1 = (grp0 + gstride) * 4, o2 = (grp0 + 2 * gstride) * 4;
+  const bool h0 = grp0 < NG && o0 < rows_left, h1 = grp0 + gstride < NG && o1 < rows_left, h2 = grp0 + 2 * gstride < NG && o2 < rows_left;
+  if (!h0) return;
+  rb_m2_unit<RAW, ACT>(g, gf, tile_u32, pitch, base, o0, rows_left, wt, bs, r0);
+  if (h2) rb_load_res(g, base, o2, rows_left, r0);
+  if (h1) rb_m2_unit<RAW, ACT>(g, gf, tile_u32, pitch, base, o1, rows_left, wt, bs, r1);
+  if (h2) rb_m2_unit<RAW, ACT>(g, gf, tile_u32, pitch, base, o2, rows_left, wt, bs, r0);
 }
 
 __global__ void __launch_bounds__(RB_THREADS, 1)
@@ -216,6 +230,7 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     else fast_divmod(tile, static_cast<uint32_t>(g.tiles_m_per_clip), g.magic_m, clip, mi);
   };
 
+  if (warp < 4) reg_dealloc<REGS_LIGHT>();           // same split as the GEMM: TMA / MMA warpgroup 40, drain 96, math 112
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -252,7 +267,7 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t pph = static_cast<uint32_t>(pair) & 1u;
         for (int s = 0; s < nb; ++s) {
           mbar_wait(&tm_empty[s], pph ^ 1);          // TMEM slot drained (second GEMM of the previous pair)
-          mbar_wait(&t0_done[s], pph);               // x tile landed and activated in place
+          mbar_wait(&x_full[(it + s) % g.nx], static_cast<uint32_t>((it + s) / g.nx) & 1u);   // activated tile landed
           tc_fence_after();
           RB_DBG(0 + s, pair);
           issue(xa + ((it + s) % g.nx) * xt_bytes, w1, tmem_base + static_cast<uint32_t>(s * RB_SLOT_COLS));
@@ -314,6 +329,7 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
   } else if (warp >= 4 + P1_WARPS) {
     // ------------------------------------------------------------ math warps
+    reg_alloc<REGS_MATH>();
     const int et = threadIdx.x - (128 + P1_WARPS * 32);
     const int cgs = g.C >> 2;
     const int gstride = RB_MATH_THREADS / cgs;
@@ -334,27 +350,8 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     };
     GemmArgs gf = {};                                // the output pointers staged_unit reads
     gf.residual = g.x; gf.out_raw = g.out_raw; gf.out_act = g.out_act;
-    const __half2 ps2 = h2_from(g.pre_scale, g.pre_scale);
-    const int n_chunks = xt_bytes >> 4;              // 16-byte chunks of an x tile
     for (int it = 0, pair = 0; it < my_tiles; it += 2, ++pair) {
       const int nb = my_tiles - it < 2 ? my_tiles - it : 2;
-      // ---- T0: a = ELU(x * pre_scale) in place (elementwise: independent of the swizzle)
-      for (int s = 0; s < nb; ++s) {
-        const int buf = (it + s) % g.nx;
-        if (et == 0) RB_DBG(12 + s, pair);
-        mbar_wait(&x_full[buf], static_cast<uint32_t>((it + s) / g.nx) & 1u);
-        if (et == 0) RB_DBG(14 + s, pair);
-        const uint32_t tile = xa_u32 + buf * xt_bytes;
-        for (int i = et; i < n_chunks; i += RB_MATH_THREADS) {
-          const uint4 u = lds_u4(tile + i * 16);
-          sts_u4(tile + i * 16, as_u32(elu_h2(__hmul2(as_h2(u.x), ps2))), as_u32(elu_h2(__hmul2(as_h2(u.y), ps2))),
-                 as_u32(elu_h2(__hmul2(as_h2(u.z), ps2))), as_u32(elu_h2(__hmul2(as_h2(u.w), ps2))));
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t0_done[s]);
-        if (et == 0) RB_DBG(16 + s, pair);
-      }
       // ---- M1: h = ELU(dw5(S1) + b1) -> operand layout in the x buffer
       for (int s = 0; s < nb; ++s) {
         int clip, mi;
@@ -382,18 +379,22 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const int r_base = mi * RB_ROWS_OUT;
         const int rows_left = min(g.T - r_base, RB_ROWS_OUT);
         const size_t base = (static_cast<size_t>(clip) * g.T + r_base) * g.C + c;
+        uint2 r0[4], r1[4];
+        if (active) {                                // residual rows do not depend on the staged tile: in flight across the wait
+          if (grp0 * 4 < rows_left) rb_load_res(g, base, grp0 * 4, rows_left, r0);
+          if (grp0 + gstride < RB_ROWS_OUT / 4 && (grp0 + gstride) * 4 < rows_left) rb_load_res(g, base, (grp0 + gstride) * 4, rows_left, r1);
+        }
         named_bar_sync(BAR_RB_FULL + s, RB_EPI_THREADS);
         if (et == 0) RB_DBG(22 + s, pair);
         const uint32_t tile_u32 = stage_u32 + s * (BM * pitch);
         __half2 wt2[5][2], bs2[2];
-        uint2 rres[4];
         if (active) load_taps(1, wt2, bs2);
         if (g.out_raw != nullptr && g.out_act != nullptr)
-          rb_m2_tile<true, true>(g, gf, tile_u32, pitch, cg, grp0, gstride, active, base, rows_left, wt2, bs2, rres);
+          rb_m2_tile<true, true>(g, gf, tile_u32, pitch, grp0, gstride, active, base, rows_left, wt2, bs2, r0, r1);
         else if (g.out_raw != nullptr)
-          rb_m2_tile<true, false>(g, gf, tile_u32, pitch, cg, grp0, gstride, active, base, rows_left, wt2, bs2, rres);
+          rb_m2_tile<true, false>(g, gf, tile_u32, pitch, grp0, gstride, active, base, rows_left, wt2, bs2, r0, r1);
         else
-          rb_m2_tile<false, true>(g, gf, tile_u32, pitch, cg, grp0, gstride, active, base, rows_left, wt2, bs2, rres);
+          rb_m2_tile<false, true>(g, gf, tile_u32, pitch, grp0, gstride, active, base, rows_left, wt2, bs2, r0, r1);
         __syncwarp();
         if (et == 0) RB_DBG(24 + s, pair);
         if (it + 2 + s < my_tiles) named_bar_arrive(BAR_RB_EMPTY + s, RB_EPI_THREADS);   // staging[s] free for the next pair

@@ -125,7 +125,8 @@ int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
 }
 
 int g_num_sms = 0;
-long long g_graph_max_samples = 32 * 16000;   // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off)
+long long g_graph_max_samples = 128 * 16000;  // calls of up to this many samples run as one CUDA graph (WV_GRAPH_MAX_SAMPLES, 0 = off);
+                                               // measured r02 on the 64 x 1 s step: +1.5 % (launch gaps), I/O staging copies included
 int g_ldy_align = 8;        // log-spectrogram row pitch in elements (WV_LDY_ALIGN: 8 = 16 B, 16 = 32 B = one DRAM sector per chunk)
 unsigned g_rows6_mask = (1u << (64 / 32)) | (1u << (128 / 32));   // STAGED tiles of these widths (bit = channels / 32) use 6-row math units:
                             // 4-row groups leave their last pass mostly idle there (WV_ROWS6_BN = comma list of widths, 0 = off)
@@ -871,8 +872,9 @@ bool resblock_fusable(const ResW& r, int C) {
          rb_pick_nx(C, ceil_div(C, BK)) >= 2;
 }
 
-// One residual block as ONE launch (resblock_sm100.cuh): reads the raw stream X only.
-void add_resblock_fused(PlanCtx& c, const ResW& r, const h16* X, int T, int C, h16* out_raw, h16* out_act,
+// One residual block as ONE launch (resblock_sm100.cuh): reads the activated stream A (GEMM operand) and the raw stream X
+// (residual): 4C bytes per element instead of the 6C of the two-launch form.
+void add_resblock_fused(PlanCtx& c, const ResW& r, const h16* X, const h16* A, int T, int C, h16* out_raw, h16* out_act,
                         float act_scale, const std::string& name) {
   Op op;
   op.type = OP_RESBLOCK;
@@ -890,7 +892,7 @@ void add_resblock_fused(PlanCtx& c, const ResW& r, const h16* X, int T, int C, h
   g.pre_scale = r.pre_scale;
   g.dw1_w = r.dw1.w; g.dw1_b = r.dw1.bias; g.dw2_w = r.dw2.w; g.dw2_b = r.dw2.bias;
   g.x = X; g.out_raw = out_raw; g.out_act = out_act; g.act_scale = act_scale;
-  if (!c.dry()) op.tmA = make_tmap(X, 3, C, T, c.B, C, static_cast<uint64_t>(C) * T, BK, BM, true);
+  if (!c.dry()) op.tmA = make_tmap(A, 3, C, T, c.B, C, static_cast<uint64_t>(C) * T, BK, BM, true);
   op.tmB = r.pw1.tm;
   op.tmR = r.pw2.tm;
   op.grid = std::min(g.num_tiles, g_num_sms);
@@ -898,7 +900,7 @@ void add_resblock_fused(PlanCtx& c, const ResW& r, const h16* X, int T, int C, h
   op.out0 = out_raw; op.out1 = out_act;
   const double n = static_cast<double>(c.B) * T;
   op.flops = n * C * (4.0 * C + 20.0);
-  op.bytes = n * C * 2.0 * (1 + (out_raw ? 1 : 0) + (out_act ? 1 : 0)) + 4.0 * C * C;
+  op.bytes = n * C * 2.0 * (2 + (out_raw ? 1 : 0) + (out_act ? 1 : 0)) + 4.0 * C * C;
   op.out_bytes[0] = out_raw ? static_cast<size_t>(n) * C * 2 : 0;
   op.out_bytes[1] = out_act ? static_cast<size_t>(n) * C * 2 : 0;
   c.tag(name + ".fused");
@@ -911,13 +913,13 @@ void plan_resblock(PlanCtx& c, const ResW& r, Buf& X, Buf& A, int T, int C, bool
                    float next_act_scale, Buf& Xn, Buf& An, const std::string& name, const DwW* pre = nullptr) {
   const long long M = static_cast<long long>(c.B) * T;
   const size_t bytes = static_cast<size_t>(M) * C * 2;
-  if (resblock_fusable(r, C)) {   // the fused kernel activates X itself: A (if the producer made one) is not read
-    if (A.valid) c.release(A);
+  if (resblock_fusable(r, C) && pre == nullptr && A.valid && X.valid) {
     Xn = Buf(); An = Buf();
     if (need_raw) Xn = c.alloc(bytes);
     if (need_act) An = c.alloc(bytes);
-    add_resblock_fused(c, r, c.ptr<h16>(X), T, C, need_raw ? c.ptr<h16>(Xn) : nullptr, need_act ? c.ptr<h16>(An) : nullptr,
-                       next_act_scale, name);
+    add_resblock_fused(c, r, c.ptr<h16>(X), c.ptr<h16>(A), T, C, need_raw ? c.ptr<h16>(Xn) : nullptr,
+                       need_act ? c.ptr<h16>(An) : nullptr, next_act_scale, name);
+    c.release(A);
     c.release(X);
     return;
   }
@@ -2540,9 +2542,10 @@ int wv_op_gemm_dw5(const void* A, const void* Wt, int B, int T, int N, int K, co
   });
 }
 
-int wv_op_resblock(const void* X, const void* W1, const float* dw1_w5c, const float* dw1_b, const void* W2,
+int wv_op_resblock(const void* X, const void* A, const void* W1, const float* dw1_w5c, const float* dw1_b, const void* W2,
                    const float* dw2_w5c, const float* dw2_b, int B, int T, int C, float pre_scale, void* out_raw,
                    void* out_act, float act_scale, void* stream) {
+  if (!X || !A) return fail(WV_ERR_INVALID, "X (raw) and A = ELU(X * pre_scale) are required");
   return guarded([&] {
     init_device_once();
     ResW r;
@@ -2562,7 +2565,7 @@ int wv_op_resblock(const void* X, const void* W1, const float* dw1_w5c, const fl
     c.base = reinterpret_cast<uint8_t*>(16);
     c.ops = &ops;
     c.B = B;
-    add_resblock_fused(c, r, static_cast<const h16*>(X), T, C, static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale, "op");
+    add_resblock_fused(c, r, static_cast<const h16*>(X), static_cast<const h16*>(A), T, C, static_cast<h16*>(out_raw), static_cast<h16*>(out_act), act_scale, "op");
     long long* dbg = nullptr;
     if (getenv("WV_TIMELINE_RB")) {
       CK(cudaMalloc(&dbg, 24 * 32 * sizeof(long long)));
