@@ -27,7 +27,7 @@ def timeit(fn, reps=10):
     return min(ts) * 1e3
 
 
-for (B, T, Cc) in [(64, 16000, 64), (64, 16000, 96), (64, 8000, 128), (64, 8000, 192), (64, 2000, 256), (64, 2000, 384), (64, 400, 768)]:
+for (B, T, Cc) in [(64, 16000, 64), (64, 16000, 96), (64, 8000, 128), (64, 8000, 192), (64, 2000, 256), (64, 2000, 384), (64, 400, 512), (64, 400, 768)]:
     A = torch.randn(B, T, Cc, device=dev).to(torch.float16)
     W = (torch.randn(Cc, Cc, device=dev) / Cc ** 0.5).to(torch.float16)
     dw = torch.randn(5, Cc, device=dev) * 0.3

@@ -47,6 +47,11 @@ GEMM_CASES = [
     (333, 768, 1536, True, False, False),       # long K
     (64000, 192, 192, False, True, True),       # many M tiles per CTA (persistent loop, both TMEM stages)
     (40000, 384, 384, False, False, True),
+    # CTA-pair mode (cluster of 2, tcgen05 cta_group::2): K >= 256, an even number of n tiles, enough tile pairs
+    (64000, 256, 256, True, True, True),        # one wide n tile
+    (40000, 512, 512, False, True, True),       # two wide n tiles, odd number of M tiles (the last one is computed twice)
+    (30000, 768, 768, True, False, True),       # three wide n tiles
+    (25600, 1024, 512, False, False, True),
 ]
 
 
@@ -181,7 +186,8 @@ def test_up_conv_transposed(B, Tin, C, r):
 
 
 @pytest.mark.parametrize("B,T,N,K", [(2, 1000, 64, 64), (1, 50, 1536, 128), (3, 401, 96, 96), (2, 124, 256, 256),
-                                     (1, 125, 192, 192), (2, 4097, 384, 384), (1, 3, 32, 32), (1, 16000, 128, 128)])
+                                     (1, 125, 192, 192), (2, 4097, 384, 384), (1, 3, 32, 32), (1, 16000, 128, 128),
+                                     (32, 2000, 256, 256), (33, 401, 512, 512), (64, 400, 768, 768)])   # CTA-pair mode
 @pytest.mark.parametrize("mode", ["act", "res_both"])
 def test_gemm_with_fused_depthwise_epilogue(B, T, N, K, mode):
     """1x1 conv -> causal depthwise k=5 (+bias, +residual) -> raw / ELU outputs in ONE kernel;

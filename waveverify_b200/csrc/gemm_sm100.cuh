@@ -69,7 +69,7 @@ constexpr int BAR_ST_FULL = 2;             // 2,3 = staging tile written (drain 
 constexpr int BAR_ST_EMPTY = 4;            // 4,5 = staging tile consumed (math arrive, drain sync)
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 512;
-constexpr int DOWN_W_BYTES = 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [2r <= 16][block_n] fp16
+constexpr int DOWN_W_BYTES = 2 * 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [half][2r <= 16][block_n] fp16 (CTA-pair mode: both halves of the wide n tile)
 
 // Epilogues 4..6 are the PRECISE variants (fp32-accurate path for the thresholded outputs, see the
 // "precise mode" block below): split-fp16 operands (hi + lo) on the tensor cores, fp32 epilogue math.
@@ -87,6 +87,12 @@ struct GemmArgs {
   int stage_bufs;     // STAGED: staging tiles (2; 1 for long-K layers, whose ring gets the space instead)
   int pair;           // 1: two M tiles (same n tile) share every W k-block: one ring stage = 2 A tiles + 1 W tile,
                       //    four 128-column accumulator stages (long-K layers are bound by L2 -> SM operand traffic)
+  int cg2;            // 1: CTA-pair mode (cluster of 2, tcgen05 cta_group::2): one MMA of M = 256 covers the M tiles of both CTAs
+                      //    and 2 * block_n columns; each CTA loads its own A tile and HALF of the W k-block (block_n rows), so a
+                      //    128 x 128 x 64 block of MACs costs 16 KB of L2 -> SM operand traffic instead of 32 KB (24 KB in pair
+                      //    mode).  The 2 * block_n accumulator columns are drained as two block_n-wide tiles.
+  uint32_t idesc2;    //    instruction descriptor of that MMA (M = 256, N = 2 * block_n)
+  uint32_t magic_n2;  //    floor(2^32 / (tiles_n / 2))
   int acc_stages, acc_cols;
   int kb_split;       // > 0: k-blocks >= kb_split re-read the A rows shifted by one (row r-1) at k - kb_split*64:
                       //      [a[i] | a[i-1]] contraction of the fused transposed-conv + 1x1 (decoder upsample)
@@ -234,6 +240,23 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
 // M tiles the second half of the last units does not exist.  With g.reverse the order is walked from the end,
 // so that a kernel starts on the rows the previous kernel of the plan wrote last (still in L2).
 __device__ __forceinline__ int seq_tile(const GemmArgs& g, int k, bool& done) {
+  if (g.cg2) {
+    // CTA-pair mode: cluster c = blockIdx.x / 2 walks UNITS u = c + (k>>1) * clusters = (M tile pair mp, wide n tile nw);
+    // the CTA of rank r owns M tile 2*mp + r (the last one twice when the count is odd: both CTAs then write the same values)
+    // and visits the two block_n-wide halves of the wide n tile in turn: every unit is exactly two tiles of this CTA.
+    const int tiles_m = g.tiles_m_per_clip * g.n_clips;
+    const int ntw = g.tiles_n >> 1;
+    const int num_units = ((tiles_m + 1) >> 1) * ntw;
+    int u = static_cast<int>(blockIdx.x >> 1) + (k >> 1) * static_cast<int>(gridDim.x >> 1);
+    done = u >= num_units;
+    if (done) return -1;
+    if (g.reverse) u = num_units - 1 - u;
+    int mp, nw;
+    if (ntw == 1) { mp = u; nw = 0; }
+    else fast_divmod(static_cast<uint32_t>(u), static_cast<uint32_t>(ntw), g.magic_n2, mp, nw);
+    const int mt = min(2 * mp + static_cast<int>(blockIdx.x & 1), tiles_m - 1);
+    return mt * g.tiles_n + 2 * nw + (k & 1);
+  }
   if (!g.pair) {
     const int l = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
     done = l >= g.num_tiles;
@@ -519,24 +542,35 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   const uint32_t stage_u32 = smem_u32(stage_tiles) + cg * 8;
   const uint32_t w_u32 = smem_u32(down_w) + cg * 8;              // taps staged as fp16 [2R][block_n]
   const int band_w = g.film != nullptr ? g.N / g.film_bands : 1;
-  int cached_nt = -1;
+  int cached_nt = -1, cached_half = -1;
   __half2 bs2[2];
   const __half2 s2 = h2_from(s_act, s_act);
   int sb = 0;
   int tiles_left = cta_tile_count(g);
   for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int c = tc.nt * g.block_n + cg * 4;
-    if (tc.nt != cached_nt) {                                      // (re)stage taps for this N tile
-      cached_nt = tc.nt;
+    // taps are staged per n tile; CTA-pair mode alternates between the two halves of a wide n tile, so both halves are
+    // staged together (keyed by the wide tile) and the bias is re-read (L1) when the half changes
+    const int tap_key = g.cg2 ? (tc.nt >> 1) : tc.nt;
+    const int half = g.cg2 ? (tc.nt & 1) : 0;
+    if (tap_key != cached_nt) {
+      cached_nt = tap_key;
       named_bar_sync(BAR_TAPS, P2_THREADS);                           // previous taps no longer read
-      for (int i = et; i < 2 * R * cgs; i += P2_THREADS) {
-        const int j = i / cgs, q = i % cgs;
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + tc.nt * g.block_n + q * 4));
+      const int n_half = g.cg2 ? 2 : 1;
+      const int nt0 = g.cg2 ? (tc.nt & ~1) : tc.nt;
+      for (int i = et; i < n_half * 2 * R * cgs; i += P2_THREADS) {
+        const int hh = i / (2 * R * cgs), ii = i % (2 * R * cgs);
+        const int j = ii / cgs, q = ii % cgs;
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(g.dw_w + j * g.N + (nt0 + hh) * g.block_n + q * 4));
         const __half2 h0 = h2_from(w4.x, w4.y), h1 = h2_from(w4.z, w4.w);
-        *reinterpret_cast<uint2*>(down_w + (j * g.block_n + q * 4) * 2) =
+        *reinterpret_cast<uint2*>(down_w + ((hh * 2 * R + j) * g.block_n + q * 4) * 2) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
       }
       named_bar_sync(BAR_TAPS, P2_THREADS);
+      cached_half = -1;
+    }
+    if (half != cached_half) {
+      cached_half = half;
       if (g.bias != nullptr) {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
         bs2[0] = h2_from(b0.x, b0.y); bs2[1] = h2_from(b0.z, b0.w);
@@ -544,6 +578,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
         bs2[0] = bs2[1] = h2_from(0.f, 0.f);
       }
     }
+    const uint32_t w_half_u32 = w_u32 + half * (2 * R * g.block_n * 2);
     __half2 gm2 = h2_from(1.f, 1.f), bt2 = h2_from(0.f, 0.f);
     if (g.film != nullptr) {
       const float* fp = g.film + static_cast<size_t>(tc.clip) * g.film_stride + (c / band_w) * 2;
@@ -566,7 +601,7 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
 #pragma unroll
         for (int j = 0; j < 2 * R; ++j) {
           const uint2 u = lds_u2(srow + j * pitch);
-          const uint2 w = lds_u2(w_u32 + j * g.block_n * 2);
+          const uint2 w = lds_u2(w_half_u32 + j * g.block_n * 2);
           if (j & 1) {
             a1[0] = __hfma2(as_h2(w.x), as_h2(u.x), a1[0]);
             a1[1] = __hfma2(as_h2(w.y), as_h2(u.y), a1[1]);
@@ -845,7 +880,9 @@ __device__ __forceinline__ void pm_down_loop(const GemmArgs& g, const uint8_t* s
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int EPI>
+// CG2 (STAGED only): the CTA-pair instantiation.  It is a separate kernel because a kernel that contains cta_group::2
+// instructions is marked as such in its ELF attributes and can only be launched as clusters of two.
+template <int EPI, bool CG2 = false>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
@@ -894,13 +931,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(w_full, 1);
     for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], STG ? P1_WARPS : (IS_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));  // one arrive per draining warp
+      // one arrive per draining warp (CTA-pair mode: the leader's barrier also collects the peer's drain warps)
+      mbar_init(&acc_empty[i], STG ? (g.cg2 ? 2 * P1_WARPS : P1_WARPS) : (IS_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (CG2) tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above overlaps the previous kernel's tail (programmatic dependent launch)
@@ -921,7 +963,28 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(num_kb * b_stage_bytes));
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smemB + kb * b_stage_bytes, &tmB, w_full, kb * BK, n_fixed);
       }
-      if (g.pair) {
+      if constexpr (CG2) {
+        // CTA pair: this CTA's A tile and ITS HALF (block_n rows) of the 2 * block_n wide W k-block; the bytes of both CTAs
+        // complete on the leader's full barrier, which the leader alone arms
+        const bool leader = (blockIdx.x & 1) == 0;
+        const uint32_t pair_bytes = 2u * static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
+        for (int ku = 0;; ++ku) {
+          bool done;
+          const int l0 = seq_tile(g, 2 * ku, done);
+          if (done) break;
+          const TileCoord t0 = tile_coord(g, l0);
+          const int r0 = t0.mi * rows_out - halo;
+          const int nrow0 = (t0.nt + static_cast<int>(blockIdx.x & 1)) * g.block_n;   // t0.nt is even: first half of the wide tile
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full[stage], pair_bytes);
+            const bool sh = g.kb_split > 0 && kb >= g.kb_split;
+            tma_load_3d_cg2(smemA + stage * A_STAGE_BYTES, &tmA, &full[stage], (sh ? kb - g.kb_split : kb) * BK, r0 - (sh ? 1 : 0), t0.clip);
+            tma_load_2d_cg2(smemB + stage * b_stage_bytes, &tmB, &full[stage], kb * BK, nrow0);
+            if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else if (g.pair) {
         // one ring stage = the k-block of TWO M tiles (same n tile) + the W k-block they share
         for (int ku = 0;; ++ku) {
           bool done, d1;
@@ -994,7 +1057,30 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t as_phase = 0;
       int dbg_it = 0;
       if (g.resident_b) mbar_wait(w_full, 0);
-      if (g.pair) {
+      if constexpr (CG2) {
+        if ((blockIdx.x & 1) == 0) {                 // the even CTA issues for the pair; commits arrive in both CTAs
+          for (int ku = 0;; ++ku) {
+            bool done;
+            seq_tile(g, 2 * ku, done);
+            if (done) break;
+            mbar_wait(&acc_empty[as], as_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * acc_cols);
+            for (int kb = 0; kb < num_kb; ++kb) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(smemA + stage * A_STAGE_BYTES));
+              const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smemB + stage * b_stage_bytes));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_f16_cg2(tmem_d, adesc + 2 * k, bdesc + 2 * k, g.idesc2, (kb | k) ? 1u : 0u);
+              umma_commit_cg2(&empty[stage]);
+              if (kb == num_kb - 1) umma_commit_cg2(&acc_full[as]);
+              if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+            if (++as == acc_stages) { as = 0; as_phase ^= 1; }
+          }
+        }
+      } else if (g.pair) {
         int c = 0;                                   // tiles issued so far: accumulator stage c % acc_stages
         for (int ku = 0;; ++ku) {
           bool done, d1;
@@ -1073,12 +1159,13 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (done) break;
         if (l_ < 0) continue;
         if (it >= g.stage_bufs) named_bar_sync(BAR_ST_EMPTY + sb, drain_bar_threads);   // math warps left tile sb
-        mbar_wait(&acc_full[as], as_phase);
+        const int sub = g.cg2 ? (it & 1) : 0;        // CTA-pair mode: the accumulator holds two block_n-wide tiles
+        if (sub == 0) mbar_wait(&acc_full[as], as_phase);
         if (q == 0 && lane == 0) WV_DBG(3, it);
         if (lane == 0) WV_DBG(36 + q, it);           // per drain warp: start
         tc_fence_after();
         const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * acc_cols);
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * acc_cols + sub * g.block_n);
         const uint32_t rowp = stage_u32 + sb * (BM * pitch) + (q * 32 + lane) * pitch;
         for (int c = 0; c < (WV_DBG_MODE(4) ? 0 : chunks); ++c) {
           tmem_ld32(taddr + c * 32, v);
@@ -1103,11 +1190,15 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
+        if (!g.cg2) {
+          if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
+        } else if (sub == 1) {
+          if (lane == 0) mbar_arrive_leader(&acc_empty[as]);   // both halves drained: tell the issuing CTA
+        }
         if (q == 0 && lane == 0) WV_DBG(4, it);
         if (lane == 0) WV_DBG(8 + q, it);            // per drain warp: end
         named_bar_arrive(BAR_ST_FULL + sb, drain_bar_threads);   // release: this warp's 32 rows are staged
-        if (++as == acc_stages) { as = 0; as_phase ^= 1; }
+        if (!g.cg2 || sub == 1) { if (++as == acc_stages) { as = 0; as_phase ^= 1; } }
         if (++sb == g.stage_bufs) sb = 0;
         ++it;
       }
@@ -1323,10 +1414,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG2) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and both signal each other's barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG2) tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

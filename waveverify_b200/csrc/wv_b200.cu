@@ -117,8 +117,13 @@ CUtensorMap make_tmap4(const void* base, uint64_t dim_k, uint64_t dim_row, uint6
   return m;
 }
 
-int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN) {
+bool g_cg2_bn96 = true;     // see pick_block_n (WV_CG2_BN96=0: keep 128-wide tiles for N = 384)
+int pick_block_n(int N, int must_divide = 0, int max_bn = MAX_BN, bool pairable = false) {
   static const int cands[] = {256, 192, 160, 128, 96, 64, 32};
+  // STAGED layers whose 128-wide n tiles come in an odd number (N = 384): 96-wide tiles pair up for the CTA-pair mode.
+  // Only for the compute-bound uses (resblock first halves, channel-halving 1x1): the residual launches are DRAM-bound
+  // and measured 14 % slower with 96-wide tiles (profiles/r02_cta_pairs.md)
+  if (pairable && max_bn == 128 && must_divide == 0 && N >= 384 && N % 128 == 0 && (N / 128) % 2 == 1 && N % 192 == 0 && g_cg2_bn96) return 96;
   for (int c : cands)
     if (c <= max_bn && N % c == 0 && (must_divide == 0 || must_divide % c == 0)) return c;
   WV_THROW(WV_ERR_UNSUPPORTED, "no tile width for N=%d", N);
@@ -141,6 +146,9 @@ int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resb
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
 int g_epi_groups = 2;       // STFT epilogue warp groups, one accumulator stage each (WV_EPI_GROUPS: 0/1 = one group of 16 warps, 2 = two groups for
                             // tiles of <= 64 columns, 4 = additionally four groups for tiles of <= 128 columns)
+int g_cg2_min_kb = 4;       // STAGED layers with >= this many k-blocks, streamed W and an even number of n tiles run as CTA pairs
+                            // (cluster of 2, tcgen05 cta_group::2, 256-row MMAs; WV_CG2_MIN_KB, 0 = off)
+int g_max_clusters = 0;     // co-resident CTA pairs of the STAGED kernel (cudaOccupancyMaxActiveClusters)
 int g_pair_min_kb = 4;      // STAGED layers with >= this many k-blocks and streamed W run two M tiles per W k-block (WV_PAIR_MIN_KB, 0 = off)
 int g_one_buf_kb = 0;       // STAGED layers with >= this many k-blocks and streamed W use one staging tile (WV_ONE_BUF_KB, 0 = off)
 int g_up_fuse_maxc = 384;   // decoder stages up to this input width run upsample + 1x1 as one GEMM (WV_UP_FUSE_MAXC, 0 = off)
@@ -168,6 +176,7 @@ void init_device_once() {
   g_num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("WV_PDL")) g_pdl = atoi(e) != 0;   // A/B switch for the profiling scripts
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+  CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STAGED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_L2NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
   CK(cudaFuncSetAttribute(gemm_sm100_kernel<EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
@@ -195,6 +204,21 @@ void init_device_once() {
   if (const char* e = getenv("WV_LAST_GEMM")) g_last_gemm = atoi(e) != 0;
   if (const char* e = getenv("WV_EPI_GROUPS")) g_epi_groups = atoi(e);
   if (const char* e = getenv("WV_PAIR_MIN_KB")) g_pair_min_kb = atoi(e);
+  if (const char* e = getenv("WV_CG2_MIN_KB")) g_cg2_min_kb = atoi(e);
+  if (const char* e = getenv("WV_CG2_BN96")) g_cg2_bn96 = atoi(e) != 0;
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * g_num_sms); cfg.blockDim = dim3(STAGED_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM_LIMIT;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm_sm100_kernel<EPI_STAGED, true>, &cfg) == cudaSuccess) g_max_clusters = nc;
+    else { cudaGetLastError(); g_max_clusters = 0; }
+    if (getenv("WV_VERBOSE")) fprintf(stderr, "[wv] %d SMs, %d co-resident CTA pairs\n", g_num_sms, g_max_clusters);
+  }
   if (const char* e = getenv("WV_ONE_BUF_KB")) g_one_buf_kb = atoi(e);
   if (const char* e = getenv("WV_UP_FUSE_MAXC")) g_up_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_PHASED_STFT")) g_phased_stft = atoi(e) != 0;
@@ -380,7 +404,7 @@ GemmW make_gemm_w(Weights& W, const std::vector<float>& rows, int N, int K, bool
   return g;
 }
 
-GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias) {
+GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias, bool pairable = false) {
   const HostTensor& t = W.get(p + ".weight");
   if (t.shape.size() != 3 || t.shape[2] != 1)
     WV_THROW(WV_ERR_INVALID, "'%s.weight' is not a 1x1 conv", p.c_str());
@@ -394,7 +418,7 @@ GemmW pointwise(Weights& W, const std::string& p, float scale, bool with_bias) {
     for (auto& v : bb) v *= scale;
   }
   // pointwise convs run through the STAGED epilogue (two staging tiles): tile width <= 128
-  return make_gemm_w(W, rows, N, K, false, pick_block_n(N, 0, g_pm ? STAGED_PM_MAX_BN : STAGED_MAX_BN), b ? bb.data() : nullptr, N);
+  return make_gemm_w(W, rows, N, K, false, pick_block_n(N, 0, g_pm ? STAGED_PM_MAX_BN : STAGED_MAX_BN, pairable && !g_pm), b ? bb.data() : nullptr, N);
 }
 
 // depthwise [C,1,k] -> [k][C]; transposed conv weights have the same memory shape
@@ -422,7 +446,7 @@ DwW depthwise(Weights& W, const std::string& p, float scale, bool with_bias, flo
 ResW resblock_w(Weights& W, const std::string& p, int idx, float rs) {
   ResW r;
   r.pre_scale = 1.f / std::sqrt(1.f + idx * rs * rs);                     // seanet.py:183
-  r.pw1 = pointwise(W, p + ".block.1.conv.conv", 1.f, false);
+  r.pw1 = pointwise(W, p + ".block.1.conv.conv", 1.f, false, true);
   r.dw1 = depthwise(W, p + ".block.2.conv.conv", 1.f, true);
   r.pw2 = pointwise(W, p + ".block.4.conv.conv", 1.f, false);
   const float tail = rs * W.scalar_or(p + ".res_scale_param", 1.f);       // seanet.py:271-277
@@ -710,11 +734,17 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   // pair mode (two M tiles per W k-block) for the long-K layers whose W tile does not stay resident
   const bool pair = staged && !pm && !resident && g.down_r == 0 && g.a2_split == 0 && g.a3_split == 0 && w.block_n <= 128 && g_pair_min_kb > 0 && num_kb >= g_pair_min_kb;
   g.pair = pair ? 1 : 0;
-  g.acc_stages = (pair || g.epi_groups == 4) ? MAX_ACC_STAGES : ACC_STAGES;   // four epilogue groups: one 128-column stage each
-  g.acc_cols = (pair || g.epi_groups == 4) ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
-  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs, pair, pm);
+  // CTA-pair mode (cta_group::2) for the same class of layers when the n tiles pair up: half the operand bytes per MAC
+  const bool cg2 = epi == EPI_STAGED && !resident && !g.dual && !g.last_mode && g.pre_w == nullptr && g.a2_split == 0 &&
+                   g.a3_split == 0 && g_cg2_min_kb > 0 && num_kb >= g_cg2_min_kb && g_max_clusters > 0 && tiles_n_ % 2 == 0 &&
+                   2 * w.block_n <= MAX_BN && g.stage_bufs == STAGE_BUFS;
+  g.cg2 = 0;
+  if (cg2) { g.pair = 0; }
+  g.acc_stages = (g.pair || g.epi_groups == 4) ? MAX_ACC_STAGES : ACC_STAGES;   // four epilogue groups: one 128-column stage each
+  g.acc_cols = (g.pair || g.epi_groups == 4) ? TMEM_COLS / MAX_ACC_STAGES : MAX_BN;
+  g.stages = gemm_stage_count(w.block_n, staged, num_kb, resident, g.stage_bufs, g.pair != 0, pm);
   if (g.stages < 2) WV_THROW(WV_ERR_UNSUPPORTED, "not enough shared memory for block_n=%d", w.block_n);
-  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs, pair, pm);
+  op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, resident, g.stage_bufs, g.pair != 0, pm);
   if (custom_tmA) {
     g.rows_per_clip = rows_per_clip;
     g.n_clips = n_clips;
@@ -756,6 +786,23 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
   g.num_tiles = tiles;
   op.g = g;
   op.grid = std::min(tiles, g_num_sms);
+  if (cg2) {
+    const long long units = (static_cast<long long>(g.tiles_m_per_clip) * g.n_clips + 1) / 2 * (g.tiles_n / 2);
+    if (units >= 2LL * g_max_clusters) {   // at least two units per CTA pair, else the single-CTA path spreads the tiles better
+      g.cg2 = 1;
+      g.idesc2 = make_idesc_f16(2 * BM, 2 * w.block_n, w.fp16);
+      const int ntw = g.tiles_n / 2;
+      g.magic_n2 = ntw == 1 ? 0u : static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(ntw));
+      op.grid = 2 * static_cast<int>(std::min<long long>(units, g_max_clusters));
+      op.g = g;
+    } else if (pair) {
+      g.pair = 1;   // fall back to the in-CTA pair mode (re-derive its layout)
+      g.acc_stages = MAX_ACC_STAGES; g.acc_cols = TMEM_COLS / MAX_ACC_STAGES;
+      g.stages = gemm_stage_count(w.block_n, staged, num_kb, false, g.stage_bufs, true, pm);
+      op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs, true, pm);
+      op.g = g;
+    }
+  }
   if (g.pair) {
     const long long units = (static_cast<long long>(g.tiles_m_per_clip) * g.n_clips + 1) / 2 * g.tiles_n;
     if (units < 4LL * g_num_sms) {   // too few units: wave quantisation costs more than the shared W loads save
@@ -1071,7 +1118,7 @@ void build_decoder_w(wv_net& n) {
     if (st.up.k != 2 * st.r) WV_THROW(WV_ERR_INVALID, "upsample kernel != 2*stride");
     const std::string up_name = p + "." + std::to_string(i - 1) + ".convtr.convtr";
     const std::string hv_name = p + "." + std::to_string(i) + ".conv.conv";
-    st.halve = pointwise(W, p + "." + std::to_string(i++) + ".conv.conv", 1.f, true);
+    st.halve = pointwise(W, p + "." + std::to_string(i++) + ".conv.conv", 1.f, true, true);
     if (g_up_fuse_maxc > 0 && C <= g_up_fuse_maxc && C % BK == 0) {
       // out[r*i + j, n] = b[n] + sum_c Wh[n,c] (a[i,c] w[c,j] + a[i-1,c] w[c,j+r])   (modules/conv.py:838-874 followed by
       // the 1x1): one GEMM over the LOW-rate rows with K = [a[i] | a[i-1]] and N = (j, n); its [Ts, r*C/2]
@@ -1780,16 +1827,27 @@ Plan& get_dec_plan(wv_net& n, int B, int F) {
 
 // Launch with programmatic stream serialization (PDL): the kernel's prologue may overlap the tail of
 // the previous kernel in the stream; every kernel calls griddepcontrol.wait before touching data.
+thread_local int g_launch_cluster = 1;   // cluster size of the next launch_k call (2 = CTA pairs; reset after the launch)
 template <typename... KArgs, typename... Args>
 void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (g_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_launch_cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = static_cast<unsigned>(g_launch_cluster); at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    g_launch_cluster = 1;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   CK(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
 }
 
@@ -1811,7 +1869,14 @@ void launch_down(int grid, cudaStream_t st, const h16* in, const float* w, const
 void launch_gemm(const Op& op, const GemmArgs& g, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(op.i[7]);
   switch (op.epi) {
-    case EPI_STAGED: launch_k(gemm_sm100_kernel<EPI_STAGED>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
+    case EPI_STAGED:
+      if (g.cg2) {
+        g_launch_cluster = 2;
+        launch_k(gemm_sm100_kernel<EPI_STAGED, true>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g);
+      } else {
+        launch_k(gemm_sm100_kernel<EPI_STAGED>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g);
+      }
+      break;
     case EPI_L2NORM: launch_k(gemm_sm100_kernel<EPI_L2NORM>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
     case EPI_STFT: launch_k(gemm_sm100_kernel<EPI_STFT>, op.grid, GEMM_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
     case EPI_STAGED_PM: launch_k(gemm_sm100_kernel<EPI_STAGED_PM>, op.grid, STAGED_THREADS, smem, st, op.tmA, op.tmB, op.tmR, g); break;
