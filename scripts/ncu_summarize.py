@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("csv")
 ap.add_argument("--md")
 ap.add_argument("--traffic-json")
+ap.add_argument("--build-id", default="")
 a = ap.parse_args()
 
 rows = list(csv.reader(open(a.csv)))
@@ -24,11 +25,18 @@ NAMES = {"gemm_sm100_kernel<0>": "gemm_std", "gemm_sm100_kernel<(int)0>": "gemm_
          "gemm_sm100_kernel<3>": "gemm_head", "gemm_sm100_kernel<(int)3>": "gemm_head"}
 
 
+EPI = {0: "gemm_std", 1: "gemm_l2norm", 2: "gemm_stft", 3: "gemm_head", 4: "gemm_std_precise", 5: "gemm_l2norm_precise",
+       6: "gemm_stft_precise"}
+
+
 def short(name):
     n = name.split("(")[0].replace("void ", "").replace("wv::", "").strip()
-    m = re.search(r"gemm_sm100_kernel<[^>]*>", name)
-    if m:
-        return NAMES.get(m.group(0), m.group(0))
+    m = re.search(r"gemm_sm100_kernel<([^>]*)>", name)
+    if m:   # template arguments: epilogue id, CTA-pair flag ("0, 1", "(int)0, (bool)1", "0, true" ...)
+        args = [re.sub(r"\([a-z ]+\)", "", t).strip() for t in m.group(1).split(",")]
+        epi = EPI.get(int(args[0]), m.group(0))
+        pair = len(args) > 1 and args[1] in ("1", "true")
+        return epi + ("_cta_pair" if pair else "")
     return n.replace("_kernel", "")
 
 
@@ -64,6 +72,15 @@ print(out)
 if a.md:
     open(a.md, "w").write(out + "\n")
 if a.traffic_json:
-    json.dump({k: {"dram_bytes_per_step": v["rd"] + v["wr"], "launches": v["launches"],
-                   "dram_bytes_per_launch": (v["rd"] + v["wr"]) / max(1, v["launches"])}
-               for k, v in agg.items() if v["rd"] + v["wr"] > 0}, open(a.traffic_json, "w"), indent=1)
+    # bench.py's kernel classes do not distinguish the CTA-pair instantiation: fold it into its class
+    tj = collections.defaultdict(lambda: {"dram_bytes_per_step": 0.0, "launches": 0})
+    for k, v in agg.items():
+        if v["rd"] + v["wr"] > 0:
+            e = tj[k.replace("_cta_pair", "")]
+            e["dram_bytes_per_step"] += v["rd"] + v["wr"]; e["launches"] += v["launches"]
+    out_j = {k: {**v, "dram_bytes_per_launch": v["dram_bytes_per_step"] / max(1, v["launches"])} for k, v in tj.items()}
+    out_j["_dram_bytes_per_step"] = sum(v["rd"] + v["wr"] for v in agg.values())
+    out_j["_device_time_us_per_step_ncu"] = tot
+    if a.build_id:
+        out_j["_build_id"] = a.build_id
+    json.dump(out_j, open(a.traffic_json, "w"), indent=1)
