@@ -162,6 +162,15 @@ int wv_effect_fir(const float* in, const float* taps, int n_taps, int B, int T, 
 int wv_effect_resample(const float* in, const float* taps, int B, int T, int orig, int nw, int width, int T_mid, int T_out,
                        int lerp, float* out, void* stream);
 
+/* ---- fp16 range check -------------------------------------------------------------------------
+ * The fast nets store activations as fp16: every fp32 -> fp16 conversion saturates at +-65504 and the packed-half2 epilogue
+ * arithmetic can overflow to inf, both silently.  With the check enabled every launch's fp16 outputs are scanned by an extra
+ * kernel (slow: run it once after loading a checkpoint, on representative full-scale audio).  wv_net_range_read synchronises,
+ * returns the counts accumulated since the last read (values AT the saturation bound, non-finite values, largest finite |v|)
+ * and resets them. */
+int wv_net_set_range_check(wv_net* net, int enable);
+int wv_net_range_read(wv_net* net, unsigned long long* saturated, unsigned long long* nonfinite, float* max_abs);
+
 /* ---- profiling / debugging (used by bench.py and the tests) ------------------------------- */
 /* When enabled, every launch of a forward is bracketed by CUDA events on the caller's stream. */
 int wv_net_set_profile(wv_net* net, int enable);

@@ -1390,6 +1390,43 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const long long base = b * g.T + t0;
               float* lp = g.logits ? g.logits + (b * g.n_out + o) * static_cast<long long>(g.T) + t0
                                    : nullptr;
+              if (t0 + 32 <= g.T && ((g.T | t0) & 15) == 0) {
+                // whole 32-sample run inside the clip and every row 16-byte aligned: the thread's
+                // 128 B of logits / probabilities leave as eight 16-byte stores, its 32 mask bytes as two
+                float l[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) l[i] = __uint_as_float(v[i]) + bo;
+                if (lp) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(lp)[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+                }
+                if (g.mask_out) {
+                  uint32_t mw[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    mw[i] = (l[4 * i] > 0.5f ? 1u : 0u) | (l[4 * i + 1] > 0.5f ? 0x100u : 0u) | (l[4 * i + 2] > 0.5f ? 0x10000u : 0u) |
+                            (l[4 * i + 3] > 0.5f ? 0x1000000u : 0u);
+                  uint4* mp = reinterpret_cast<uint4*>(g.mask_out + base);
+                  mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+                  mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+                }
+                if (g.probs || g.partial) {
+                  uint4 pw[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+                  if (g.partial && g.presence) { pw[0] = __ldcg(reinterpret_cast<const uint4*>(g.presence + base)); pw[1] = __ldcg(reinterpret_cast<const uint4*>(g.presence + base) + 1); }
+                  const uint32_t pwv[8] = {pw[0].x, pw[0].y, pw[0].z, pw[0].w, pw[1].x, pw[1].y, pw[1].z, pw[1].w};
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const float p = __fdividef(1.f, 1.f + __expf(-l[i]));   // MUFU.RCP: 2 ulp, far inside the 3e-4 bit margin
+                    l[i] = p;
+                    if (g.partial) psum += g.presence ? (((pwv[i >> 2] >> ((i & 3) * 8)) & 0xffu) ? p : 0.f) : p;
+                  }
+                  if (g.probs) {
+                    float4* pp = reinterpret_cast<float4*>(g.probs + base);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pp[i] = make_float4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+                  }
+                }
+              } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 if (t0 + i < g.T) {
@@ -1400,6 +1437,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   if (g.probs) g.probs[base + i] = p;
                   if (g.partial) psum += g.presence ? (__ldcg(g.presence + base + i) ? p : 0.f) : p;
                 }
+              }
               }
             }
           }

@@ -744,4 +744,40 @@ __global__ void refine_advance_kernel(cudaGraphConditionalHandle loop, const Ref
   cudaGraphSetConditional(loop, it * K < st->count ? 1u : 0u);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Range check of a stored fp16 tensor (wv_net_set_range_check): every fp32 -> fp16 conversion of the path saturates at
+// +-65504 (cvt.rn.satfinite) and the packed half2 epilogue arithmetic can overflow to inf, both silently.  With the check
+// enabled every launch's fp16 outputs are scanned: stats[0] += values at the saturation bound, stats[1] += non-finite
+// values, stats[2] = max |v| (fp16 bits; order-preserving for non-negative halves).
+__global__ void __launch_bounds__(256)
+range_check_kernel(const uint4* __restrict__ p, long long n16, unsigned long long* __restrict__ stats) {
+  unsigned sat = 0, bad = 0, mx = 0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n16; i += static_cast<long long>(gridDim.x) * 256) {
+    const uint4 u = __ldcg(p + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const unsigned a = (w[k] >> (16 * hh)) & 0x7fffu;
+        sat += a == 0x7bffu;
+        bad += a >= 0x7c00u;
+        mx = max(mx, a < 0x7c00u ? a : 0u);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sat += __shfl_xor_sync(0xffffffffu, sat, d);
+    bad += __shfl_xor_sync(0xffffffffu, bad, d);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (sat) atomicAdd(stats, static_cast<unsigned long long>(sat));
+    if (bad) atomicAdd(stats + 1, static_cast<unsigned long long>(bad));
+    atomicMax(stats + 2, static_cast<unsigned long long>(mx));
+  }
+}
+
 }  // namespace wv

@@ -1010,7 +1010,10 @@ struct wv_net {
   cudaStream_t cap_stream = nullptr; // capture stream for the small-batch CUDA graphs
   unsigned long long clock = 0;      // LRU clock of the plan caches
   std::map<std::vector<int>, std::unique_ptr<RefineGraph>> refine;   // keyed by (B, T, K, logits, presence)
+  bool check_range = false;               // scan every launch's fp16 outputs for saturated / non-finite values (wv_net_set_range_check)
+  unsigned long long* range_stats = nullptr;   // device: {saturated, non-finite, max |v| as fp16 bits}
   ~wv_net() {
+    if (range_stats) cudaFree(range_stats);
     refine.clear();
     if (cap_stream) cudaStreamDestroy(cap_stream);
     plans.clear();
@@ -1967,6 +1970,25 @@ void run_plan(wv_net& n, Plan& plan, const IoPtrs& io, cudaStream_t st, int stop
         launch_k(latent_in_kernel, op.grid, 256, 0, st, io.z_in, static_cast<h16*>(op.out0), op.i[0], op.i[1], op.i[2]);
         break;
     }
+    if (n.check_range && n.range_stats != nullptr) {
+      // fp16 outputs only: the precise nets store their raw streams as fp32 (out0 of their STAGED / conv_pre launches)
+      const bool out0_f32 = (op.type == OP_GEMM && op.epi == EPI_STAGED_PM) || op.type == OP_CONV_PRE_PM || op.type == OP_FILM;
+      const void* outs[2] = {out0_f32 ? nullptr : op.out0, op.out1};
+      for (int w = 0; w < 2; ++w)
+        if (outs[w] != nullptr && op.out_bytes[w] >= 16) {
+          const long long n16 = static_cast<long long>(op.out_bytes[w] / 16);
+          range_check_kernel<<<elem_grid(n16), 256, 0, st>>>(static_cast<const uint4*>(outs[w]), n16, n.range_stats);
+          if (getenv("WV_RANGE_VERBOSE")) {   // per-launch report (diagnostics): running totals after this output
+            unsigned long long h[4];
+            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpy(h, n.range_stats, sizeof(h), cudaMemcpyDeviceToHost));
+            const uint16_t bits = static_cast<uint16_t>(h[2]);
+            __half hv;
+            memcpy(&hv, &bits, 2);
+            fprintf(stderr, "[wv range] %-24s out%d: saturated %llu non-finite %llu max|v| %g (running)\n", op.tag.c_str(), w, h[0], h[1], __half2float(hv));
+          }
+        }
+    }
     if (prof) CK(cudaEventRecord(plan.events[op_index + 1], st));
     if (op_index == stop_after) break;
   }
@@ -2169,7 +2191,7 @@ static int forward_common(wv_net* net, int B, int T, const IoPtrs& io0, cudaStre
       if (io.probs) io.probs += so;
       // small (launch-bound) calls replay a CUDA graph; it is captured the second time a shape + output set is seen,
       // so one-off clip lengths (file API) do not pay capture + instantiation + staging memory for a single use
-      bool graph = bn == B && !net->profile && g_graph_max_samples > 0 && static_cast<long long>(B) * T <= g_graph_max_samples;
+      bool graph = bn == B && !net->profile && !net->check_range && g_graph_max_samples > 0 && static_cast<long long>(B) * T <= g_graph_max_samples;
       if (graph) {
         const uint32_t key = io_key(io);
         graph = plan.graphs.count(key) > 0 || ++plan.graph_seen[key] >= 2;
@@ -2467,6 +2489,38 @@ int wv_effect_resample(const float* in, const float* taps, int B, int T, int ori
     effect_resample_kernel<<<elem_grid(static_cast<long long>(B) * T_out), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         in, taps, B, T, orig, nw, width, 2 * width + orig, T_mid, T_out, lerp, out);
     CK(cudaGetLastError());
+  });
+}
+
+// ---- fp16 range check ------------------------------------------------------------------------
+int wv_net_set_range_check(wv_net* net, int enable) {
+  if (!net) return fail(WV_ERR_INVALID, "null net");
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    if (enable && !net->range_stats) {
+      CK(cudaMalloc(reinterpret_cast<void**>(&net->range_stats), 4 * sizeof(unsigned long long)));
+      CK(cudaMemset(net->range_stats, 0, 4 * sizeof(unsigned long long)));
+    }
+    net->check_range = enable != 0;
+  });
+}
+
+int wv_net_range_read(wv_net* net, unsigned long long* saturated, unsigned long long* nonfinite, float* max_abs) {
+  if (!net || !net->range_stats) return fail(WV_ERR_INVALID, "range check was never enabled on this net");
+  return guarded([&] {
+    DeviceGuard dg(net->device);
+    unsigned long long h[4];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, net->range_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(net->range_stats, 0, sizeof(h)));
+    if (saturated) *saturated = h[0];
+    if (nonfinite) *nonfinite = h[1];
+    if (max_abs) {
+      const uint16_t bits = static_cast<uint16_t>(h[2]);
+      __half hv;
+      memcpy(&hv, &bits, 2);
+      *max_abs = __half2float(hv);
+    }
   });
 }
 

@@ -169,6 +169,16 @@ class _B200Module(nn.Module):
         for net in self._nets.values():
             _lib.check(_lib.lib().wv_net_set_chunk(net.handle, int(n)), "set_chunk")
 
+    def set_range_check(self, enable: bool):
+        """Scan every launch's fp16 outputs for saturated (|v| = 65504) / non-finite values (slow; diagnostics)."""
+        _lib.check(_lib.lib().wv_net_set_range_check(self._native(False).handle, int(bool(enable))), "set_range_check")
+
+    def range_read(self) -> dict:
+        """Counts since the last read: dict(saturated, nonfinite, max_abs).  Synchronises and resets."""
+        sat, bad, mx = C.c_ulonglong(0), C.c_ulonglong(0), C.c_float(0.0)
+        _lib.check(_lib.lib().wv_net_range_read(self._native(False).handle, C.byref(sat), C.byref(bad), C.byref(mx)), "range_read")
+        return dict(saturated=int(sat.value), nonfinite=int(bad.value), max_abs=float(mx.value))
+
     def set_profile(self, enable: bool):
         _lib.check(_lib.lib().wv_net_set_profile(self._native().handle, int(bool(enable))), "set_profile")
 
