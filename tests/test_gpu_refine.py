@@ -78,3 +78,23 @@ def test_partial_selection_and_masked_decode():
         for k in ("bits", "avg", "conf", "valid"):
             want = torch.where(sel.reshape(-1, *([1] * (fast[k].dim() - 1))), prec[k], fast[k])
             assert torch.equal(out[k], want), (k, pm is not None)
+
+
+def test_refine_survives_workspace_growth_and_chunking():
+    """The refine graphs hold pointers into the precise net's workspace: a later, larger precise call moves the workspace
+    (plans and graphs are rebuilt), and a sub-batch limit clamps the number of slots."""
+    D = detector()
+    y = clips(6, 8000, 7)
+    ref = D.detect_batch(y, precise=True)
+    D.EXACT_TAU = D.EXACT_TAU_SHORT = 1.0
+    D.refine_slots = 2
+    a = D.detect_batch(y)
+    big = clips(48, 16000, 8)
+    D.detect_batch(big, precise=True)                  # grows the precise net's workspace
+    b = D.detect_batch(y)
+    D.set_chunk_samples(8000)                          # one clip per sub-batch / slot
+    c = D.detect_batch(y)
+    D.set_chunk_samples(0)
+    for out in (a, b, c):
+        for k in ("bits", "avg", "conf", "valid"):
+            assert torch.equal(out[k], ref[k]), k
