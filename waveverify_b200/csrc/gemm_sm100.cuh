@@ -69,6 +69,7 @@ constexpr int BAR_ST_FULL = 2;             // 2,3 = staging tile written (drain 
 constexpr int BAR_ST_EMPTY = 4;            // 4,5 = staging tile consumed (math arrive, drain sync)
 constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 constexpr int GEMM_BAR_BYTES = 512;
+constexpr int RES_BAR_INDEX = 32;           // mbarriers [32, 36) of the barrier block: residual tile full[2] / empty[2]
 constexpr int DOWN_W_BYTES = 2 * 16 * STAGED_MAX_BN * 2;   // staged down-conv taps [half][2r <= 16][block_n] fp16 (CTA-pair mode: both halves of the wide n tile)
 
 // Epilogues 4..6 are the PRECISE variants (fp32-accurate path for the thresholded outputs, see the
@@ -107,6 +108,9 @@ struct GemmArgs {
   int a_prefetch;     // > 0: the producer asks L2 for the A rows of the tile this many tiles ahead (cp.async.bulk.prefetch.tensor):
                       //   DRAM -> L2 runs further ahead than the shared-memory ring can hold
   int res_early2;     // 1: the residual rows of a thread's second unit are requested before the hand-off barrier as well
+  int res_tma;        // 1: the residual tile of every output tile is TMA-loaded (tmR, unswizzled [block_n x 128] box) into one of two
+                      //    shared-memory buffers by warp 3, one tile ahead; the math warps read it from there instead of issuing
+                      //    per-thread ld.global (W resident: the ring streams A only and can spare the 2 x 128 x block_n x 2 bytes)
   int unit_rows;      // STAGED math units: rows per unit (4, or 6 for tile widths whose 4-row groups leave the second pass mostly idle)
   int a_evict_first;  // 1: A operand loads carry the L2 evict_first hint (streamed once)
   int reverse;        // 1: walk the tiles from the last one down (L2 reuse across consecutive launches)
@@ -408,6 +412,11 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   int cached_nt = -1;
   __half2 wt[TAPS][2], bs[2];
   const bool two = g.math_groups == 2;
+  // residual tiles staged by TMA (g.res_tma): buffers behind the staging tiles, barriers in the CTA's barrier block
+  const bool rt = RES && !PRE && g.res_tma != 0;
+  const int res_tile_bytes = BM * g.block_n * 2;
+  const uint32_t res_u32 = ((smem_u32(stage_tiles) + g.stage_bufs * BM * pitch + 127u) & ~127u) + cg * 8;
+  uint64_t* res_bars = reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(stage_tiles) - DOWN_W_BYTES - GEMM_BAR_BYTES) + RES_BAR_INDEX;
   int sb = two ? my_grp : 0;
   const int tiles_cta = cta_tile_count(g);
   int tiles_left = two ? (tiles_cta - my_grp + 1) >> 1 : tiles_cta;   // tiles this group still has to process
@@ -439,7 +448,14 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     // before waiting for the drain warps, those of a
     // second unit before the first unit's math, so their latency overlaps the wait / the math.
     uint2 rres[R], rnext[R];
+    const int rbuf = idx & 1;                                      // two groups: == my_grp
     auto load_res = [&](int ro, uint2 (&r)[R]) {
+      if (rt) {                                                    // rows past the clip end are TMA zero fill (and never stored)
+        const uint32_t a = res_u32 + rbuf * res_tile_bytes + ro * (g.block_n * 2);
+#pragma unroll
+        for (int i = 0; i < R; ++i) r[i] = ro + i < BM ? lds_u2(a + i * (g.block_n * 2)) : make_uint2(0u, 0u);
+        return;
+      }
       if constexpr (PRE) {   // v[t,c] = b[c] + sum_j w[j][c] * x[t-4+j], rounded to fp16 like conv_pre_kernel stores it
         const float* xp = g.pre_x + static_cast<size_t>(tc.clip) * g.pre_T;
         const int t0 = r_base + ro - 4;
@@ -479,14 +495,20 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     bool have = active && grp < N_GROUPS && grp * R < rows_left;
     bool early2 = false;                                           // second unit's residual already requested
     if constexpr (RES) {
-      if (have) load_res(grp * R, rres);
-      if (!PRE && g.res_early2) {                                  // both units of the tile in flight across the barrier wait
+      if (have && !rt) load_res(grp * R, rres);
+      if (!PRE && g.res_early2 && !rt) {                           // both units of the tile in flight across the barrier wait
         const int gn0 = grp + gstride;
         if (have && gn0 < N_GROUPS && gn0 * R < rows_left) { load_res(gn0 * R, rnext); early2 = true; }
       }
     }
     if (et_all == 0) WV_DBG(7, dbg_it);                           // warp 0 reaches the hand-off barrier
     named_bar_sync(BAR_ST_FULL + sb, bar_threads);                 // drain warps staged tile sb
+    if constexpr (RES) {
+      if (rt) {
+        mbar_wait(&res_bars[rbuf], static_cast<uint32_t>(idx >> 1) & 1u);   // the tile's residual rows landed
+        if (have) load_res(grp * R, rres);
+      }
+    }
     if (et_all == 0) WV_DBG(5, dbg_it);
     if (lane == 0) WV_DBG(24 + (et_all >> 5), dbg_it);   // per math warp: start
     const uint32_t tile_u32 = stage_u32 + sb * (BM * pitch);
@@ -513,6 +535,9 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
       have = have_next;
     }
     __syncwarp();
+    if constexpr (RES) {
+      if (rt && lane == 0) mbar_arrive(&res_bars[2 + rbuf]);       // this warp is done with the residual buffer
+    }
     if (lane == 0) WV_DBG(12 + (et_all >> 5), dbg_it);   // per math warp: end
     if (--tiles_left >= keep) named_bar_arrive(BAR_ST_EMPTY + sb, bar_threads);   // tile sb may be refilled
     if (et_all == 0) WV_DBG(6, dbg_it);              // warp 0: after releasing the staging tile
@@ -929,6 +954,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&empty[i], 1);
     }
     mbar_init(w_full, 1);
+    if (STG && g.res_tma) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars[RES_BAR_INDEX + i], 1);                                                    // full: the producer's expect_tx
+        mbar_init(&bars[RES_BAR_INDEX + 2 + i], g.math_groups == 2 ? P2_WARPS / 2 : P2_WARPS);     // empty: one arrive per math warp
+      }
+    }
     for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
       // one arrive per draining warp (CTA-pair mode: the leader's barrier also collects the peer's drain warps)
@@ -1142,6 +1173,21 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (STG && warp < 4) {
     reg_dealloc<REGS_LIGHT>();   // warps 2 (TMEM allocator) and 3: the whole warpgroup must take part
+    if constexpr (!PM && !CG2) {
+      if (warp == 3 && lane == 0 && g.res_tma) {
+        // residual producer: the [128 rows x block_n] residual tile of every tile of this CTA, one tile ahead of the math warps
+        const int pitch_ = staged_pitch_bytes(g.block_n);
+        uint8_t* res_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_tiles + g.stage_bufs * BM * pitch_) + 127) & ~static_cast<uintptr_t>(127));
+        const uint32_t bytes = static_cast<uint32_t>(BM * g.block_n * 2);
+        int i = 0;
+        for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++i) {
+          const int buf = i & 1;
+          mbar_wait(&bars[RES_BAR_INDEX + 2 + buf], (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&bars[RES_BAR_INDEX + buf], bytes);
+          tma_load_3d(res_tiles + buf * bytes, &tmR, &bars[RES_BAR_INDEX + buf], tc.nt * g.block_n, tc.mi * rows_out, tc.clip);
+        }
+      }
+    }
   } else if (STG && warp >= 4) {
     const int pitch = staged_pitch_bytes(g.block_n, PM);
     const int chunks = g.block_n / 32;

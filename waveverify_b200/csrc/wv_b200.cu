@@ -141,6 +141,9 @@ int g_a_prefetch = 0;       // STAGED / STFT producers prefetch the A rows of th
 bool g_pre_fuse = false;    // the first encoder resblock recomputes its residual (= conv_pre output) from the waveform instead of reading it
                             // (WV_PRE_FUSE=1; bit-identical; measured r01h: conv_pre 68 -> 61 us, r0.out 113 -> 121 us, +-0 overall: off)
 int g_res1_kb = 0;          // largest W tile (KB) kept resident next to a single staging tile (WV_RES1_KB; 0 = off)
+bool g_res_tma = true;      // residual tiles of the resblock second halves by TMA into shared memory (WV_RES_TMA=0: per-thread ld.global;
+                            // see gemm_sm100.cuh res_tma; measured r02: dec.u2 / u3 second halves -10..-13 %)
+int g_res_tma_min_stages = 4;   // fewest A ring stages left next to the residual buffers (WV_RES_TMA_MIN_STAGES)
 bool g_res_early2 = true;   // residual rows of the second unit of a tile requested before the drain hand-off too (WV_RES_EARLY2=0: after it)
 int g_spec_fuse_maxc = 128; // encoder stages up to this width run the last resblock's second half and the spectrogram 1x1 as ONE launch (WV_SPEC_FUSE_MAXC, 0 = off)
 bool g_last_gemm = true;    // decoder output conv (C -> 1, k = 5) on the tensor cores (WV_LAST_GEMM=0: CUDA-core kernel)
@@ -188,6 +191,8 @@ void init_device_once() {
   if (const char* e = getenv("WV_LDY_ALIGN")) g_ldy_align = atoi(e);
   if (const char* e = getenv("WV_SPEC_FUSE_MAXC")) g_spec_fuse_maxc = atoi(e);
   if (const char* e = getenv("WV_RES_EARLY2")) g_res_early2 = atoi(e) != 0;
+  if (const char* e = getenv("WV_RES_TMA")) g_res_tma = atoi(e) != 0;
+  if (const char* e = getenv("WV_RES_TMA_MIN_STAGES")) g_res_tma_min_stages = std::max(2, atoi(e));
   if (const char* e = getenv("WV_RES1_KB")) g_res1_kb = atoi(e);
   if (const char* e = getenv("WV_PRE_FUSE")) g_pre_fuse = atoi(e) != 0;
   if (const char* e = getenv("WV_A_PREFETCH")) g_a_prefetch = atoi(e);
@@ -822,6 +827,18 @@ void add_gemm(PlanCtx& c, int epi, const GemmW& w, const void* A, int lda, long 
     op.i[7] = gemm_smem_bytes(w.block_n, staged, num_kb, false, g.stage_bufs, false, pm);
     op.g = g;
   }
+  // residual tile by TMA: W resident (the ring streams A only), plain single-CTA launches with a stored residual
+  if (g_res_tma && epi == EPI_STAGED && g.residual != nullptr && g.resident_b && !g.cg2 && !g.pair && !g.dual && g.a2_split == 0 &&
+      g.down_r == 0 && !g.last_mode && g.pre_w == nullptr && g.ldo == w.N) {
+    const int res_bytes = 2 * BM * w.block_n * 2 + 128;
+    int st = g.stages, bytes = op.i[7];
+    while (st > g_res_tma_min_stages && bytes + res_bytes > GEMM_SMEM_LIMIT) { --st; bytes -= A_STAGE_BYTES; }
+    if (bytes + res_bytes <= GEMM_SMEM_LIMIT) {
+      g.res_tma = 1; g.stages = st;
+      op.i[7] = bytes + res_bytes;
+      op.g = g;
+    }
+  }
   {
     const double Mt = static_cast<double>(g.rows_per_clip) * g.n_clips;
     op.flops = 2.0 * Mt * w.N * (w.K_alg > 0 ? w.K_alg : K);   // algorithmic (the split contraction issues 3-4x the MMAs)
@@ -1140,7 +1157,7 @@ void build_decoder_w(wv_net& n) {
           }
           if (hb) bias[static_cast<size_t>(j) * Ch + n] = hb->data[n];
         }
-      st.up_halve = make_gemm_w(W, rows, r * Ch, 2 * C, true, pick_block_n(r * Ch, 0, STAGED_MAX_BN), bias.data(), r * Ch);
+      st.up_halve = make_gemm_w(W, rows, r * Ch, 2 * C, true, pick_block_n(r * Ch, 0, STAGED_MAX_BN, true), bias.data(), r * Ch);
     }
     for (int j = 0; j < cf.n_residual_dec; ++j)
       st.res.push_back(resblock_w(W, p + "." + std::to_string(i++), j, rs));     // idx=j, seanet.py:1159
