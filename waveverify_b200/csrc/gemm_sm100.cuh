@@ -243,8 +243,9 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
 // two M tiles with the same n tile, u -> (mp, nt), tile = (2*mp + (k&1))*tiles_n + nt; with an odd number of
 // M tiles the second half of the last units does not exist.  With g.reverse the order is walked from the end,
 // so that a kernel starts on the rows the previous kernel of the plan wrote last (still in L2).
+template <bool CG2>
 __device__ __forceinline__ int seq_tile(const GemmArgs& g, int k, bool& done) {
-  if (g.cg2) {
+  if constexpr (CG2) {
     // CTA-pair mode: cluster c = blockIdx.x / 2 walks UNITS u = c + (k>>1) * clusters = (M tile pair mp, wide n tile nw);
     // the CTA of rank r owns M tile 2*mp + r (the last one twice when the count is odd: both CTAs then write the same values)
     // and visits the two block_n-wide halves of the wide n tile in turn: every unit is exactly two tiles of this CTA.
@@ -278,16 +279,18 @@ __device__ __forceinline__ int seq_tile(const GemmArgs& g, int k, bool& done) {
   const int mt = 2 * mp + (k & 1);
   return mt < tiles_m ? mt * g.tiles_n + nt : -1;
 }
+template <bool CG2>
 __device__ __forceinline__ int cta_tile_count(const GemmArgs& g) {
   int n = 0;
   for (int k = 0;; ++k) {
     bool done;
-    const int l = seq_tile(g, k, done);
+    const int l = seq_tile<CG2>(g, k, done);
     if (done) break;
     n += l >= 0;
   }
   return n;
 }
+template <bool CG2>
 struct TileWalker {
   int k, tile, clip, mi, nt;   // tile = physical index, num_tiles when the CTA is done
   __device__ __forceinline__ TileWalker(const GemmArgs& g) : k(-1), tile(0), clip(0), mi(0), nt(0) { next(g); }
@@ -295,7 +298,7 @@ struct TileWalker {
     for (;;) {
       ++k;
       bool done;
-      const int l = seq_tile(g, k, done);
+      const int l = seq_tile<CG2>(g, k, done);
       if (done) { tile = g.num_tiles; return; }
       if (l < 0) continue;
       tile = l;
@@ -389,7 +392,7 @@ __device__ __forceinline__ void staged_unit(const GemmArgs& g, uint32_t srow /*s
 
 // STAGED math warps.  thread = (4-channel group, R-row group): 8-byte smem reads / global accesses
 // keep a warp on contiguous row segments; a thread walks its row groups in passes of 384 threads.
-template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE, bool DUAL = false, bool PRE = false>
+template <int TAPS, int R, bool RES, bool RAW, bool ACT, bool SCALE, bool DUAL = false, bool PRE = false, bool CG2 = false, bool RT = false>
 __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   constexpr int HALO = TAPS - 1;
   constexpr int ROWS_OUT = BM - HALO;
@@ -413,16 +416,16 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
   __half2 wt[TAPS][2], bs[2];
   const bool two = g.math_groups == 2;
   // residual tiles staged by TMA (g.res_tma): buffers behind the staging tiles, barriers in the CTA's barrier block
-  const bool rt = RES && !PRE && g.res_tma != 0;
+  constexpr bool rt = RES && !PRE && RT;   // compile-time: the two residual paths do not share a loop body (registers)
   const int res_tile_bytes = BM * g.block_n * 2;
   const uint32_t res_u32 = ((smem_u32(stage_tiles) + g.stage_bufs * BM * pitch + 127u) & ~127u) + cg * 8;
   uint64_t* res_bars = reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(stage_tiles) - DOWN_W_BYTES - GEMM_BAR_BYTES) + RES_BAR_INDEX;
   int sb = two ? my_grp : 0;
-  const int tiles_cta = cta_tile_count(g);
+  const int tiles_cta = cta_tile_count<CG2>(g);
   int tiles_left = two ? (tiles_cta - my_grp + 1) >> 1 : tiles_cta;   // tiles this group still has to process
   const int keep = two ? 1 : g.stage_bufs;                         // no later drain waits for the last `keep` tiles
   int dbg_it = 0, idx = 0;
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++idx) {
+  for (TileWalker<CG2> tc(g); tc.tile < g.num_tiles; tc.next(g), ++idx) {
     if (two && (idx & 1) != my_grp) continue;
     const int r_base = tc.mi * ROWS_OUT;                           // first OUTPUT row of the tile
     const int c = tc.nt * bn + cg * 4;
@@ -450,7 +453,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     uint2 rres[R], rnext[R];
     const int rbuf = idx & 1;                                      // two groups: == my_grp
     auto load_res = [&](int ro, uint2 (&r)[R]) {
-      if (rt) {                                                    // rows past the clip end are TMA zero fill (and never stored)
+      if constexpr (rt) {                                          // rows past the clip end are TMA zero fill (and never stored)
         const uint32_t a = res_u32 + rbuf * res_tile_bytes + ro * (g.block_n * 2);
 #pragma unroll
         for (int i = 0; i < R; ++i) r[i] = ro + i < BM ? lds_u2(a + i * (g.block_n * 2)) : make_uint2(0u, 0u);
@@ -504,7 +507,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
     if (et_all == 0) WV_DBG(7, dbg_it);                           // warp 0 reaches the hand-off barrier
     named_bar_sync(BAR_ST_FULL + sb, bar_threads);                 // drain warps staged tile sb
     if constexpr (RES) {
-      if (rt) {
+      if constexpr (rt) {
         mbar_wait(&res_bars[rbuf], static_cast<uint32_t>(idx >> 1) & 1u);   // the tile's residual rows landed
         if (have) load_res(grp * R, rres);
       }
@@ -553,7 +556,7 @@ __device__ __forceinline__ void staged_math_loop(const GemmArgs& g, const uint8_
 // A tile holds input rows [mi*OUTS*R - R, +128) and produces OUTS = 128/R - 1 output rows.
 // thread = (4-channel group, output row); taps are staged in shared memory (2R*4 floats per thread
 // would not fit in registers for R = 8).
-template <int R>
+template <int R, bool CG2>
 __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_t* stage_tiles, uint8_t* down_w, int lane) {
   constexpr int OUTS = BM / R - 1;
   const int pitch = staged_pitch_bytes(g.block_n);
@@ -571,18 +574,18 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
   __half2 bs2[2];
   const __half2 s2 = h2_from(s_act, s_act);
   int sb = 0;
-  int tiles_left = cta_tile_count(g);
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+  int tiles_left = cta_tile_count<CG2>(g);
+  for (TileWalker<CG2> tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int c = tc.nt * g.block_n + cg * 4;
     // taps are staged per n tile; CTA-pair mode alternates between the two halves of a wide n tile, so both halves are
     // staged together (keyed by the wide tile) and the bias is re-read (L1) when the half changes
-    const int tap_key = g.cg2 ? (tc.nt >> 1) : tc.nt;
-    const int half = g.cg2 ? (tc.nt & 1) : 0;
+    const int tap_key = CG2 ? (tc.nt >> 1) : tc.nt;
+    const int half = CG2 ? (tc.nt & 1) : 0;
     if (tap_key != cached_nt) {
       cached_nt = tap_key;
       named_bar_sync(BAR_TAPS, P2_THREADS);                           // previous taps no longer read
-      const int n_half = g.cg2 ? 2 : 1;
-      const int nt0 = g.cg2 ? (tc.nt & ~1) : tc.nt;
+      const int n_half = CG2 ? 2 : 1;
+      const int nt0 = CG2 ? (tc.nt & ~1) : tc.nt;
       for (int i = et; i < n_half * 2 * R * cgs; i += P2_THREADS) {
         const int hh = i / (2 * R * cgs), ii = i % (2 * R * cgs);
         const int j = ii / cgs, q = ii % cgs;
@@ -653,14 +656,15 @@ __device__ __forceinline__ void staged_down_loop(const GemmArgs& g, const uint8_
 }
 
 // last_mode math: one thread per output sample of the tile (124 of the 384 math threads).
+template <bool CG2>
 __device__ __forceinline__ void staged_last_loop(const GemmArgs& g, const uint8_t* stage_tiles) {
   constexpr int ROWS_OUT = BM - 4;
   const int pitch = staged_pitch_bytes(g.block_n);
   const int et = threadIdx.x - (128 + P1_WARPS * 32);
   const uint32_t stage_u32 = smem_u32(stage_tiles);
   int sb = 0;
-  int tiles_left = cta_tile_count(g);
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+  int tiles_left = cta_tile_count<CG2>(g);
+  for (TileWalker<CG2> tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     named_bar_sync(BAR_ST_FULL + sb, EPI_THREADS);
     const int t = tc.mi * ROWS_OUT + et;
     if (et < ROWS_OUT && t < g.last_T) {
@@ -683,12 +687,17 @@ __device__ __forceinline__ void staged_last_loop(const GemmArgs& g, const uint8_
   }
 }
 
-template <int TAPS, int R>
+template <int TAPS, int R, bool CG2>
 __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   const bool res = g.residual != nullptr, raw = g.out_raw != nullptr, act = g.out_act != nullptr;
   const bool scale = act && g.act_scale != 1.f;
-#define WV_MATH(RS, W, A, S) staged_math_loop<TAPS, R, RS, W, A, S>(g, stage_tiles, lane)
-  if (res) {
+#define WV_MATH(RS, W, A, S) staged_math_loop<TAPS, R, RS, W, A, S, false, false, CG2>(g, stage_tiles, lane)
+#define WV_MATH_RT(W, A, S) staged_math_loop<TAPS, R, true, W, A, S, false, false, CG2, true>(g, stage_tiles, lane)
+  if (res && g.res_tma) {   // residual tile staged in shared memory by warp 3
+    if (raw && act) { if (scale) WV_MATH_RT(true, true, true); else WV_MATH_RT(true, true, false); }
+    else if (raw) WV_MATH_RT(true, false, false);
+    else { if (scale) WV_MATH_RT(false, true, true); else WV_MATH_RT(false, true, false); }
+  } else if (res) {
     if (raw && act) { if (scale) WV_MATH(true, true, true, true); else WV_MATH(true, true, true, false); }
     else if (raw) WV_MATH(true, true, false, false);
     else { if (scale) WV_MATH(true, false, true, true); else WV_MATH(true, false, true, false); }
@@ -698,13 +707,14 @@ __device__ __forceinline__ void staged_math_dispatch(const GemmArgs& g, const ui
     else { if (scale) WV_MATH(false, false, true, true); else WV_MATH(false, false, true, false); }
   }
 #undef WV_MATH
+#undef WV_MATH_RT
 }
-template <int TAPS>
+template <int TAPS, bool CG2>
 __device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_t* stage_tiles, int lane) {
   if constexpr (TAPS == 5) {
     if (g.pre_w != nullptr) {   // first encoder resblock: residual recomputed from the waveform (conv_pre)
       const bool sc = g.act_scale != 1.f;
-#define WV_PRE(RR, RAWO, SC, DU) staged_math_loop<5, RR, true, RAWO, true, SC, DU, true>(g, stage_tiles, lane)
+#define WV_PRE(RR, RAWO, SC, DU) staged_math_loop<5, RR, true, RAWO, true, SC, DU, true, CG2>(g, stage_tiles, lane)
       if (g.dual) {             // single-resblock stages (Locator): the same launch also carries the spectrogram 1x1
         if (g.unit_rows == 6) { if (sc) WV_PRE(6, false, true, true); else WV_PRE(6, false, false, true); }
         else { if (sc) WV_PRE(4, false, true, true); else WV_PRE(4, false, false, true); }
@@ -717,19 +727,19 @@ __device__ __forceinline__ void staged_math_rows(const GemmArgs& g, const uint8_
     }
     if (g.dual) {   // last encoder resblock + spectrogram 1x1: residual in, activated output only
       if (g.unit_rows == 6) {
-        if (g.act_scale != 1.f) staged_math_loop<5, 6, true, false, true, true, true>(g, stage_tiles, lane);
-        else staged_math_loop<5, 6, true, false, true, false, true>(g, stage_tiles, lane);
+        if (g.act_scale != 1.f) staged_math_loop<5, 6, true, false, true, true, true, false, CG2>(g, stage_tiles, lane);
+        else staged_math_loop<5, 6, true, false, true, false, true, false, CG2>(g, stage_tiles, lane);
       } else {
-        if (g.act_scale != 1.f) staged_math_loop<5, 4, true, false, true, true, true>(g, stage_tiles, lane);
-        else staged_math_loop<5, 4, true, false, true, false, true>(g, stage_tiles, lane);
+        if (g.act_scale != 1.f) staged_math_loop<5, 4, true, false, true, true, true, false, CG2>(g, stage_tiles, lane);
+        else staged_math_loop<5, 4, true, false, true, false, true, false, CG2>(g, stage_tiles, lane);
       }
       return;
     }
   }
   // 6- and 8-row units were measured slower at 96 columns (16 row groups per pass: 4-row units already fill two
   // passes); at 64 columns (24 row groups per pass) 4-row units leave the second pass 7/24 occupied
-  if (g.unit_rows == 6) staged_math_dispatch<TAPS, 6>(g, stage_tiles, lane);
-  else staged_math_dispatch<TAPS, 4>(g, stage_tiles, lane);
+  if (g.unit_rows == 6) staged_math_dispatch<TAPS, 6, CG2>(g, stage_tiles, lane);
+  else staged_math_dispatch<TAPS, 4, CG2>(g, stage_tiles, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -770,8 +780,8 @@ __device__ __forceinline__ void pm_math_loop(const GemmArgs& g, const uint8_t* s
   int cached_nt = -1;
   float4 wt[TAPS], bs = make_float4(0.f, 0.f, 0.f, 0.f);
   int sb = 0;
-  int tiles_left = cta_tile_count(g);
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+  int tiles_left = cta_tile_count<false>(g);
+  for (TileWalker<false> tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int r_base = tc.mi * ROWS_OUT;
     const int c = tc.nt * g.block_n + cg * 4;
     if (active && tc.nt != cached_nt) {
@@ -856,8 +866,8 @@ __device__ __forceinline__ void pm_down_loop(const GemmArgs& g, const uint8_t* s
   int cached_nt = -1;
   float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
   int sb = 0;
-  int tiles_left = cta_tile_count(g);
-  for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g)) {
+  int tiles_left = cta_tile_count<false>(g);
+  for (TileWalker<false> tc(g); tc.tile < g.num_tiles; tc.next(g)) {
     const int c = tc.nt * g.block_n + cg * 4;
     if (tc.nt != cached_nt) {
       cached_nt = tc.nt;
@@ -963,7 +973,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < MAX_ACC_STAGES; ++i) {
       mbar_init(&acc_full[i], 1);
       // one arrive per draining warp (CTA-pair mode: the leader's barrier also collects the peer's drain warps)
-      mbar_init(&acc_empty[i], STG ? (g.cg2 ? 2 * P1_WARPS : P1_WARPS) : (IS_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));
+      mbar_init(&acc_empty[i], STG ? (CG2 ? 2 * P1_WARPS : P1_WARPS) : (IS_STFT && g.epi_groups > 1 ? EPI_WARPS / g.epi_groups : EPI_WARPS));
     }
     fence_mbar_init();
   }
@@ -990,7 +1000,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint64_t pol = l2_policy_evict_first();
       if (g.resident_b) {   // the n tile of a CTA is fixed (grid is a multiple of tiles_n): load W once
         bool d0;
-        const int n_fixed = tile_coord(g, seq_tile(g, 0, d0)).nt * g.block_n;
+        const int n_fixed = tile_coord(g, seq_tile<CG2>(g, 0, d0)).nt * g.block_n;
         mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(num_kb * b_stage_bytes));
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smemB + kb * b_stage_bytes, &tmB, w_full, kb * BK, n_fixed);
       }
@@ -1001,7 +1011,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t pair_bytes = 2u * static_cast<uint32_t>(A_STAGE_BYTES + b_stage_bytes);
         for (int ku = 0;; ++ku) {
           bool done;
-          const int l0 = seq_tile(g, 2 * ku, done);
+          const int l0 = seq_tile<CG2>(g, 2 * ku, done);
           if (done) break;
           const TileCoord t0 = tile_coord(g, l0);
           const int r0 = t0.mi * rows_out - halo;
@@ -1019,9 +1029,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // one ring stage = the k-block of TWO M tiles (same n tile) + the W k-block they share
         for (int ku = 0;; ++ku) {
           bool done, d1;
-          const int l0 = seq_tile(g, 2 * ku, done);
+          const int l0 = seq_tile<CG2>(g, 2 * ku, done);
           if (done) break;
-          const int l1 = seq_tile(g, 2 * ku + 1, d1);
+          const int l1 = seq_tile<CG2>(g, 2 * ku + 1, d1);
           const TileCoord t0 = tile_coord(g, l0);
           const TileCoord t1 = l1 >= 0 ? tile_coord(g, l1) : t0;
           const int ra = t0.mi * rows_out - halo, rb = t1.mi * rows_out - halo;
@@ -1041,9 +1051,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else
       {
-      TileWalker pf(g);
+      TileWalker<CG2> pf(g);
       for (int i = 0; i < g.a_prefetch && pf.tile < g.num_tiles; ++i) pf.next(g);
-      for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++dbg_it) {
+      for (TileWalker<CG2> tc(g); tc.tile < g.num_tiles; tc.next(g), ++dbg_it) {
         if (g.a_prefetch > 0 && pf.tile < g.num_tiles) {
           const int pr0 = pf.mi * rows_out - halo;
           if (pf.nt == 0 && pr0 >= 0 && g.phases <= 1) {
@@ -1092,7 +1102,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if ((blockIdx.x & 1) == 0) {                 // the even CTA issues for the pair; commits arrive in both CTAs
           for (int ku = 0;; ++ku) {
             bool done;
-            seq_tile(g, 2 * ku, done);
+            seq_tile<CG2>(g, 2 * ku, done);
             if (done) break;
             mbar_wait(&acc_empty[as], as_phase ^ 1);
             tc_fence_after();
@@ -1115,9 +1125,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int c = 0;                                   // tiles issued so far: accumulator stage c % acc_stages
         for (int ku = 0;; ++ku) {
           bool done, d1;
-          seq_tile(g, 2 * ku, done);
+          seq_tile<CG2>(g, 2 * ku, done);
           if (done) break;
-          const int nv = seq_tile(g, 2 * ku + 1, d1) >= 0 ? 2 : 1;
+          const int nv = seq_tile<CG2>(g, 2 * ku + 1, d1) >= 0 ? 2 : 1;
           const int s0 = c % acc_stages, s1 = (c + 1) % acc_stages;
           mbar_wait(&acc_empty[s0], ((c / acc_stages) & 1) ^ 1);
           if (nv == 2) mbar_wait(&acc_empty[s1], (((c + 1) / acc_stages) & 1) ^ 1);
@@ -1147,7 +1157,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } else
       for (int k_ = 0;; ++k_, ++dbg_it) {
         bool done;
-        const int l_ = seq_tile(g, k_, done);
+        const int l_ = seq_tile<CG2>(g, k_, done);
         if (done) break;
         if (l_ < 0) continue;
         mbar_wait(&acc_empty[as], as_phase ^ 1);
@@ -1180,7 +1190,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint8_t* res_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stage_tiles + g.stage_bufs * BM * pitch_) + 127) & ~static_cast<uintptr_t>(127));
         const uint32_t bytes = static_cast<uint32_t>(BM * g.block_n * 2);
         int i = 0;
-        for (TileWalker tc(g); tc.tile < g.num_tiles; tc.next(g), ++i) {
+        for (TileWalker<CG2> tc(g); tc.tile < g.num_tiles; tc.next(g), ++i) {
           const int buf = i & 1;
           mbar_wait(&bars[RES_BAR_INDEX + 2 + buf], (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&bars[RES_BAR_INDEX + buf], bytes);
@@ -1201,11 +1211,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t v[32];
       for (int k_ = 0;; ++k_) {
         bool done;
-        const int l_ = seq_tile(g, k_, done);
+        const int l_ = seq_tile<CG2>(g, k_, done);
         if (done) break;
         if (l_ < 0) continue;
         if (it >= g.stage_bufs) named_bar_sync(BAR_ST_EMPTY + sb, drain_bar_threads);   // math warps left tile sb
-        const int sub = g.cg2 ? (it & 1) : 0;        // CTA-pair mode: the accumulator holds two block_n-wide tiles
+        const int sub = CG2 ? (it & 1) : 0;        // CTA-pair mode: the accumulator holds two block_n-wide tiles
         if (sub == 0) mbar_wait(&acc_full[as], as_phase);
         if (q == 0 && lane == 0) WV_DBG(3, it);
         if (lane == 0) WV_DBG(36 + q, it);           // per drain warp: start
@@ -1236,7 +1246,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (!g.cg2) {
+        if constexpr (!CG2) {
           if (lane == 0) mbar_arrive(&acc_empty[as]);   // TMEM stage free: the MMAs of tile i+2 may start
         } else if (sub == 1) {
           if (lane == 0) mbar_arrive_leader(&acc_empty[as]);   // both halves drained: tell the issuing CTA
@@ -1244,7 +1254,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (q == 0 && lane == 0) WV_DBG(4, it);
         if (lane == 0) WV_DBG(8 + q, it);            // per drain warp: end
         named_bar_arrive(BAR_ST_FULL + sb, drain_bar_threads);   // release: this warp's 32 rows are staged
-        if (!g.cg2 || sub == 1) { if (++as == acc_stages) { as = 0; as_phase ^= 1; } }
+        if (!CG2 || sub == 1) { if (++as == acc_stages) { as = 0; as_phase ^= 1; } }
         if (++sb == g.stage_bufs) sb = 0;
         ++it;
       }
@@ -1263,16 +1273,16 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         else pm_math_loop<1>(g, stage_tiles);
       } else
       if (g.last_mode) {
-        staged_last_loop(g, stage_tiles);
+        staged_last_loop<CG2>(g, stage_tiles);
       } else if (g.down_r > 0) {
         switch (g.down_r) {
-          case 2: staged_down_loop<2>(g, stage_tiles, down_w, lane); break;
-          case 4: staged_down_loop<4>(g, stage_tiles, down_w, lane); break;
-          case 5: staged_down_loop<5>(g, stage_tiles, down_w, lane); break;
-          default: staged_down_loop<8>(g, stage_tiles, down_w, lane); break;
+          case 2: staged_down_loop<2, CG2>(g, stage_tiles, down_w, lane); break;
+          case 4: staged_down_loop<4, CG2>(g, stage_tiles, down_w, lane); break;
+          case 5: staged_down_loop<5, CG2>(g, stage_tiles, down_w, lane); break;
+          default: staged_down_loop<8, CG2>(g, stage_tiles, down_w, lane); break;
         }
-      } else if (g.taps == 5) staged_math_rows<5>(g, stage_tiles, lane);
-      else staged_math_rows<1>(g, stage_tiles, lane);
+      } else if (g.taps == 5) staged_math_rows<5, CG2>(g, stage_tiles, lane);
+      else staged_math_rows<1, CG2>(g, stage_tiles, lane);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (16 warps)
@@ -1290,7 +1300,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t as_phase = 0;
     for (int k_ = 0;; ++k_) {
       bool done;
-      const int l_ = seq_tile(g, k_, done);
+      const int l_ = seq_tile<CG2>(g, k_, done);
       if (done) break;
       if (l_ < 0) continue;
       if (two_groups && as != grp) {                     // another group's tile (acc_stages == epi_groups: stage = tile index mod groups)
