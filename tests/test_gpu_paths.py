@@ -59,7 +59,9 @@ def test_knob_paths_agree(tmp_path):
     # bit-identical alternatives: math-warp organisation and residual recomputation do not change any arithmetic
     for name, env in (("groups1", {"WV_MATH_GROUPS": "1"}), ("groups2", {"WV_MATH_GROUPS": "2"}),
                       ("rows4", {"WV_ROWS6_BN": "0"}), ("pre", {"WV_PRE_FUSE": "1"}), ("prefetch", {"WV_A_PREFETCH": "4"}),
-                      ("res_late", {"WV_RES_EARLY2": "0"}), ("epi4", {"WV_EPI_GROUPS": "4"}), ("res1", {"WV_RES1_KB": "128"})):
+                      ("res_late", {"WV_RES_EARLY2": "0"}), ("epi4", {"WV_EPI_GROUPS": "4"}), ("res1", {"WV_RES1_KB": "128"}),
+                      ("res_ldg", {"WV_RES_TMA": "0"}), ("res_tma3", {"WV_RES_TMA_MIN_STAGES": "3"}),
+                      ("no_cta_pairs", {"WV_CG2_MIN_KB": "0", "WV_CG2_BN96": "0"}), ("no_graph", {"WV_GRAPH_MAX_SAMPLES": "0"})):
         alt = run(tmp_path, name, env)
         for k in base:
             assert np.array_equal(base[k], alt[k]), f"{name}: {k} differs"
@@ -74,3 +76,31 @@ def test_knob_paths_agree(tmp_path):
         assert np.abs(base["avg"] - alt["avg"]).max() <= 2e-4, name
         safe = np.abs(base["avg"] - 0.5) > 3e-4
         assert (base["bits"] == alt["bits"])[safe].all(), name
+
+
+def test_cta_pair_path_agrees_at_a_size_where_it_is_selected(tmp_path):
+    """The CTA-pair launches need >= 2 tile pairs per SM pair: 48 x 1 s selects them for the deep stages.  Same arithmetic
+    per element (only the tile shapes change): the Generator's output is bit-identical with the mode switched off."""
+    script = r"""
+import sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+from helpers import BASE_KW, fixture_weights
+from waveverify_b200 import Generator
+c, sd = fixture_weights("generator", False, 5)
+m = Generator(**{**BASE_KW["generator"], "bias": True, "zero_init": False}); m.load_state_dict(sd); m = m.cuda()
+rng = np.random.RandomState(12)
+x = torch.from_numpy(0.1 * rng.standard_normal((48, 1, 16000)).astype(np.float32)).cuda()
+msg = torch.from_numpy(rng.randint(0, 2, (48, 16)).astype(np.float32)).cuda()
+wm, y, _ = m.embed_batch(x, msg)
+torch.cuda.synchronize()
+np.savez(sys.argv[1], wm=wm.cpu().numpy())
+"""
+    outs = {}
+    for name, env in (("on", {}), ("off", {"WV_CG2_MIN_KB": "0", "WV_CG2_BN96": "0"})):
+        out = str(tmp_path / f"cg2_{name}.npz")
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([sys.executable, "-c", f"ROOT={ROOT!r}\n" + script, out], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[name] = np.load(out)["wm"]
+    assert np.array_equal(outs["on"], outs["off"])
