@@ -214,13 +214,14 @@ SURVEY_IO_BYTES = 1.28e6      # embed 8 B/sample + detect/locate with fp32 logit
 
 
 def build_id():
-    """sha256 prefix of the shared library the run loaded: stamps the ncu summaries so that staleness is visible."""
+    """sha256 prefix of the CUDA sources the shared library is built from (waveverify_b200/build.py DEPS): stamps the ncu
+    summaries so that staleness is visible.  (The binary itself is not bit-reproducible: nvcc embeds a fresh id per build.)"""
     import hashlib
-    from waveverify_b200 import _lib
+    from waveverify_b200 import build as b
     h = hashlib.sha256()
-    with open(_lib.LIB_PATH, "rb") as f:
-        for blk in iter(lambda: f.read(1 << 20), b""):
-            h.update(blk)
+    for path in sorted(b.DEPS):
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode() + b"\0" + f.read())
     return h.hexdigest()[:12]
 
 

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 tag = sys.argv[1]
-bid = open(f"gpurun_out/build_id_{tag}.txt").read().strip()
+bid = open(f"gpurun_out/build_id_{tag}.txt").read().strip()   # bench.build_id(): hash of the CUDA sources
 subprocess.run([sys.executable, "scripts/ncu_summarize.py", f"gpurun_out/launches_{tag}.csv", "--md", "profiles/r02_launches_64x1s.md",
                 "--traffic-json", "profiles/ncu_traffic.json", "--build-id", bid], check=True, stdout=subprocess.DEVNULL)
 shutil.copy(f"gpurun_out/launches_{tag}.csv", "profiles/r02_launches_64x1s.csv")
