@@ -203,7 +203,7 @@ def test_validation_pipeline_runs_and_counts():
         assert r["mask"].shape == r["locator_mask"].shape
 
 
-def test_fir_effects_against_oracle():
+def test_fir_effects_within_2e_6_of_the_published_julius_algorithm():
     """julius low / high / band-pass (parity unpinned: julius is absent; oracle = its published algorithm in
     float64).  Tolerance: fp32 accumulation of <= 129 taps, |x| <= 0.5 -> 2e-6 absolute."""
     sr = 16000
