@@ -535,17 +535,27 @@ def metric_counters(bits: torch.Tensor, valid: Optional[torch.Tensor], msg: torc
     dev = bits.device if bits is not None else pred_mask.device
     if counters is None:
         counters = torch.zeros(6, dtype=torch.int64, device=dev)
+
+    def as_u8(t):
+        """uint8 view of a flag tensor; the kernel treats any non-zero byte as set, so uint8 / bool inputs are passed as they are"""
+        t = t.to(dev)
+        if t.dtype == torch.bool:
+            t = t.view(torch.uint8)
+        elif t.dtype != torch.uint8:
+            t = (t != 0).to(torch.uint8)
+        return t.contiguous()
+
     b8 = v8 = m8 = p8 = g8 = None
     B = nb = 0
     if bits is not None:
-        b8 = bits.to(torch.uint8).contiguous()
+        b8 = as_u8(bits)
         B, nb = b8.shape
-        m8 = (msg.to(dev) != 0).to(torch.uint8).contiguous()
-        v8 = valid.to(torch.uint8).contiguous() if valid is not None else None
+        m8 = as_u8(msg)
+        v8 = as_u8(valid) if valid is not None else None
     n_mask = 0
     if pred_mask is not None:
-        p8 = (pred_mask != 0).to(torch.uint8).contiguous()
-        g8 = (gt_mask.to(dev) != 0).to(torch.uint8).contiguous()
+        p8 = as_u8(pred_mask)
+        g8 = as_u8(gt_mask)
         if p8.numel() != g8.numel():
             raise ValueError(f"Shape mismatch: predicted={tuple(p8.shape)}, ground_truth={tuple(g8.shape)}")
         n_mask = p8.numel()
