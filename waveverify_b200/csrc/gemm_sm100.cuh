@@ -213,8 +213,9 @@ __device__ __forceinline__ void reg_alloc() {
 // can be re-acquired): the TMA / MMA warpgroup drops to 40, the drain warpgroup keeps 96, the
 // twelve math warps grow to 112:  128*40 + 128*96 + 384*112 = 60416 <= 61440.
 constexpr int REGS_LIGHT = 40;
-constexpr int REGS_MATH = 112;
-static_assert(128 * REGS_LIGHT + 128 * 96 + P2_THREADS * REGS_MATH <= STAGED_THREADS * 96,
+constexpr int REGS_DRAIN = 80;     // the drain warps hold one 32-register TMEM chunk: what they give back goes to the math warps
+constexpr int REGS_MATH = 120;
+static_assert(128 * REGS_LIGHT + 128 * REGS_DRAIN + P2_THREADS * REGS_MATH <= STAGED_THREADS * 96,
               "setmaxnreg budget exceeds the CTA's launch allocation");
 
 // q = x / d, r = x % d with a host-computed magic = floor(2^32 / d): one mul.hi + one fix-up.
@@ -1203,6 +1204,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int chunks = g.block_n / 32;
     if (warp < 4 + P1_WARPS) {
       // ---------------------------------------------------------- drain warps: TMEM -> fp16 -> smem
+      reg_dealloc<REGS_DRAIN>();
       const int q = warp - 4;   // == warp % 4: TMEM lane quarter this warp may touch
       const int drain_bar_threads = P1_WARPS * 32 + (g.math_groups == 2 ? P2_THREADS / 2 : P2_THREADS);
       const uint32_t stage_u32 = smem_u32(stage_tiles);

@@ -284,6 +284,7 @@ resblock_sm100_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
     }
   } else if (warp >= 4 && warp < 4 + P1_WARPS) {
+    reg_dealloc<REGS_DRAIN>();                       // (the math warps' 120 registers come out of this warpgroup's share)
     // ------------------------------------------------------------ drain warps: TMEM -> fp16 -> staging[slot]
     const int q = warp - 4;
     const int chunks = g.C / 32;
