@@ -46,7 +46,7 @@ tensor pipe at 57 - 63 % of peak, against 8 - 19 % for the DRAM-bound wide layer
 The wide layers move their algorithmic bytes once (second halves: 786 MB of in + out tensors against the measured DRAM bytes in
 the table); with the residual tile staged by TMA their `barrier` share fell from 38 - 40 % (build de4d640d1818, per-thread
 residual loads: `dec.u3.r0.out` 161.6 us, `dec.u2.r0.out` 168.4 us) to about 20 %.  All launches run at 96 registers per thread
-at launch (640 threads x 96 = 61 440; `setmaxnreg` redistributes: 40 / 96 / 112).
+at launch (640 threads x 96 = 61 440; `setmaxnreg` redistributes: 40 / 80 / 120).
 
 Launch list of the same build (`profiles/r02_launches_64x1s.md`, `ncu --metrics gpu__time_duration.sum,dram__bytes_*`):
 {tj['_device_time_us_per_step_ncu']:.0f} us serialised, {tj['_dram_bytes_per_step'] / 1e9:.1f} GB of DRAM traffic per step

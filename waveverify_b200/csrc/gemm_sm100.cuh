@@ -210,8 +210,8 @@ __device__ __forceinline__ void reg_alloc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 // 640 threads x 96 registers at launch = 61440 (only registers released by this CTA's own warps
-// can be re-acquired): the TMA / MMA warpgroup drops to 40, the drain warpgroup keeps 96, the
-// twelve math warps grow to 112:  128*40 + 128*96 + 384*112 = 60416 <= 61440.
+// can be re-acquired): the TMA / MMA warpgroup drops to 40, the drain warpgroup drops to 80, the
+// twelve math warps grow to 120:  128*40 + 128*80 + 384*120 = 61440.
 constexpr int REGS_LIGHT = 40;
 constexpr int REGS_DRAIN = 80;     // the drain warps hold one 32-register TMEM chunk: what they give back goes to the math warps
 constexpr int REGS_MATH = 120;
